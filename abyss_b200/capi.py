@@ -1,0 +1,261 @@
+"""ctypes binding of libabyssb200.so (the C ABI in include/abyss_b200.h).
+
+This is the stub a maintainer of a Python harness would write; the C++ CLI links the same
+library directly.  There is deliberately no fallback: if the CUDA library is missing the
+import raises, and if no GPU is present every compute call fails with ABB_ENODEV.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libabyssb200.so")
+
+ABB_OK, ABB_EINVAL, ABB_ENODEV, ABB_ECUDA, ABB_ENOMEM, ABB_ESTATE = 0, -1, -2, -3, -4, -5
+COUNTING, BIT, CASCADING = 0, 1, 2
+
+
+class AbbError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libabyssb200 error {code}: {msg}")
+        self.code = code
+
+
+class InsertStats(C.Structure):
+    _fields_ = [("kmers", C.c_uint64), ("slots", C.c_uint64), ("windows", C.c_uint64),
+                ("deferred", C.c_uint64), ("launches", C.c_uint64),
+                ("ms_hash", C.c_float), ("ms_insert", C.c_float)]
+
+
+class Contig(C.Structure):
+    _fields_ = [("seed_read", C.c_uint64), ("seq_offset", C.c_uint64),
+                ("length", C.c_uint32), ("coverage", C.c_uint32)]
+
+
+class AssemblyParams(C.Structure):
+    _fields_ = [("trim", C.c_uint), ("verbose", C.c_uint)]
+
+
+class AssemblyCounters(C.Structure):
+    _fields_ = [("solid_reads", C.c_uint64), ("visited_reads", C.c_uint64),
+                ("reads_processed", C.c_uint64), ("bases_assembled", C.c_uint64),
+                ("contig_id", C.c_uint64)]
+
+
+_u64p = C.POINTER(C.c_uint64)
+_u8p = C.POINTER(C.c_uint8)
+_vp = C.c_void_p
+
+# name -> (restype, argtypes); every symbol declared in include/abyss_b200.h
+SIGNATURES = {
+    "abb_version": (C.c_int, []),
+    "abb_last_error": (C.c_char_p, []),
+    "abb_device_count": (C.c_int, []),
+    "abb_filter_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_uint64, C.c_uint, C.c_uint, C.c_uint, C.c_char_p, C.c_int]),
+    "abb_filter_destroy": (C.c_int, [_vp]),
+    "abb_filter_kmer_size": (C.c_uint, [_vp]),
+    "abb_filter_hash_num": (C.c_uint, [_vp]),
+    "abb_filter_size": (C.c_uint64, [_vp]),
+    "abb_filter_size_in_bytes": (C.c_uint64, [_vp]),
+    "abb_filter_threshold": (C.c_uint, [_vp]),
+    "abb_filter_levels": (C.c_uint, [_vp]),
+    "abb_filter_set_threshold": (C.c_int, [_vp, C.c_uint]),
+    "abb_insert_reads": (C.c_int, [_vp, _vp, _vp, C.c_uint64, _u64p]),
+    "abb_insert_reads_dev": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint64, _u64p]),
+    "abb_insert_hashes": (C.c_int, [_vp, _vp, C.c_uint64]),
+    "abb_contains_hashes": (C.c_int, [_vp, _vp, C.c_uint64, _vp]),
+    "abb_mincount_hashes": (C.c_int, [_vp, _vp, C.c_uint64, _vp]),
+    "abb_hash_reads": (C.c_int, [C.c_uint, C.c_char_p, _vp, _vp, C.c_uint64, _vp, _vp, _u64p, C.c_int]),
+    "abb_filter_download": (C.c_int, [_vp, C.c_int, _vp, C.c_uint64]),
+    "abb_filter_upload": (C.c_int, [_vp, C.c_int, _vp, C.c_uint64]),
+    "abb_filter_clear": (C.c_int, [_vp]),
+    "abb_filter_popcount": (C.c_int, [_vp, _u64p, _u64p]),
+    "abb_assembler_create": (C.c_int, [C.POINTER(_vp), _vp, C.POINTER(AssemblyParams)]),
+    "abb_assembler_destroy": (C.c_int, [_vp]),
+    "abb_assembler_process_reads": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.POINTER(C.POINTER(Contig)), _u64p, C.POINTER(C.c_char_p)]),
+    "abb_assembler_counters": (C.c_int, [_vp, C.POINTER(AssemblyCounters)]),
+    "abb_assembler_read_results": (C.c_int, [_vp, C.POINTER(_u8p), _u64p]),
+    "abb_assembler_assembled_filter": (_vp, [_vp]),
+    "abb_filter_insert_stats": (C.c_int, [_vp, C.POINTER(InsertStats), C.c_int]),
+    "abb_filter_set_window": (C.c_int, [_vp, C.c_uint64]),
+}
+
+_lib = None
+
+
+def load(path: str | None = None) -> C.CDLL:
+    """Load the CUDA library; raises (no fallback) when it has not been built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise ImportError(f"{p} not found: build it with `python -m abyss_b200.build` "
+                          "(libabyssb200 is CUDA-only, there is no CPU fallback)")
+    lib = C.CDLL(p)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export it
+        fn.restype = res
+        fn.argtypes = args
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != ABB_OK:
+        raise AbbError(rc, load().abb_last_error().decode(errors="replace"))
+
+
+def pack_reads(seqs) -> tuple[np.ndarray, np.ndarray]:
+    """list of str/bytes -> (bases uint8[], offsets uint64[n+1])"""
+    bs = [s.encode() if isinstance(s, str) else bytes(s) for s in seqs]
+    offs = np.zeros(len(bs) + 1, dtype=np.uint64)
+    if bs:
+        offs[1:] = np.cumsum([len(b) for b in bs], dtype=np.uint64)
+    bases = np.frombuffer(b"".join(bs), dtype=np.uint8).copy() if bs else np.zeros(0, dtype=np.uint8)
+    return bases, offs
+
+
+def fixed_length_reads(ascii_2d: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
+    """(n, L) uint8 array of ASCII bases -> (bases, offsets) without copying per read"""
+    n, L = ascii_2d.shape
+    return np.ascontiguousarray(ascii_2d).reshape(-1), (np.arange(n + 1, dtype=np.uint64) * np.uint64(L))
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(_vp)
+
+
+def hash_reads(k: int, seqs_or_arrays, mask: str = "", device: int = 0):
+    """RollingHashIterator over a batch: returns (h0[slots], valid[slots], slot_offsets[n+1])."""
+    lib = load()
+    bases, offs = seqs_or_arrays if isinstance(seqs_or_arrays, tuple) else pack_reads(seqs_or_arrays)
+    lens = np.diff(offs).astype(np.int64)
+    counts = np.maximum(lens - k + 1, 0).astype(np.uint64)
+    slot_offs = np.zeros(len(counts) + 1, dtype=np.uint64)
+    slot_offs[1:] = np.cumsum(counts, dtype=np.uint64)
+    total = int(slot_offs[-1])
+    h0 = np.zeros(total, dtype=np.uint64)
+    valid = np.zeros(total, dtype=np.uint8)
+    n_slots = C.c_uint64(0)
+    check(lib.abb_hash_reads(k, mask.encode(), _ptr(bases), _ptr(offs), len(offs) - 1, _ptr(h0), _ptr(valid),
+                             C.byref(n_slots), device))
+    assert n_slots.value == total, (n_slots.value, total)
+    return h0, valid, slot_offs
+
+
+class Filter:
+    """Host mirror of the reference's Bloom filter classes over a device-resident array.
+
+    kind COUNTING  ~ CountingBloomFilter<uint8_t>(size, H, k, threshold)  (CountingBloomFilter.hpp:31-50)
+    kind BIT       ~ BloomFilter(size_bits, H, k)                          (BloomFilter.hpp:64-74)
+    kind CASCADING ~ HashAgnosticCascadingBloom(size_bits, H, levels, k)   (HashAgnosticCascadingBloom.h:43-55)
+    """
+
+    def __init__(self, kind: int, size: int, num_hashes: int, k: int, arg: int = 0, mask: str = "", device: int = 0):
+        self._lib = load()
+        self._h = _vp()
+        check(self._lib.abb_filter_create(C.byref(self._h), kind, size, num_hashes, k, arg, mask.encode(), device))
+        self.kind = kind
+
+    @classmethod
+    def counting(cls, counters, num_hashes, k, threshold=0, mask="", device=0):
+        return cls(COUNTING, counters, num_hashes, k, threshold, mask, device)
+
+    @classmethod
+    def bits(cls, size_bits, num_hashes, k, mask="", device=0):
+        return cls(BIT, size_bits, num_hashes, k, 0, mask, device)
+
+    @classmethod
+    def cascading(cls, size_bits, num_hashes, levels, k, mask="", device=0):
+        return cls(CASCADING, size_bits, num_hashes, k, levels, mask, device)
+
+    # -- reference getters
+    def getKmerSize(self): return self._lib.abb_filter_kmer_size(self._h)
+    def getHashNum(self): return self._lib.abb_filter_hash_num(self._h)
+    def size(self): return self._lib.abb_filter_size(self._h)
+    def sizeInBytes(self): return self._lib.abb_filter_size_in_bytes(self._h)
+    def threshold(self): return self._lib.abb_filter_threshold(self._h)
+    def levels(self): return self._lib.abb_filter_levels(self._h)
+    def set_threshold(self, t): check(self._lib.abb_filter_set_threshold(self._h, t))
+    def set_window(self, w): check(self._lib.abb_filter_set_window(self._h, w))
+
+    @property
+    def handle(self):
+        return self._h
+
+    def close(self):
+        if self._h:
+            self._lib.abb_filter_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- pass 1
+    def insert_reads(self, seqs_or_arrays) -> int:
+        bases, offs = seqs_or_arrays if isinstance(seqs_or_arrays, tuple) else pack_reads(seqs_or_arrays)
+        n = C.c_uint64(0)
+        check(self._lib.abb_insert_reads(self._h, _ptr(bases), _ptr(offs), len(offs) - 1, C.byref(n)))
+        return n.value
+
+    def insert_reads_dev(self, d_bases_ptr: int, d_offs_ptr: int, n_reads: int, n_bases: int) -> int:
+        n = C.c_uint64(0)
+        check(self._lib.abb_insert_reads_dev(self._h, _vp(d_bases_ptr), _vp(d_offs_ptr), n_reads, n_bases, C.byref(n)))
+        return n.value
+
+    # -- literal hash interface
+    def _hashes(self, hashes):
+        h = np.ascontiguousarray(hashes, dtype=np.uint64).reshape(-1, self.getHashNum())
+        return h, h.shape[0]
+
+    def insert(self, hashes):
+        h, n = self._hashes(hashes)
+        check(self._lib.abb_insert_hashes(self._h, _ptr(h), n))
+
+    def contains(self, hashes) -> np.ndarray:
+        h, n = self._hashes(hashes)
+        out = np.zeros(n, dtype=np.uint8)
+        check(self._lib.abb_contains_hashes(self._h, _ptr(h), n, _ptr(out)))
+        return out.astype(bool)
+
+    def minCount(self, hashes) -> np.ndarray:
+        h, n = self._hashes(hashes)
+        out = np.zeros(n, dtype=np.uint8)
+        check(self._lib.abb_mincount_hashes(self._h, _ptr(h), n, _ptr(out)))
+        return out
+
+    # -- raw array
+    def download(self, level: int = -1) -> np.ndarray:
+        out = np.empty(self.sizeInBytes(), dtype=np.uint8)
+        check(self._lib.abb_filter_download(self._h, level, _ptr(out), out.size))
+        return out
+
+    def upload(self, data: np.ndarray, level: int = -1):
+        d = np.ascontiguousarray(data, dtype=np.uint8)
+        check(self._lib.abb_filter_upload(self._h, level, _ptr(d), d.size))
+
+    def clear(self):
+        check(self._lib.abb_filter_clear(self._h))
+
+    def popcounts(self) -> tuple[int, int]:
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        check(self._lib.abb_filter_popcount(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def popCount(self): return self.popcounts()[0]
+    def filtered_popcount(self): return self.popcounts()[1]
+    def FPR(self): return (self.popCount() / self.size()) ** self.getHashNum()
+    def filtered_FPR(self): return (self.filtered_popcount() / self.size()) ** self.getHashNum()
+
+    def stats(self, reset: bool = False) -> InsertStats:
+        st = InsertStats()
+        check(self._lib.abb_filter_insert_stats(self._h, C.byref(st), int(reset)))
+        return st

@@ -1,0 +1,101 @@
+// abb_common.h -- host-side plumbing shared by the C-ABI translation units.
+#pragma once
+#include "../../include/abyss_b200.h"
+#include "abb_device.cuh"
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+
+namespace abb {
+
+void set_error(const char* fmt, ...);
+
+#define ABB_CUDA(call)                                                                             \
+	do {                                                                                           \
+		cudaError_t e__ = (call);                                                                  \
+		if (e__ != cudaSuccess) {                                                                  \
+			abb::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+			return (e__ == cudaErrorMemoryAllocation) ? ABB_ENOMEM                                 \
+			       : (e__ == cudaErrorNoDevice || e__ == cudaErrorInsufficientDriver) ? ABB_ENODEV \
+			                                                                          : ABB_ECUDA; \
+		}                                                                                          \
+	} while (0)
+
+#define ABB_CHECK(expr)            \
+	do {                           \
+		int rc__ = (expr);         \
+		if (rc__ != ABB_OK)        \
+			return rc__;           \
+	} while (0)
+
+#define ABB_REQUIRE(cond, ...)         \
+	do {                               \
+		if (!(cond)) {                 \
+			abb::set_error(__VA_ARGS__); \
+			return ABB_EINVAL;         \
+		}                              \
+	} while (0)
+
+/** growable device buffer */
+template <typename T>
+struct DevBuf {
+	T* p = nullptr;
+	size_t cap = 0;
+	int reserve(size_t n)
+	{
+		if (n <= cap)
+			return ABB_OK;
+		if (p)
+			cudaFree(p);
+		p = nullptr;
+		cap = 0;
+		size_t want = n + n / 8 + 256;
+		ABB_CUDA(cudaMalloc((void**)&p, want * sizeof(T)));
+		cap = want;
+		return ABB_OK;
+	}
+	void release()
+	{
+		if (p)
+			cudaFree(p);
+		p = nullptr;
+		cap = 0;
+	}
+};
+
+inline unsigned blocks_for(uint64_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
+
+} // namespace abb
+
+/** The filter handle (opaque in the C ABI). */
+struct abb_filter {
+	int device = 0;
+	int kind = ABB_COUNTING;
+	uint64_t size = 0;            // counters, or bits per level
+	uint64_t bytes_per_level = 0; // bytes of one level
+	unsigned H = 0, k = 0, threshold = 0, levels = 1;
+	std::string mask;
+	uint8_t* d_care = nullptr; // k bytes (mask == '1'), only with a spaced seed
+	uint8_t* d_data = nullptr;
+	abb::HashCfg cfg;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+	// ordered-insert workspace
+	uint64_t window = 0; // slots per window
+	unsigned long long* d_tags = nullptr;
+	uint64_t tag_slots = 0;
+	unsigned epoch = 0;
+	unsigned* d_deferred = nullptr;
+	unsigned* d_ndef = nullptr;
+	unsigned long long* d_stats = nullptr; // [0] deferred [1] max rounds [2] serial [3..4] popcount scratch
+
+	// per-call buffers
+	abb::DevBuf<uint8_t> bases;
+	abb::DevBuf<uint64_t> offs, slot_offs, h0, lit;
+	abb::DevBuf<uint8_t> valid, scan_tmp, out8;
+
+	// statistics
+	abb_insert_stats st = {};
+};

@@ -1,0 +1,167 @@
+/*
+ * abyss_b200.h -- C ABI of libabyssb200.so: the B200 (sm_100a) implementation of the
+ * abyss-bloom-dbg hot path (ntHash -> Bloom insert -> Bloom-backed unitig extension).
+ *
+ * The reference (bcgsc/abyss 2.3.10) has no FFI layer: its seam is the duck-typed Bloom filter
+ * template parameter (BloomT / SolidKmerSetT / BF) that loadSeq, allKmersInBloom,
+ * RollingBloomDBG<BF> and assemble() are templated on.  Each entry point
+ * below names the reference interface it replaces (file:line under the reference tree).
+ * Per-k-mer virtual calls cannot feed a GPU, so everything is batch oriented.
+ *
+ * Conventions: extern "C"; plain pointers and sizes; every function returns ABB_OK (0) or a
+ * negative ABB_E* code and records a message retrievable with abb_last_error(); no exceptions
+ * cross the boundary; one host thread per handle (streams are internal); buffers are caller
+ * owned.  Where the reference would print and exit(1) (Common/IOUtil.h:14-22,
+ * BloomFilter.hpp:376-379) this library returns an error instead; the CLI turns it into exit.
+ * There is NO CPU fallback: without a usable CUDA device every compute call fails with
+ * ABB_ENODEV.
+ */
+#ifndef ABYSS_B200_H
+#define ABYSS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ABB_VERSION 100
+
+enum {
+	ABB_OK = 0,
+	ABB_EINVAL = -1, /* bad argument (what the reference would assert / exit on) */
+	ABB_ENODEV = -2, /* no CUDA device / driver */
+	ABB_ECUDA = -3,  /* CUDA runtime failure, see abb_last_error() */
+	ABB_ENOMEM = -4,
+	ABB_ESTATE = -5  /* call not valid for this handle kind / state */
+};
+
+/* filter kinds */
+enum {
+	ABB_COUNTING = 0, /* CountingBloomFilter<uint8_t>, vendor/btl_bloomfilter/CountingBloomFilter.hpp:26-113 */
+	ABB_BIT = 1,      /* BloomFilter, vendor/btl_bloomfilter/BloomFilter.hpp:40-432 */
+	ABB_CASCADING = 2 /* HashAgnosticCascadingBloom, Bloom/HashAgnosticCascadingBloom.h:26-182 */
+};
+
+typedef struct abb_filter abb_filter;
+typedef struct abb_assembler abb_assembler;
+
+/* ---- library ---- */
+int abb_version(void);
+const char* abb_last_error(void);
+int abb_device_count(void); /* <0 on error */
+
+/* ---- filter lifecycle --------------------------------------------------------------------
+ * size: number of counters (ABB_COUNTING; CountingBloomFilter ctor :31-50 pads to a multiple of
+ *       8) or number of bits per level (ABB_BIT / ABB_CASCADING; must be a multiple of 8,
+ *       BloomFilter.hpp:374-379).
+ * arg:  count threshold (ABB_COUNTING, `--kc`), ignored (ABB_BIT), number of levels (ABB_CASCADING).
+ * mask: spaced seed ("" or NULL = none; MaskedKmer::setMask, BloomDBG/MaskedKmer.h:38-55).
+ */
+int abb_filter_create(abb_filter** out, int kind, uint64_t size, unsigned num_hashes, unsigned k,
+                      unsigned arg, const char* mask, int device);
+int abb_filter_destroy(abb_filter* f);
+/* getters: getKmerSize/getHashNum/size/sizeInBytes/threshold (CountingBloomFilter.hpp:75-80) */
+unsigned abb_filter_kmer_size(const abb_filter* f);
+unsigned abb_filter_hash_num(const abb_filter* f);
+uint64_t abb_filter_size(const abb_filter* f);
+uint64_t abb_filter_size_in_bytes(const abb_filter* f); /* bytes of ONE level */
+unsigned abb_filter_threshold(const abb_filter* f);
+unsigned abb_filter_levels(const abb_filter* f);
+int abb_filter_set_threshold(abb_filter* f, unsigned threshold);
+
+/* ---- pass 1: loadSeq / loadFile (BloomDBG/BloomIO.h:32-41,50-94) --------------------------
+ * Hash every k-mer of every read (RollingHashIterator semantics: upper-cased, windows touching a
+ * non-ACGT base skipped) and insert it, with results IDENTICAL to inserting read by read, k-mer
+ * by k-mer in the given order on one thread (the reference at -j1).
+ * bases: concatenated read characters; offsets[n_reads+1]: start of each read in bases.
+ * n_kmers_out (optional): number of k-mers inserted.
+ * The _dev variant takes device-resident buffers (no host<->device copy inside the call). */
+int abb_insert_reads(abb_filter* f, const char* bases, const uint64_t* offsets, uint64_t n_reads,
+                     uint64_t* n_kmers_out);
+int abb_insert_reads_dev(abb_filter* f, const char* d_bases, const uint64_t* d_offsets,
+                         uint64_t n_reads, uint64_t n_bases, uint64_t* n_kmers_out);
+
+/* ---- the literal `const uint64_t hashes[]` interface (for parity tests) --------------------
+ * hashes: n * num_hashes values, k-mer major -- exactly what RollingHashIterator::operator*
+ * yields (BloomDBG/RollingHashIterator.h:147-151).  insert (CountingBloomFilter.hpp:199-204,
+ * BloomFilter.hpp:186-195, HashAgnosticCascadingBloom.h:124-133) is applied in array order. */
+int abb_insert_hashes(abb_filter* f, const uint64_t* hashes, uint64_t n);
+int abb_contains_hashes(abb_filter* f, const uint64_t* hashes, uint64_t n, uint8_t* out);  /* contains(): :185-196 */
+int abb_mincount_hashes(abb_filter* f, const uint64_t* hashes, uint64_t n, uint8_t* out);  /* minCount(): :54-64 */
+
+/* ---- hashing only (RollingHashIterator + RollingHash::getHashes) ---------------------------
+ * For each read r and window position p < max(0, len_r - k + 1), slot = slot_offsets[r] + p where
+ * slot_offsets is the exclusive prefix sum of the per-read window counts.  out_h0[slot] is the
+ * canonical (masked) ntHash, out_valid[slot] is 1 if the reference iterator would yield it.
+ * Returns the total number of slots through n_slots_out. */
+int abb_hash_reads(unsigned k, const char* mask, const char* bases, const uint64_t* offsets,
+                   uint64_t n_reads, uint64_t* out_h0, uint8_t* out_valid, uint64_t* n_slots_out,
+                   int device);
+
+/* ---- raw array <-> host (operator<< / loadFilter: CountingBloomFilter.hpp:262-379,
+ * BloomFilter.hpp:98-163,288-294; for ABB_CASCADING `level` selects the level, -1 = last,
+ * which is the only one the reference serialises, HashAgnosticCascadingBloom.h:143-150) */
+int abb_filter_download(abb_filter* f, int level, uint8_t* host, uint64_t nbytes);
+int abb_filter_upload(abb_filter* f, int level, const uint8_t* host, uint64_t nbytes);
+int abb_filter_clear(abb_filter* f);
+
+/* ---- statistics: popCount / filtered_popcount (CountingBloomFilter.hpp:219-244), getPop
+ * (BloomFilter.hpp:313-320).  FPR = pow(pop/size, H) is left to the caller. */
+int abb_filter_popcount(abb_filter* f, uint64_t* nonzero, uint64_t* at_or_above_threshold);
+
+/* ---- pass 2: BloomDBG::assemble / processRead (BloomDBG/bloom-dbg.h:783-882,900-1089) -------
+ * The assembler owns the "assembled k-mers" bit filter (bloom-dbg.h:910-911: size() bits, same H,
+ * same k) and the contigEndKmers table (:992-993) and consumes reads in file order, batch by
+ * batch.  Output is identical to the reference at -j1.
+ */
+typedef struct abb_assembly_params {
+	unsigned trim;      /* AssemblyParams::trim (AssemblyParams.h:67), default k */
+	unsigned verbose;
+} abb_assembly_params;
+
+typedef struct abb_contig {
+	uint64_t seed_read;   /* index (in the whole input stream) of the read that seeded it */
+	uint64_t seq_offset;  /* into the sequence buffer returned alongside */
+	uint32_t length;      /* bases */
+	uint32_t coverage;    /* getSeqAbsoluteKmerCoverage (bloom-dbg.h:95-109) */
+} abb_contig;
+
+/* counters mirror BloomDBG/AssemblyCounters.h:15-29 */
+typedef struct abb_assembly_counters {
+	uint64_t solid_reads, visited_reads, reads_processed, bases_assembled, contig_id;
+} abb_assembly_counters;
+
+int abb_assembler_create(abb_assembler** out, abb_filter* solid, const abb_assembly_params* params);
+int abb_assembler_destroy(abb_assembler* a);
+/* Process the next batch of reads (file order).  On return *contigs / *seqs point at library-
+ * owned buffers valid until the next call on this handle. */
+int abb_assembler_process_reads(abb_assembler* a, const char* bases, const uint64_t* offsets,
+                                uint64_t n_reads, const abb_contig** contigs, uint64_t* n_contigs,
+                                const char** seqs);
+int abb_assembler_counters(const abb_assembler* a, abb_assembly_counters* out);
+/* optional per-read outcome log of the last batch (ReadResult, bloom-dbg.h:256-293);
+ * codes: 0 SHORTER_THAN_K, 1 NON_ACGT, 2 BLUNT_END, 3 NOT_SOLID, 4 ALL_KMERS_VISITED,
+ * 5 GENERATED_CONTIGS */
+int abb_assembler_read_results(const abb_assembler* a, const uint8_t** codes, uint64_t* n);
+/* access to the assembled-k-mer bit filter (for checkpoints / tests) */
+abb_filter* abb_assembler_assembled_filter(abb_assembler* a);
+
+/* ---- profiling hooks used by bench.py ---------------------------------------------------- */
+typedef struct abb_insert_stats {
+	uint64_t kmers;           /* valid k-mers inserted */
+	uint64_t slots;           /* k-mer windows hashed */
+	uint64_t windows;         /* ordered windows processed */
+	uint64_t deferred;        /* events that lost a reservation and went through the ordered pass */
+	uint64_t launches;        /* kernels launched by this library since the last reset */
+	float ms_hash, ms_insert; /* CUDA-event time on the library stream since the last reset */
+} abb_insert_stats;
+int abb_filter_insert_stats(abb_filter* f, abb_insert_stats* out, int reset);
+/* tuning: ordered-window size in k-mer slots (power of two, <= 2^20); 0 = default */
+int abb_filter_set_window(abb_filter* f, uint64_t window_slots);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ABYSS_B200_H */

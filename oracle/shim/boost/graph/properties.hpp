@@ -1,0 +1,28 @@
+// Test infrastructure only: stand-in header so the UNMODIFIED reference sources compile
+// without Boost/autoconf (see oracle/README.md). Not part of the product.
+#pragma once
+#include <boost/graph/graph_traits.hpp>
+namespace boost {
+struct no_property {};
+enum default_color_type { white_color, gray_color, green_color, red_color, black_color };
+template <class C> struct color_traits {
+  static default_color_type white() { return white_color; }
+  static default_color_type gray() { return gray_color; }
+  static default_color_type black() { return black_color; }
+};
+struct read_write_property_map_tag {};
+template <class PM> struct property_traits;
+enum vertex_bundle_t { vertex_bundle }; enum edge_bundle_t { edge_bundle };
+enum vertex_name_t { vertex_name }; enum edge_name_t { edge_name };
+enum vertex_index_t { vertex_index }; enum edge_weight_t { edge_weight };
+template <class G> struct edge_bundle_type { typedef no_property type; };
+template <class G> struct vertex_bundle_type { typedef no_property type; };
+template <class G> struct edge_property { typedef no_property type; };
+template <class G> struct vertex_property { typedef no_property type; };
+template <class T> void function_requires() {}
+}
+#define BOOST_INSTALL_PROPERTY(KIND, NAME)
+namespace boost {
+template <class R, class PM> struct put_get_helper {};
+struct readable_property_map_tag {};
+}
