@@ -1,0 +1,745 @@
+// abb_walk.cuh -- Bloom-backed de Bruijn graph traversal (pass 2), warp-uniform.
+//
+// Replaces, for the RollingBloomDBG<CountingBloomFilter> instantiation only:
+//   RollingBloomDBG out/in_edge iterators + vertex_exists     BloomDBG/RollingBloomDBG.h:302-436
+//   lookAhead / trueBranch / successor / ambiguous            Graph/ExtendPath.h:99-397
+//   extendPathBySingleVertex / extendPath                     Graph/ExtendPath.h:403-459,621-720
+//   getContigType / preprocessCircularContig / trimBranchKmers / isTip   BloomDBG/bloom-dbg.h:622-776
+//   the per-read loop of processRead                          BloomDBG/bloom-dbg.h:837-879
+//
+// Execution model: ONE WARP walks one seed read.  Every function below is executed by all 32
+// lanes with identical ("uniform") arguments and control flow; lanes only diverge inside the Ctx
+// primitives:  Ctx::neighbors() probes the 8 neighbour k-mers x H hash functions of a vertex with
+// one lane per (neighbour, hash) pair -- one HBM round trip per graph step -- and the scratch
+// helpers let lane 0 write while everybody reads.  Because all graph logic is uniform scalar code
+// over a Ctx, tests/host_walk instantiates the very same templates with a trivial single-thread
+// Ctx to debug the logic without a GPU (test infrastructure; the library never runs it).
+//
+// Vertex identity: the reference compares vertices by canonical hash AND canonical string
+// (RollingBloomDBG.h:92-100, RC-invariant).  Here identity is the 64-bit canonical ntHash alone;
+// two distinct k-mers colliding inside one local traversal has probability ~2^-64 per comparison.
+// Spaced seeds are not supported in pass 2 (the assembler refuses a masked filter).
+#pragma once
+#include "abb_device.cuh"
+
+namespace abb {
+
+enum Dir : unsigned { FWD = 0, REV = 1 };
+ABB_HD Dir opposite(Dir d) { return d == FWD ? REV : FWD; }
+
+/** PathExtensionResultCode (Graph/ExtendPath.h:45-57) */
+enum ExtCode : unsigned { ER_AMBI_IN = 0, ER_AMBI_OUT = 1, ER_DEAD_END = 2, ER_CYCLE = 3, ER_LENGTH_LIMIT = 4 };
+
+/** ReadResult (BloomDBG/bloom-dbg.h:256-266), compacted */
+enum ReadCode : uint8_t {
+	RC_SHORTER_THAN_K = 0, RC_NON_ACGT = 1, RC_BLUNT_END = 2, RC_NOT_SOLID = 3, RC_ALL_KMERS_VISITED = 4,
+	RC_GENERATED_CONTIGS = 5, RC_CANDIDATE = 6 /* internal: solid, not blunt, not yet decided */
+};
+
+constexpr unsigned kFpTrim = 5; // hard-coded in the reference (bloom-dbg.h:500,550,661,741,847)
+
+// ------------------------------------------------------------------------------------------
+// 2-bit packed k-mer: base i (0 = leftmost) lives at bits [2(k-1-i), 2(k-1-i)+1] of a KW*64-bit
+// integer, w[0] least significant.  Appending a base is a 2-bit left shift.
+// ------------------------------------------------------------------------------------------
+template <int KW>
+struct Kmer {
+	uint64_t w[KW];
+};
+
+template <int KW>
+ABB_HD unsigned kmer_last(const Kmer<KW>& km) { return (unsigned)(km.w[0] & 3); }
+
+template <int KW>
+ABB_HD unsigned kmer_base(const Kmer<KW>& km, unsigned k, unsigned i)
+{
+	const unsigned p = 2 * (k - 1 - i);
+	uint64_t word = 0;
+#pragma unroll
+	for (int j = 0; j < KW; ++j)
+		if ((unsigned)j == (p >> 6))
+			word = km.w[j];
+	return (unsigned)((word >> (p & 63)) & 3);
+}
+template <int KW>
+ABB_HD unsigned kmer_first(const Kmer<KW>& km, unsigned k) { return kmer_base(km, k, 0); }
+
+/** drop the first base, append b */
+template <int KW>
+ABB_HD void kmer_append(Kmer<KW>& km, unsigned k, unsigned b)
+{
+#pragma unroll
+	for (int j = KW - 1; j > 0; --j)
+		km.w[j] = (km.w[j] << 2) | (km.w[j - 1] >> 62);
+	km.w[0] = (km.w[0] << 2) | b;
+	// clear everything at and above bit 2k
+	const unsigned top = 2 * k;
+#pragma unroll
+	for (int j = 0; j < KW; ++j) {
+		const unsigned lo = 64u * j;
+		if (top <= lo)
+			km.w[j] = 0;
+		else if (top < lo + 64)
+			km.w[j] &= (1ULL << (top - lo)) - 1;
+	}
+}
+/** drop the last base, prepend b */
+template <int KW>
+ABB_HD void kmer_prepend(Kmer<KW>& km, unsigned k, unsigned b)
+{
+#pragma unroll
+	for (int j = 0; j < KW - 1; ++j)
+		km.w[j] = (km.w[j] >> 2) | (km.w[j + 1] << 62);
+	km.w[KW - 1] >>= 2;
+	const unsigned p = 2 * (k - 1);
+#pragma unroll
+	for (int j = 0; j < KW; ++j)
+		if ((unsigned)j == (p >> 6))
+			km.w[j] |= (uint64_t)b << (p & 63);
+}
+template <int KW>
+ABB_HD bool kmer_equal(const Kmer<KW>& a, const Kmer<KW>& b)
+{
+	bool eq = true;
+#pragma unroll
+	for (int j = 0; j < KW; ++j)
+		eq &= a.w[j] == b.w[j];
+	return eq;
+}
+
+/** A vertex: k-mer + rolling hash state (RollingBloomDBGVertex, RollingBloomDBG.h:33-159) */
+template <int KW>
+struct Vtx {
+	Kmer<KW> km;
+	HashPair h;
+	ABB_HD uint64_t canon() const { return h.canonical(); }
+};
+
+/** Move to the neighbour in direction d with new base b; returns the base that fell off.
+ *  (vertex.shift + setLastBase, RollingBloomDBG.h:56-70; RollingHash.h:88-128,175-193) */
+template <int KW>
+ABB_HD unsigned vtx_step(Vtx<KW>& v, unsigned k, const RollTab& rt, Dir d, unsigned b)
+{
+	unsigned out;
+	if (d == FWD) {
+		out = kmer_first(v.km, k);
+		v.h = roll_right(v.h, rt, out, b);
+		kmer_append(v.km, k, b);
+	} else {
+		out = kmer_last(v.km);
+		v.h = roll_left(v.h, rt, out, b);
+		kmer_prepend(v.km, k, b);
+	}
+	return out;
+}
+/** undo a vtx_step(d, .) that dropped `out` */
+template <int KW>
+ABB_HD void vtx_unstep(Vtx<KW>& v, unsigned k, const RollTab& rt, Dir d, unsigned out)
+{
+	vtx_step(v, k, rt, opposite(d), out);
+}
+
+/** vertex of the k bases at s[0..k) given as 2-bit codes (NTC64 from scratch, nthash.hpp:220-239) */
+template <int KW>
+ABB_HD Vtx<KW> vtx_from_codes(const uint8_t* s, unsigned k, bool ascii)
+{
+	Vtx<KW> v;
+#pragma unroll
+	for (int j = 0; j < KW; ++j)
+		v.km.w[j] = 0;
+	v.h.fh = v.h.rh = 0;
+	for (unsigned i = 0; i < k; ++i) {
+		const unsigned c = ascii ? base_code(s[i]) : s[i];
+		kmer_append(v.km, k, c & 3);
+		v.h.fh = srol1(v.h.fh) ^ seed_of(c);
+	}
+	for (unsigned i = 0; i < k; ++i) {
+		const unsigned c = ascii ? base_code(s[k - 1 - i]) : s[k - 1 - i];
+		v.h.rh = srol1(v.h.rh) ^ seed_of(3 - c);
+	}
+	return v;
+}
+
+/** reverse complement (RollingBloomDBGVertex::reverseComplement, RollingBloomDBG.h:72-76) */
+template <int KW>
+ABB_HD Vtx<KW> vtx_revcomp(const Vtx<KW>& v, unsigned k)
+{
+	Vtx<KW> r;
+#pragma unroll
+	for (int j = 0; j < KW; ++j)
+		r.km.w[j] = 0;
+	for (unsigned i = 0; i < k; ++i)
+		kmer_append(r.km, k, 3 - kmer_base(v.km, k, k - 1 - i));
+	r.h.fh = v.h.rh;
+	r.h.rh = v.h.fh;
+	return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// Scratch layouts (per warp, in global memory)
+// ------------------------------------------------------------------------------------------
+/** one active trueBranch() call (Graph/ExtendPath.h:173-244) */
+struct Frame {
+	uint64_t hv;   // canonical hash of this call's vertex v (the "visited" set is the stack)
+	uint64_t meta; // see pack/unpack below
+};
+constexpr unsigned kFrameCap = 4096;  // trueBranch recursion depth bound per warp
+constexpr unsigned kLookCap = 2048;   // lookAhead visited-list bound per warp (<= 1 + 4 + .. + 4^5 = 1365)
+
+ABB_HD uint64_t frame_pack(unsigned dir, unsigned phase, unsigned depth, unsigned omask, unsigned imask, unsigned enter_dir,
+                           unsigned dropped)
+{
+	return (uint64_t)dir | ((uint64_t)phase << 1) | ((uint64_t)omask << 3) | ((uint64_t)imask << 7) |
+	       ((uint64_t)enter_dir << 11) | ((uint64_t)dropped << 12) | ((uint64_t)depth << 16);
+}
+struct FrameView {
+	unsigned dir, phase, omask, imask, enter_dir, dropped, depth;
+};
+ABB_HD FrameView frame_unpack(uint64_t m)
+{
+	FrameView f;
+	f.dir = (unsigned)(m & 1);
+	f.phase = (unsigned)((m >> 1) & 3);
+	f.omask = (unsigned)((m >> 3) & 15);
+	f.imask = (unsigned)((m >> 7) & 15);
+	f.enter_dir = (unsigned)((m >> 11) & 1);
+	f.dropped = (unsigned)((m >> 12) & 3);
+	f.depth = (unsigned)(m >> 16);
+	return f;
+}
+
+ABB_HD unsigned ctz4(unsigned m) { return (m & 1) ? 0 : (m & 2) ? 1 : (m & 4) ? 2 : 3; }
+
+/**
+ * Ctx concept (device: WarpCtx in abb_assemble.cu; host emulation: tests/host_walk):
+ *   unsigned k, trim; RollTab rt;
+ *   template<int KW> unsigned neighbors(const Vtx<KW>&)   bits 0-3: out-neighbours A,C,G,T exist; 4-7: in-neighbours
+ *   uint64_t rd64(const uint64_t*), void wr64(uint64_t*, uint64_t), uint8_t rd8(const uint8_t*), void wr8(uint8_t*, uint8_t)
+ *   void sync()                      make lane-0 writes visible to the warp
+ *   bool find64(const uint64_t* a, unsigned n, uint64_t key, unsigned stride_words)   cooperative linear search
+ *   uint8_t* alloc(uint64_t bytes)   arena bump allocation, zero-filled iff zero==true; nullptr when exhausted
+ *   void fail(unsigned why), bool failed()   record an overflow; the walk of this read is abandoned and retried by the host
+ *   void copy8(dst, src, n), copy8_rev(dst, src, n)   cooperative byte copies (rev: dst[i] = src[n-1-i])
+ *   void rehash(old, oldcap, new, newcap)              cooperative PathSet growth
+ *   void mark_covered(ps, rh, cov, nk, contig)         cooperative: flag read k-mers that lie on the contig path
+ *   Frame* frames; uint64_t* look;   per-warp scratch
+ */
+
+// ------------------------------------------------------------------------------------------
+// lookAhead (Graph/ExtendPath.h:99-161): bounded DFS with a permanent visited set
+// ------------------------------------------------------------------------------------------
+template <int KW, class Ctx>
+ABB_HD bool look_ahead(Ctx& c, const Vtx<KW>& start, Dir dir, unsigned limit)
+{
+	unsigned nvis = 0;
+	c.wr64(c.look + nvis++, start.canon()); // visited.insert(u)
+	if (limit == 0)
+		return true;
+	Vtx<KW> cur = start;
+	// explicit stack, depth <= limit <= 8: remaining-neighbour mask and dropped base per level
+	unsigned masks[8], dropped[8];
+	unsigned sp = 0;
+	{
+		const unsigned m = c.neighbors(cur);
+		masks[0] = dir == FWD ? (m & 15) : (m >> 4);
+		dropped[0] = 0;
+		sp = 1;
+	}
+	c.sync();
+	while (sp > 0) {
+		unsigned& m = masks[sp - 1];
+		if (m == 0) {
+			--sp;
+			if (sp > 0)
+				vtx_unstep(cur, c.k, c.rt, dir, dropped[sp]);
+			continue;
+		}
+		const unsigned b = ctz4(m);
+		m &= m - 1;
+		const unsigned out = vtx_step(cur, c.k, c.rt, dir, b);
+		const uint64_t hv = cur.canon();
+		if (c.find64(c.look, nvis, hv, 1)) { // already visited
+			vtx_unstep(cur, c.k, c.rt, dir, out);
+			continue;
+		}
+		if (nvis >= kLookCap) {
+			c.fail(1);
+			return true;
+		}
+		c.wr64(c.look + nvis++, hv);
+		c.sync();
+		if (sp >= limit) // depth of cur == sp
+			return true;
+		const unsigned nm = c.neighbors(cur);
+		dropped[sp] = out;
+		masks[sp] = dir == FWD ? (nm & 15) : (nm >> 4);
+		++sp;
+	}
+	return false;
+}
+
+// ------------------------------------------------------------------------------------------
+// trueBranch (Graph/ExtendPath.h:173-261), iterative; the DFS stack doubles as `visited`
+// ------------------------------------------------------------------------------------------
+template <int KW, class Ctx>
+ABB_HD bool true_branch(Ctx& c, const Vtx<KW>& u, Dir dir, unsigned base, unsigned trim_i)
+{
+	if (trim_i == 0) // "depth >= trim" with an empty visited set
+		return true;
+	Vtx<KW> cur = u;
+	const uint64_t hu_top = u.canon();
+	unsigned out = vtx_step(cur, c.k, c.rt, dir, base);
+	unsigned sp = 0;
+	{
+		const unsigned m = c.neighbors(cur);
+		c.wr64(&c.frames[0].hv, cur.canon());
+		c.wr64(&c.frames[0].meta, frame_pack(dir, 0, 0, m & 15, m >> 4, dir, out));
+		sp = 1;
+		c.sync();
+	}
+	while (sp > 0) {
+		Frame* F = &c.frames[sp - 1];
+		FrameView f = frame_unpack(c.rd64(&F->meta));
+		const Dir fdir = (Dir)f.dir;
+		if (f.phase == 0) {
+			unsigned m = fdir == FWD ? f.omask : f.imask;
+			if (m != 0) {
+				const unsigned b = ctz4(m);
+				m &= m - 1;
+				if (fdir == FWD)
+					f.omask = m;
+				else
+					f.imask = m;
+				c.wr64(&F->meta, frame_pack(f.dir, 0, f.depth, f.omask, f.imask, f.enter_dir, f.dropped));
+				out = vtx_step(cur, c.k, c.rt, fdir, b);
+				const uint64_t hv = cur.canon();
+				// trueBranch(edge, depth + 1, same dir): visited? deep enough?
+				if (c.find64(&c.frames[0].hv, sp, hv, 2) || f.depth + 1 >= trim_i)
+					return true;
+				if (sp >= kFrameCap) {
+					c.fail(2);
+					return true;
+				}
+				const unsigned nm = c.neighbors(cur);
+				c.wr64(&c.frames[sp].hv, hv);
+				c.wr64(&c.frames[sp].meta, frame_pack(f.dir, 0, f.depth + 1, nm & 15, nm >> 4, f.dir, out));
+				++sp;
+				c.sync();
+				continue;
+			}
+			// no more same-direction neighbours: decide whether to turn around (ExtendPath.h:206,227)
+			const bool turn = f.depth >= kFpTrim || look_ahead(c, cur, fdir, kFpTrim);
+			if (!turn) { // visited.erase(v); return false
+				vtx_unstep(cur, c.k, c.rt, (Dir)f.enter_dir, f.dropped);
+				--sp;
+				continue;
+			}
+			f.phase = 2;
+			c.wr64(&F->meta, frame_pack(f.dir, 2, f.depth, f.omask, f.imask, f.enter_dir, f.dropped));
+			c.sync();
+		}
+		// phase 2: edges in the opposite direction, skipping the vertex we came from
+		{
+			const Dir od = opposite(fdir);
+			unsigned m = od == FWD ? f.omask : f.imask;
+			if (m == 0) { // visited.erase(v); return false
+				vtx_unstep(cur, c.k, c.rt, (Dir)f.enter_dir, f.dropped);
+				--sp;
+				continue;
+			}
+			const unsigned b = ctz4(m);
+			m &= m - 1;
+			if (od == FWD)
+				f.omask = m;
+			else
+				f.imask = m;
+			c.wr64(&F->meta, frame_pack(f.dir, 2, f.depth, f.omask, f.imask, f.enter_dir, f.dropped));
+			out = vtx_step(cur, c.k, c.rt, od, b);
+			const uint64_t hv = cur.canon();
+			const uint64_t hu = sp >= 2 ? c.rd64(&c.frames[sp - 2].hv) : hu_top;
+			if (hv == hu) { // "if (source(*iei, g) == u) continue"
+				vtx_unstep(cur, c.k, c.rt, od, out);
+				c.sync();
+				continue;
+			}
+			// trueBranch(edge, 0, opposite dir); trim_i >= 1 here
+			if (c.find64(&c.frames[0].hv, sp, hv, 2))
+				return true;
+			if (sp >= kFrameCap) {
+				c.fail(2);
+				return true;
+			}
+			const unsigned nm = c.neighbors(cur);
+			c.wr64(&c.frames[sp].hv, hv);
+			c.wr64(&c.frames[sp].meta, frame_pack(od, 0, 0, nm & 15, nm >> 4, od, out));
+			++sp;
+			c.sync();
+		}
+	}
+	return false;
+}
+
+// ------------------------------------------------------------------------------------------
+// successor (Graph/ExtendPath.h:314-362)
+// ------------------------------------------------------------------------------------------
+/** nbmask = c.neighbors(u).  Returns the result code; *vbase = base of the last true branch seen */
+template <int KW, class Ctx>
+ABB_HD ExtCode successor(Ctx& c, const Vtx<KW>& u, unsigned nbmask, Dir dir, unsigned* vbase)
+{
+	const unsigned m = dir == FWD ? (nbmask & 15) : (nbmask >> 4);
+	for (unsigned i = 0;; i = (i == 0) ? 1 : (2 * i < c.trim ? 2 * i : c.trim)) {
+		unsigned cnt = 0;
+		for (unsigned mm = m; mm; mm &= mm - 1) {
+			const unsigned b = ctz4(mm);
+			if (true_branch(c, u, dir, b, i)) {
+				*vbase = b;
+				if (++cnt >= 2)
+					break;
+			}
+		}
+		if (cnt == 0)
+			return ER_DEAD_END;
+		if (cnt == 1)
+			return ER_LENGTH_LIMIT;
+		if (i == c.trim)
+			return ER_AMBI_OUT;
+	}
+}
+
+/** ambiguous(u, dir) (ExtendPath.h:368-375) */
+template <int KW, class Ctx>
+ABB_HD bool ambiguous(Ctx& c, const Vtx<KW>& u, Dir dir)
+{
+	unsigned b = 0;
+	return successor(c, u, c.neighbors(u), dir, &b) == ER_AMBI_OUT;
+}
+/** ambiguous(u, expected, dir) (ExtendPath.h:384-397) */
+template <int KW, class Ctx>
+ABB_HD bool ambiguous_expected(Ctx& c, const Vtx<KW>& u, uint64_t expected_canon, Dir dir)
+{
+	unsigned b = 0;
+	const ExtCode r = successor(c, u, c.neighbors(u), dir, &b);
+	if (r == ER_AMBI_OUT)
+		return true;
+	if (r == ER_LENGTH_LIMIT) {
+		Vtx<KW> v = u;
+		vtx_step(v, c.k, c.rt, dir, b);
+		return v.canon() != expected_canon;
+	}
+	return false;
+}
+
+// ------------------------------------------------------------------------------------------
+// exact set of the canonical hashes of the path vertices (extendPath's `visited`, ExtendPath.h:699-703)
+// open addressing in arena memory, doubled when more than 1/4 full; key 0 is tracked separately
+// ------------------------------------------------------------------------------------------
+struct PathSet {
+	uint64_t* tab;
+	unsigned cap; // power of two
+	unsigned n;
+	bool has_zero;
+};
+
+ABB_HD uint64_t pathset_slot(uint64_t key, unsigned cap) { return ((key * 0x9E3779B97F4A7C15ULL) >> 24) & (cap - 1); }
+
+template <class Ctx>
+ABB_HD bool pathset_init(Ctx& c, PathSet& ps, unsigned cap)
+{
+	ps.tab = (uint64_t*)c.alloc((uint64_t)cap * 8, true);
+	ps.cap = cap;
+	ps.n = 0;
+	ps.has_zero = false;
+	return ps.tab != nullptr;
+}
+template <class Ctx>
+ABB_HD bool pathset_contains(Ctx& c, const PathSet& ps, uint64_t key)
+{
+	if (key == 0)
+		return ps.has_zero;
+	for (uint64_t s = pathset_slot(key, ps.cap);; s = (s + 1) & (ps.cap - 1)) {
+		const uint64_t v = c.rd64(ps.tab + s);
+		if (v == key)
+			return true;
+		if (v == 0)
+			return false;
+	}
+}
+/** returns true if newly inserted; *ok = false on arena exhaustion */
+template <class Ctx>
+ABB_HD bool pathset_insert(Ctx& c, PathSet& ps, uint64_t key, bool* ok)
+{
+	if (key == 0) {
+		const bool fresh = !ps.has_zero;
+		ps.has_zero = true;
+		return fresh;
+	}
+	if ((ps.n + 1) * 4 > ps.cap) { // grow: re-insert everything into a table twice the size
+		PathSet big;
+		if (!pathset_init(c, big, ps.cap * 2)) {
+			*ok = false;
+			return false;
+		}
+		big.has_zero = ps.has_zero;
+		c.rehash(ps.tab, ps.cap, big.tab, big.cap); // cooperative re-insert of every non-zero entry
+		big.n = ps.n;
+		ps = big;
+	}
+	for (uint64_t s = pathset_slot(key, ps.cap);; s = (s + 1) & (ps.cap - 1)) {
+		const uint64_t v = c.rd64(ps.tab + s);
+		if (v == key)
+			return false;
+		if (v == 0) {
+			c.wr64(ps.tab + s, key);
+			c.sync();
+			++ps.n;
+			return true;
+		}
+	}
+}
+
+/** growable byte vector in arena memory (bases appended during an extension) */
+struct ByteVec {
+	uint8_t* p;
+	unsigned cap, n;
+};
+template <class Ctx>
+ABB_HD bool bytevec_push(Ctx& c, ByteVec& v, uint8_t x)
+{
+	if (v.n == v.cap) {
+		const unsigned ncap = v.cap ? v.cap * 2 : 1024;
+		uint8_t* np = c.alloc(ncap, false);
+		if (!np)
+			return false;
+		c.copy8(np, v.p, v.n);
+		v.p = np;
+		v.cap = ncap;
+	}
+	c.wr8(v.p + v.n, x);
+	++v.n;
+	return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// extendPath in one direction (Graph/ExtendPath.h:403-459,621-681) with ExtendPathParams
+// {trimLen = trim, fpTrim = 5, maxLen = NO_LIMIT, lookBehind = true, lookBehindStartVertex = false}
+// (bloom-dbg.h:845-850).
+//   head      in: the end vertex of the path in direction dir; out: the new end vertex
+//   psize     in/out: number of vertices in the path
+//   bases     receives the new base of every vertex pushed (in push order)
+// ------------------------------------------------------------------------------------------
+template <int KW, class Ctx>
+ABB_HD ExtCode extend_dir(Ctx& c, Vtx<KW>& head, Dir dir, unsigned* psize, ByteVec& bases, PathSet& ps, bool* ok)
+{
+	bool look_behind = false; // lookBehindStartVertex
+	uint64_t prev_h = 0;
+	for (;;) {
+		const unsigned nb = c.neighbors(head);
+		unsigned b = 0;
+		if (look_behind) { // extendPathBySingleVertex, ExtendPath.h:419-446
+			const ExtCode r = successor(c, head, nb, opposite(dir), &b);
+			if (r == ER_AMBI_OUT)
+				return ER_AMBI_IN;
+			if (*psize > 1) {
+				if (r == ER_DEAD_END)
+					return ER_AMBI_IN;
+				Vtx<KW> t = head;
+				vtx_step(t, c.k, c.rt, opposite(dir), b);
+				if (t.canon() != prev_h) // we are on a tip rejoining the graph
+					return ER_AMBI_IN;
+			}
+		}
+		const ExtCode r = successor(c, head, nb, dir, &b);
+		if (r != ER_LENGTH_LIMIT)
+			return r;
+		const uint64_t old_h = head.canon();
+		const unsigned out = vtx_step(head, c.k, c.rt, dir, b);
+		if (!pathset_insert(c, ps, head.canon(), ok)) { // visited.insert(head) failed: ER_CYCLE, pop
+			vtx_unstep(head, c.k, c.rt, dir, out);
+			return *ok ? ER_CYCLE : ER_DEAD_END;
+		}
+		if (!bytevec_push(c, bases, (uint8_t)b)) { // FWD: the new last base; REV: the new first base
+			*ok = false;
+			return ER_DEAD_END;
+		}
+		++*psize;
+		prev_h = old_h;
+		look_behind = true; // params.lookBehind
+		if (c.failed())
+			return ER_DEAD_END;
+	}
+}
+
+/** isTip (bloom-dbg.h:758-776) */
+ABB_HD bool is_tip(unsigned length, ExtCode left, ExtCode right, unsigned trim)
+{
+	if (length > trim)
+		return false;
+	if (left == ER_DEAD_END && (right == ER_DEAD_END || right == ER_AMBI_IN))
+		return true;
+	if (right == ER_DEAD_END && (left == ER_DEAD_END || left == ER_AMBI_IN))
+		return true;
+	return false;
+}
+
+/** result of extending one seed k-mer */
+struct ContigOut {
+	uint8_t* seq;    // 2-bit codes, one per byte, after trimming (pathToSeq, bloom-dbg.h:132-158)
+	unsigned len;    // bases
+	unsigned psize;  // vertices before trimming (contigPath.size() as isTip sees it)
+	ExtCode left, right;
+	bool tip;        // isTip: not output, but its k-mers still count as assembled for this read
+	bool popped_front, popped_back; // a real path vertex (not a pushed duplicate) was trimmed off that end
+	uint64_t front_h, back_h;       // canonical hashes of the trimmed-off vertices
+};
+
+/**
+ * Extend seed both ways, decide tip-ness, trim branch k-mers (bloom-dbg.h:852-869).
+ * ps must be a fresh PathSet; it ends up holding every vertex of the untrimmed path.
+ */
+template <int KW, class Ctx>
+ABB_HD bool extend_seed(Ctx& c, const Vtx<KW>& seed, PathSet& ps, ContigOut* o)
+{
+	const unsigned k = c.k;
+	bool ok = true;
+	pathset_insert(c, ps, seed.canon(), &ok);
+	ByteVec left = { nullptr, 0, 0 }, right = { nullptr, 0, 0 };
+	unsigned psize = 1;
+	Vtx<KW> front = seed, back = seed;
+	o->left = extend_dir(c, front, REV, &psize, left, ps, &ok);
+	if (!ok || c.failed())
+		return false;
+	o->right = extend_dir(c, back, FWD, &psize, right, ps, &ok);
+	if (!ok || c.failed())
+		return false;
+	o->psize = psize;
+	o->tip = is_tip(psize, o->left, o->right, c.trim);
+	o->popped_front = o->popped_back = false;
+	o->front_h = o->back_h = 0;
+
+	// materialise pathToSeq(contigPath): reversed(left) + seed + right, with one spare byte each side
+	// for the vertex preprocessCircularContig may push
+	const unsigned n = psize + k - 1;
+	uint8_t* buf = c.alloc((uint64_t)n + 2, false);
+	if (!buf)
+		return false;
+	uint8_t* s = buf + 1;
+	c.copy8_rev(s, left.p, left.n);
+	for (unsigned i = 0; i < k; ++i)
+		c.wr8(s + left.n + i, (uint8_t)kmer_base(seed.km, k, i));
+	c.copy8(s + left.n + k, right.p, right.n);
+	c.sync();
+	o->seq = s;
+	o->len = n;
+	if (o->tip || psize == 1) // trimBranchKmers returns immediately for a single vertex (bloom-dbg.h:727-728)
+		return true;
+
+	// ---- trimBranchKmers (bloom-dbg.h:720-756) ----
+	unsigned l = psize;
+	bool pushed_front = false, pushed_back = false;
+	{ // getContigType (bloom-dbg.h:629-644): is there an edge back -> front?
+		const unsigned om = c.neighbors(back) & 15;
+		bool edge = false;
+		for (unsigned mm = om; mm && !edge; mm &= mm - 1) {
+			Vtx<KW> x = back;
+			vtx_step(x, k, c.rt, FWD, ctz4(mm));
+			edge = x.canon() == front.canon();
+		}
+		if (edge && psize > 2) { // preprocessCircularContig (bloom-dbg.h:648-697)
+			Vtx<KW> v = front;
+			vtx_step(v, k, c.rt, REV, kmer_first(back.km, k)); // v.shift(ANTISENSE, back.getBase(0))
+			const bool circular = kmer_equal(v.km, back.km);
+			const bool branch_start = ambiguous(c, front, FWD) || ambiguous(c, front, REV);
+			const bool branch_end = ambiguous(c, back, FWD) || ambiguous(c, back, REV);
+			if (branch_start && !branch_end) {
+				// push_back(front) / push_back(rc(front)): pathToSeq lets the last k-mer overwrite its k columns
+				const Vtx<KW> x = circular ? front : vtx_revcomp(front, k);
+				for (unsigned i = 0; i < k; ++i)
+					c.wr8(s + (l - 1) + 1 + i, (uint8_t)kmer_base(x.km, k, i));
+				back = x;
+				pushed_back = true;
+				++l;
+			} else if (!branch_start && branch_end) {
+				// push_front(back) / push_front(rc(back)): only column 0 survives the later overwrites
+				const Vtx<KW> x = circular ? back : vtx_revcomp(back, k);
+				--s;
+				c.wr8(s, (uint8_t)kmer_first(x.km, k));
+				front = x;
+				pushed_front = true;
+				++l;
+			}
+			c.sync();
+		}
+	}
+	// path[1] and path[l-2] read back from the overlay: the old front occupies columns 1..k after a
+	// push_front, and a pushed back vertex is a consistent edge (back -> front, or back -> rc(front)
+	// in a hairpin), so it leaves the old back's columns unchanged
+	const Vtx<KW> second = vtx_from_codes<KW>(s + 1, k, false);
+	const Vtx<KW> penult = vtx_from_codes<KW>(s + (l - 2), k, false);
+	const bool amb1 = ambiguous_expected(c, front, second.canon(), FWD);
+	const bool amb2 = ambiguous_expected(c, back, penult.canon(), REV);
+	unsigned begin = 0, end = l + k - 1;
+	if (amb1) {
+		++begin;
+		if (!pushed_front) {
+			o->popped_front = true;
+			o->front_h = front.canon();
+		}
+	}
+	if (amb2) {
+		--end;
+		if (!pushed_back) {
+			o->popped_back = true;
+			o->back_h = back.canon();
+		}
+	}
+	o->seq = s + begin;
+	o->len = end - begin;
+	return true;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// the extension loop of processRead (bloom-dbg.h:837-879) for one candidate read:
+// every read k-mer not yet on a contig generated from this read seeds an extension.
+// Emit::operator()(ctx, seed_index, contig) is called for every non-tip contig, in order.
+// Returns false when scratch memory ran out (the host retries the read).
+// ------------------------------------------------------------------------------------------
+template <int KW, class Ctx, class Emit>
+ABB_HD bool walk_read(Ctx& c, const uint8_t* read_ascii, unsigned L, Emit& emit)
+{
+	const unsigned k = c.k;
+	const unsigned nk = L - k + 1;
+	uint64_t* rh = (uint64_t*)c.alloc((uint64_t)nk * 8, false);
+	uint8_t* cov = c.alloc(nk, true);
+	if (!rh || !cov)
+		return false;
+	{ // seqToPath (bloom-dbg.h:115-125): canonical hash of every read k-mer
+		Vtx<KW> v = vtx_from_codes<KW>(read_ascii, k, true);
+		c.wr64(rh, v.canon());
+		for (unsigned i = 1; i < nk; ++i) {
+			vtx_step(v, k, c.rt, FWD, base_code(read_ascii[i + k - 1]) & 3);
+			c.wr64(rh + i, v.canon());
+		}
+		c.sync();
+	}
+	Vtx<KW> rv = vtx_from_codes<KW>(read_ascii, k, true);
+	unsigned ri = 0;
+	for (unsigned i = 0; i < nk; ++i) {
+		if (c.rd8(cov + i)) // assembledKmers.find(*it) != end
+			continue;
+		for (; ri < i; ++ri)
+			vtx_step(rv, k, c.rt, FWD, base_code(read_ascii[ri + k]) & 3);
+		PathSet ps;
+		if (!pathset_init(c, ps, 1024))
+			return false;
+		ContigOut o;
+		if (!extend_seed(c, rv, ps, &o) || c.failed())
+			return false;
+		if (!o.tip)
+			emit(c, i, o);
+		c.mark_covered(ps, rh, cov, nk, o);
+	}
+	return !c.failed();
+}
+
+} // namespace abb
