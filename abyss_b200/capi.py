@@ -36,7 +36,7 @@ class Contig(C.Structure):
 
 
 class AssemblyParams(C.Structure):
-    _fields_ = [("trim", C.c_uint), ("verbose", C.c_uint)]
+    _fields_ = [("trim", C.c_uint), ("verbose", C.c_uint), ("read_log", C.c_uint), ("reserved", C.c_uint)]
 
 
 class AssemblyCounters(C.Structure):
@@ -259,3 +259,92 @@ class Filter:
         st = InsertStats()
         check(self._lib.abb_filter_insert_stats(self._h, C.byref(st), int(reset)))
         return st
+
+
+READ_CODES = ["SHORTER_THAN_K", "NON_ACGT", "BLUNT_END", "NOT_SOLID", "ALL_KMERS_VISITED", "GENERATED_CONTIGS", "CANDIDATE"]
+
+
+class Assembler:
+    """BloomDBG::assemble (bloom-dbg.h:900-1089) over a device-resident counting filter.
+
+    Feed batches of reads in file order with process_reads(); each call returns the unitigs the
+    reference would have printed while processing exactly those reads, in the same order."""
+
+    def __init__(self, solid: Filter, trim: int | None = None, read_log: bool = False, verbose: int = 0):
+        self._lib = load()
+        self._solid = solid  # keep alive
+        self._h = _vp()
+        p = AssemblyParams(0xFFFFFFFF if trim is None else trim, verbose, int(read_log), 0)
+        check(self._lib.abb_assembler_create(C.byref(self._h), solid.handle, C.byref(p)))
+
+    def close(self):
+        if self._h:
+            self._lib.abb_assembler_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def process_reads(self, seqs_or_arrays):
+        """returns list of (seed_read_index, sequence str, coverage)"""
+        bases, offs = seqs_or_arrays if isinstance(seqs_or_arrays, tuple) else pack_reads(seqs_or_arrays)
+        contigs = C.POINTER(Contig)()
+        n = C.c_uint64(0)
+        seqs = C.c_char_p()
+        check(self._lib.abb_assembler_process_reads(self._h, _ptr(bases), _ptr(offs), len(offs) - 1, C.byref(contigs),
+                                                    C.byref(n), C.byref(seqs)))
+        out = []
+        if n.value:
+            base = C.cast(seqs, C.c_void_p).value
+            for i in range(n.value):
+                c = contigs[i]
+                out.append((c.seed_read, C.string_at(base + c.seq_offset, c.length).decode(), c.coverage))
+        return out
+
+    def read_results(self) -> np.ndarray:
+        codes = _u8p()
+        n = C.c_uint64(0)
+        check(self._lib.abb_assembler_read_results(self._h, C.byref(codes), C.byref(n)))
+        return np.ctypeslib.as_array(codes, shape=(n.value,)).copy() if n.value else np.zeros(0, dtype=np.uint8)
+
+    def counters(self) -> AssemblyCounters:
+        c = AssemblyCounters()
+        check(self._lib.abb_assembler_counters(self._h, C.byref(c)))
+        return c
+
+
+def counters_for_budget(bloom_size_bytes: int) -> int:
+    """bloom-dbg.cc:359-367: counters = roundUpToMultiple(round(B / 1.125), 64)"""
+    r = int(bloom_size_bytes / 1.125 + 0.5)
+    return r if r % 64 == 0 else r + 64 - r % 64
+
+
+def bloom_dbg(read_ids, seqs_or_arrays, k: int, kc: int = 2, num_hashes: int = 4, bloom_size: int | None = None,
+              counters: int | None = None, trim: int | None = None, batch_reads: int | None = None, read_log: bool = False,
+              device: int = 0):
+    """abyss-bloom-dbg -k K --kc KC -H H -b B (countingBloomAssembly, bloom-dbg.cc:347-386) on one GPU.
+    Returns (fasta_text, read_codes)."""
+    if counters is None:
+        counters = counters_for_budget(bloom_size)
+    bases, offs = seqs_or_arrays if isinstance(seqs_or_arrays, tuple) else pack_reads(seqs_or_arrays)
+    n = len(offs) - 1
+    f = Filter.counting(counters, num_hashes, k, kc, device=device)
+    f.insert_reads((bases, offs))
+    a = Assembler(f, trim, read_log)
+    out, codes = [], []
+    cid = 0
+    step = batch_reads or n or 1
+    for lo in range(0, n, step):
+        hi = min(n, lo + step)
+        b0, b1 = int(offs[lo]), int(offs[hi])
+        sub = (bases[b0:b1], (offs[lo:hi + 1] - offs[lo]).astype(np.uint64))
+        for seed, seq, cov in a.process_reads(sub):
+            out.append(f">{cid} {len(seq)} {cov} read:{read_ids[seed]}\n{seq}\n")
+            cid += 1
+        codes.append(a.read_results())
+    a.close()
+    f.close()
+    return "".join(out), (np.concatenate(codes) if codes else np.zeros(0, dtype=np.uint8))

@@ -32,7 +32,7 @@ static uint64_t next_pow2(uint64_t x)
 	return p;
 }
 
-static int select_device(int device)
+int select_device(int device)
 {
 	int n = 0;
 	cudaError_t e = cudaGetDeviceCount(&n);
@@ -177,7 +177,7 @@ k_count_valid(const uint8_t* __restrict__ valid, uint64_t n, unsigned long long*
 }
 
 /** K1 launcher for reads [r0, r1): h0/valid index = slot_offs[r] + j - slot_base */
-static int launch_hash(abb_filter* f, unsigned k, const uint8_t* d_care, const uint8_t* d_bases,
+int launch_hash(abb_filter* f, unsigned k, const uint8_t* d_care, const uint8_t* d_bases,
                        const uint64_t* d_offs, const uint64_t* d_slot_offs, uint64_t r0, uint64_t r1,
                        uint64_t slot_base, uint64_t* d_h0, uint8_t* d_valid, cudaStream_t stream, uint64_t* launches)
 {
@@ -201,7 +201,7 @@ static int launch_hash(abb_filter* f, unsigned k, const uint8_t* d_care, const u
 }
 
 /** slot_offs[0..n_reads] = exclusive prefix sum of per-read window counts; returns the total */
-static int compute_slot_offsets(unsigned k, const uint64_t* d_offs, uint64_t n_reads, DevBuf<uint64_t>& slot_offs,
+int compute_slot_offsets(unsigned k, const uint64_t* d_offs, uint64_t n_reads, DevBuf<uint64_t>& slot_offs,
                                 DevBuf<uint8_t>& tmp, cudaStream_t stream, uint64_t* total, uint64_t* launches)
 {
 	ABB_CHECK(slot_offs.reserve(n_reads + 1));

@@ -1,12 +1,850 @@
-// abb_assemble.cu -- pass 2 (BloomDBG::assemble / processRead) behind the C ABI.
-// Work in progress: entry points exist so the ABI is complete; the kernels land next.
+// abb_assemble.cu -- pass 2 (BloomDBG::assemble / processRead, bloom-dbg.h:783-882,972-1089)
+// behind the C ABI.
+//
+// The reference processes reads strictly one after another at -j1; each read either is skipped
+// (short / non-ACGT / blunt end / not solid / all k-mers already assembled) or seeds unitig
+// extensions whose k-mers are then marked in the "assembled" bit Bloom filter.  Two facts make
+// this parallel without changing a byte of the output:
+//   (1) the classification tests and the extension of a seed k-mer are pure functions of the
+//       read-only solid filter (Graph/ExtendPath.h takes a const Graph&);
+//   (2) the assembled filter only ever gains bits, so "all k-mers assembled" is monotone: a read
+//       that is covered now stays covered.
+// Pipeline per batch of reads (file order):
+//   K3a classify      warp per read, all reads at once            (pure)
+//   loop over the candidate reads in file order:
+//     K3b visited     warp per candidate vs the CURRENT assembled filter; covered reads are final
+//     K4  extend      warp per not-yet-covered candidate, speculatively, many at once (pure)
+//     K1  hash        ntHash of the produced unitigs
+//     K5  replay      ONE CTA walks the speculated reads in file order doing exactly the
+//                     reference's bookkeeping: re-test "all assembled" with the now-current filter,
+//                     redundancy test, mark assembled, coverage = sum of minCount; 1024 threads
+//                     share the k-mers of each unitig
+// so every order-dependent decision is taken in file order with the same filter state the
+// reference would have, while the expensive graph walks run thousands at a time.
 #include "abb_common.h"
+#include "abb_walk.cuh"
+#include <algorithm>
+#include <cstring>
+#include <new>
+#include <vector>
 
+namespace abb {
+
+// ------------------------------------------------------------------------------------------
+// device context: the Ctx concept of abb_walk.cuh for one warp
+// ------------------------------------------------------------------------------------------
+struct WarpCtx {
+	unsigned k, trim;
+	RollTab rt;
+	const HashCfg* cfg;
+	const uint8_t* counters;
+	unsigned threshold;
+	unsigned lane;
+	Frame* frames;
+	uint64_t* look;
+	uint8_t* arena;
+	unsigned long long arena_size;
+	unsigned long long* arena_top;
+	unsigned fail_;
+
+	/** bits 0-3: out-neighbours (append A,C,G,T) present in the solid filter; bits 4-7: in-neighbours
+	 *  (prepend).  Lane = 4 * neighbour + hash slot: 8 neighbours x 4 hash functions per round trip
+	 *  (out/in_edge_iterator::next + vertex_exists, RollingBloomDBG.h:302-327,357-383,436-445). */
+	template <int KW>
+	__device__ unsigned neighbors(const Vtx<KW>& v) const
+	{
+		const unsigned n = lane >> 2, hs = lane & 3;
+		const HashPair h = n < 4 ? roll_right(v.h, rt, kmer_first(v.km, k), n) : roll_left(v.h, rt, kmer_last(v.km), n - 4);
+		const uint64_t h0 = h.canonical();
+		bool ok = true;
+		for (unsigned i = hs; i < cfg->H; i += 4)
+			ok &= __ldcg(counters + nth_pos(h0, *cfg, i)) >= threshold;
+		unsigned b = __ballot_sync(0xffffffffu, ok);
+		b &= b >> 1;
+		b &= b >> 2; // bit 4n = AND of the four lanes of neighbour n
+		unsigned r = 0;
+#pragma unroll
+		for (int j = 0; j < 8; ++j)
+			r |= ((b >> (4 * j)) & 1u) << j;
+		return r;
+	}
+	// scratch accesses: every lane stores the same value to the same address and reads back its own
+	// store, so no intra-warp synchronisation is needed for uniform data
+	__device__ uint64_t rd64(const uint64_t* p) const { return *(const volatile uint64_t*)p; }
+	__device__ void wr64(uint64_t* p, uint64_t v) const { *(volatile uint64_t*)p = v; }
+	__device__ uint8_t rd8(const uint8_t* p) const { return *(const volatile uint8_t*)p; }
+	__device__ void wr8(uint8_t* p, uint8_t v) const { *(volatile uint8_t*)p = v; }
+	__device__ void sync() const { __syncwarp(); }
+	__device__ bool find64(const uint64_t* a, unsigned n, uint64_t key, unsigned stride) const
+	{
+		for (unsigned base = 0; base < n; base += 32) {
+			const unsigned i = base + lane;
+			const bool hit = i < n && *(const volatile uint64_t*)(a + (size_t)i * stride) == key;
+			if (__any_sync(0xffffffffu, hit))
+				return true;
+		}
+		return false;
+	}
+	__device__ uint8_t* alloc(unsigned long long bytes, bool zero)
+	{
+		bytes = (bytes + 15) & ~15ULL;
+		unsigned long long off = 0;
+		if (lane == 0)
+			off = atomicAdd(arena_top, bytes);
+		off = __shfl_sync(0xffffffffu, off, 0);
+		if (off + bytes > arena_size) {
+			fail(3);
+			return nullptr;
+		}
+		uint8_t* p = arena + off;
+		if (zero) {
+			uint4* q = reinterpret_cast<uint4*>(p);
+			for (unsigned long long i = lane; i < bytes / 16; i += 32)
+				q[i] = make_uint4(0, 0, 0, 0);
+			__syncwarp();
+		}
+		return p;
+	}
+	__device__ void fail(unsigned why) { fail_ |= 1u << why; }
+	__device__ bool failed() const { return fail_ != 0; }
+	__device__ void copy8(uint8_t* d, const uint8_t* s, unsigned n) const
+	{
+		for (unsigned i = lane; i < n; i += 32)
+			d[i] = s[i];
+		__syncwarp();
+	}
+	__device__ void copy8_rev(uint8_t* d, const uint8_t* s, unsigned n) const
+	{
+		for (unsigned i = lane; i < n; i += 32)
+			d[i] = s[n - 1 - i];
+		__syncwarp();
+	}
+	__device__ void rehash(const uint64_t* o, unsigned ocap, uint64_t* nt, unsigned ncap) const
+	{
+		for (unsigned s = lane; s < ocap; s += 32) {
+			const uint64_t v = o[s];
+			if (v == 0)
+				continue;
+			uint64_t t = pathset_slot(v, ncap);
+			while (atomicCAS((unsigned long long*)(nt + t), 0ULL, (unsigned long long)v) != 0ULL)
+				t = (t + 1) & (ncap - 1);
+		}
+		__syncwarp();
+	}
+	__device__ void mark_covered(const PathSet& ps, const uint64_t* rh, uint8_t* cov, unsigned nk, const ContigOut& o) const
+	{
+		for (unsigned j = lane; j < nk; j += 32) {
+			if (cov[j])
+				continue;
+			const uint64_t key = rh[j];
+			if (!pathset_contains(*this, ps, key))
+				continue;
+			if ((o.popped_front && key == o.front_h) || (o.popped_back && key == o.back_h))
+				continue;
+			cov[j] = 1;
+		}
+		__syncwarp();
+	}
+};
+
+/** one unitig produced by K4 */
+struct ContigRec {
+	unsigned long long seq; // device pointer to 2-bit codes, one per byte
+	unsigned spec;          // index of the seeding read in the speculative set
+	unsigned ordinal;       // n-th contig of that read
+	unsigned len;
+	unsigned seed_pos;
+	unsigned psize;
+	unsigned char left, right, pad0, pad1;
+};
+
+struct DevEmit {
+	ContigRec* recs;
+	unsigned* nrecs;
+	unsigned cap;
+	unsigned spec, ordinal;
+	__device__ void operator()(WarpCtx& c, unsigned seed_pos, const ContigOut& o)
+	{
+		if (c.lane == 0) {
+			const unsigned idx = atomicAdd(nrecs, 1u);
+			if (idx < cap) {
+				ContigRec r;
+				r.seq = (unsigned long long)o.seq;
+				r.spec = spec;
+				r.ordinal = ordinal;
+				r.len = o.len;
+				r.seed_pos = seed_pos;
+				r.psize = o.psize;
+				r.left = (unsigned char)o.left;
+				r.right = (unsigned char)o.right;
+				r.pad0 = r.pad1 = 0;
+				recs[idx] = r;
+			}
+		}
+		++ordinal;
+	}
+};
+
+struct WalkCfg {
+	unsigned k, trim, threshold;
+	RollTab rt;
+	const uint8_t* counters;
+};
+
+__device__ __forceinline__ WarpCtx make_ctx(const WalkCfg& w, const HashCfg* cfg, Frame* frames, uint64_t* look, unsigned gwarp,
+                                            uint8_t* arena, unsigned long long arena_size, unsigned long long* arena_top)
+{
+	WarpCtx c;
+	c.k = w.k;
+	c.trim = w.trim;
+	c.rt = w.rt;
+	c.cfg = cfg;
+	c.counters = w.counters;
+	c.threshold = w.threshold;
+	c.lane = threadIdx.x & 31;
+	c.frames = frames ? frames + (size_t)gwarp * kFrameCap : nullptr;
+	c.look = look + (size_t)gwarp * kLookCap;
+	c.arena = arena;
+	c.arena_size = arena_size;
+	c.arena_top = arena_top;
+	c.fail_ = 0;
+	return c;
+}
+
+constexpr int kWalkWarps = 4; // warps per CTA for the walking kernels
+
+// ------------------------------------------------------------------------------------------
+// K3a: classify every read of the batch (processRead's tests, bloom-dbg.h:803-817)
+// ------------------------------------------------------------------------------------------
+template <int KW>
+__global__ void __launch_bounds__(kWalkWarps * 32)
+k_classify(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offs, const uint64_t* __restrict__ slot_offs,
+           const uint64_t* __restrict__ h0, const uint8_t* __restrict__ valid, uint64_t n_reads, WalkCfg w,
+           const __grid_constant__ HashCfg cfg, uint64_t* look, int exact_codes, uint8_t* __restrict__ codes)
+{
+	const unsigned gwarp = blockIdx.x * kWalkWarps + (threadIdx.x >> 5);
+	const unsigned nwarps = gridDim.x * kWalkWarps;
+	WarpCtx c = make_ctx(w, &cfg, nullptr, look, gwarp, nullptr, 0, nullptr);
+	const unsigned lane = c.lane;
+	for (uint64_t r = gwarp; r < n_reads; r += nwarps) {
+		const uint64_t beg = offs[r];
+		const unsigned L = (unsigned)(offs[r + 1] - beg);
+		uint8_t code;
+		if (L < w.k) {
+			code = RC_SHORTER_THAN_K;
+		} else {
+			const uint64_t s0 = slot_offs[r];
+			const unsigned nk = L - w.k + 1;
+			// allACGT(seq): every base of a read with L >= k lies in some window
+			bool bad = false;
+			for (unsigned j = lane; j < nk; j += 32)
+				bad |= valid[s0 + j] == 0;
+			if (__any_sync(0xffffffffu, bad)) {
+				code = RC_NON_ACGT;
+			} else {
+				// allKmersInBloom(seq, solidKmerSet) (bloom-dbg.h:60-78)
+				bool solid = true;
+				for (unsigned base = 0; base < nk && solid; base += 32) {
+					const unsigned j = base + lane;
+					bool ok = true;
+					if (j < nk) {
+						const uint64_t h = h0[s0 + j];
+						for (unsigned i = 0; i < cfg.H; ++i)
+							ok &= __ldcg(w.counters + nth_pos(h, cfg, i)) >= w.threshold;
+					}
+					solid = __all_sync(0xffffffffu, ok);
+				}
+				if (!solid && !exact_codes) {
+					code = RC_NOT_SOLID;
+				} else {
+					// hasBluntEnd (bloom-dbg.h:494-532): lookAhead(first k-mer, REVERSE, 5) on the read and on
+					// its reverse complement
+					const Vtx<KW> first = vtx_from_codes<KW>(bases + beg, w.k, true);
+					bool blunt = !look_ahead(c, first, REV, kFpTrim);
+					if (!blunt) {
+						const Vtx<KW> last = vtx_from_codes<KW>(bases + beg + L - w.k, w.k, true);
+						blunt = !look_ahead(c, vtx_revcomp(last, w.k), REV, kFpTrim);
+					}
+					code = blunt ? RC_BLUNT_END : (solid ? RC_CANDIDATE : RC_NOT_SOLID);
+				}
+			}
+		}
+		if (lane == 0)
+			codes[r] = code;
+	}
+}
+
+// ------------------------------------------------------------------------------------------
+// K3b: allKmersInBloom(seq, assembledKmerSet) for candidates cand[c0 .. c0+n) (bloom-dbg.h:823)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_visited(const unsigned* __restrict__ cand, unsigned c0, unsigned n, const uint64_t* __restrict__ slot_offs,
+          const uint64_t* __restrict__ h0, const __grid_constant__ HashCfg cfg, const uint8_t* __restrict__ bits,
+          uint8_t* __restrict__ out)
+{
+	const unsigned gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	if (gwarp >= n)
+		return;
+	const unsigned r = cand[c0 + gwarp];
+	const uint64_t s0 = slot_offs[r];
+	const unsigned nk = (unsigned)(slot_offs[r + 1] - s0);
+	bool all = true;
+	for (unsigned base = 0; base < nk && all; base += 32) {
+		const unsigned j = base + lane;
+		bool ok = true;
+		if (j < nk) {
+			const uint64_t h = h0[s0 + j];
+			for (unsigned i = 0; i < cfg.H; ++i) {
+				const uint64_t p = nth_pos(h, cfg, i);
+				ok &= (__ldcg(bits + (p >> 3)) >> (p & 7)) & 1;
+			}
+		}
+		all = __all_sync(0xffffffffu, ok);
+	}
+	if (lane == 0)
+		out[gwarp] = all;
+}
+
+// ------------------------------------------------------------------------------------------
+// K4: extend -- one warp per speculated read runs processRead's extension loop
+// ------------------------------------------------------------------------------------------
+template <int KW>
+__global__ void __launch_bounds__(kWalkWarps * 32)
+k_extend(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offs, const unsigned* __restrict__ spec, unsigned n_spec,
+         WalkCfg w, const __grid_constant__ HashCfg cfg, Frame* frames, uint64_t* look, uint8_t* arena,
+         unsigned long long arena_size, unsigned long long* arena_top, ContigRec* recs, unsigned* nrecs, unsigned rec_cap,
+         unsigned* __restrict__ status)
+{
+	const unsigned gwarp = blockIdx.x * kWalkWarps + (threadIdx.x >> 5);
+	if (gwarp >= n_spec)
+		return;
+	WarpCtx c = make_ctx(w, &cfg, frames, look, gwarp, arena, arena_size, arena_top);
+	const unsigned r = spec[gwarp];
+	const uint64_t beg = offs[r];
+	const unsigned L = (unsigned)(offs[r + 1] - beg);
+	DevEmit emit = { recs, nrecs, rec_cap, gwarp, 0 };
+	const bool ok = walk_read<KW>(c, bases + beg, L, emit);
+	if (c.lane == 0)
+		status[gwarp] = ok ? 0u : (c.fail_ ? c.fail_ : 1u);
+}
+
+/** dense ASCII copies of the ordered unitigs (pathToSeq output as characters) */
+__global__ void __launch_bounds__(256)
+k_gather(const ContigRec* __restrict__ recs, unsigned n, const uint64_t* __restrict__ coffs, uint8_t* __restrict__ out)
+{
+	for (unsigned c = blockIdx.x; c < n; c += gridDim.x) {
+		const uint8_t* s = reinterpret_cast<const uint8_t*>(recs[c].seq);
+		uint8_t* d = out + coffs[c];
+		for (unsigned i = threadIdx.x; i < recs[c].len; i += blockDim.x)
+			d[i] = "ACGT"[s[i] & 3];
+	}
+}
+
+// ------------------------------------------------------------------------------------------
+// K5: ordered replay by one CTA (outputContig, bloom-dbg.h:538-620, and the "visited" test :823)
+// ------------------------------------------------------------------------------------------
+struct EndSet { // KmerHash contigEndKmers (bloom-dbg.h:37-47,992-993), keyed by canonical hash
+	unsigned long long* tab;
+	unsigned cap; // power of two
+	unsigned* n;  // [0] entries, [1] has_zero
+};
+__device__ bool endset_contains(const EndSet& e, uint64_t key)
+{
+	if (key == 0)
+		return e.n[1] != 0;
+	for (uint64_t s = pathset_slot(key, e.cap);; s = (s + 1) & (e.cap - 1)) {
+		const unsigned long long v = e.tab[s];
+		if (v == key)
+			return true;
+		if (v == 0)
+			return false;
+	}
+}
+__device__ void endset_insert(const EndSet& e, uint64_t key)
+{
+	if (key == 0) {
+		e.n[1] = 1;
+		return;
+	}
+	for (uint64_t s = pathset_slot(key, e.cap);; s = (s + 1) & (e.cap - 1)) {
+		const unsigned long long v = e.tab[s];
+		if (v == key)
+			return;
+		if (v == 0) {
+			e.tab[s] = key;
+			++e.n[0];
+			return;
+		}
+	}
+}
+__global__ void k_endset_rehash(const unsigned long long* o, unsigned ocap, unsigned long long* nt, unsigned ncap)
+{
+	for (unsigned s = blockIdx.x * blockDim.x + threadIdx.x; s < ocap; s += gridDim.x * blockDim.x) {
+		const unsigned long long v = o[s];
+		if (v == 0)
+			continue;
+		uint64_t t = pathset_slot(v, ncap);
+		while (atomicCAS(nt + t, 0ULL, v) != 0ULL)
+			t = (t + 1) & (ncap - 1);
+	}
+}
+
+struct ReplayIO {
+	// speculated reads, in file order
+	const unsigned* spec;        // read index in the batch
+	const unsigned* spec_cbeg;   // [n_spec + 1] first contig of each read
+	unsigned n_spec;
+	// reads
+	const uint64_t* slot_offs;
+	const uint64_t* h0;
+	// contigs (ordered)
+	const uint64_t* cslot;       // [n_contigs + 1] k-mer slot offsets into ch0
+	const uint64_t* ch0;
+	const unsigned* clen;
+	// outputs
+	uint8_t* rcode;              // per speculated read: RC_ALL_KMERS_VISITED or RC_GENERATED_CONTIGS
+	uint8_t* caccept;            // per contig: 1 = printed
+	unsigned* ccov;              // per contig: coverage
+};
+
+__global__ void __launch_bounds__(1024)
+k_replay(ReplayIO io, const __grid_constant__ HashCfg cfg, unsigned k, const uint8_t* __restrict__ counters, uint8_t* bits,
+         EndSet ends)
+{
+	__shared__ unsigned s_cov;
+	__shared__ int s_flag;
+	const unsigned tid = threadIdx.x, nt = blockDim.x;
+	for (unsigned s = 0; s < io.n_spec; ++s) {
+		const unsigned r = io.spec[s];
+		const uint64_t rs0 = io.slot_offs[r];
+		const unsigned rnk = (unsigned)(io.slot_offs[r + 1] - rs0);
+		// skip reads in previously assembled regions (bloom-dbg.h:823-827)
+		int all = 1;
+		for (unsigned base = 0; base < rnk && all; base += nt) {
+			const unsigned j = base + tid;
+			int ok = 1;
+			if (j < rnk) {
+				const uint64_t h = io.h0[rs0 + j];
+				for (unsigned i = 0; i < cfg.H; ++i) {
+					const uint64_t p = nth_pos(h, cfg, i);
+					ok &= (__ldcg(bits + (p >> 3)) >> (p & 7)) & 1;
+				}
+			}
+			all = __syncthreads_and(ok);
+		}
+		if (all) {
+			if (tid == 0)
+				io.rcode[s] = RC_ALL_KMERS_VISITED;
+			continue;
+		}
+		if (tid == 0)
+			io.rcode[s] = RC_GENERATED_CONTIGS;
+		for (unsigned c = io.spec_cbeg[s]; c < io.spec_cbeg[s + 1]; ++c) {
+			const uint64_t c0 = io.cslot[c];
+			const unsigned nk = (unsigned)(io.cslot[c + 1] - c0);
+			const unsigned len = io.clen[c];
+			int redundant;
+			if (len < k + kFpTrim - 1) {
+				// very short contigs: exact table of end k-mers (bloom-dbg.h:576-586)
+				if (tid == 0) {
+					const uint64_t v1 = io.ch0[c0], v2 = io.ch0[c0 + nk - 1];
+					int red = endset_contains(ends, v1) && endset_contains(ends, v2);
+					if (!red) {
+						endset_insert(ends, v1);
+						endset_insert(ends, v2);
+					}
+					s_flag = red;
+				}
+				__syncthreads();
+				redundant = s_flag;
+				__syncthreads();
+			} else {
+				redundant = 1; // allKmersInBloom(seq, assembledKmerSet) (bloom-dbg.h:588)
+				for (unsigned base = 0; base < nk && redundant; base += nt) {
+					const unsigned j = base + tid;
+					int ok = 1;
+					if (j < nk) {
+						const uint64_t h = io.ch0[c0 + j];
+						for (unsigned i = 0; i < cfg.H; ++i) {
+							const uint64_t p = nth_pos(h, cfg, i);
+							ok &= (__ldcg(bits + (p >> 3)) >> (p & 7)) & 1;
+						}
+					}
+					redundant = __syncthreads_and(ok);
+				}
+			}
+			if (redundant) {
+				if (tid == 0)
+					io.caccept[c] = 0;
+				continue;
+			}
+			// addKmersToBloom(seq, assembledKmerSet) + getSeqAbsoluteKmerCoverage (bloom-dbg.h:83-109,594-602)
+			if (tid == 0)
+				s_cov = 0;
+			__syncthreads();
+			unsigned cov = 0;
+			for (unsigned j = tid; j < nk; j += nt) {
+				const uint64_t h = io.ch0[c0 + j];
+				unsigned mn = 255;
+				for (unsigned i = 0; i < cfg.H; ++i) {
+					const uint64_t p = nth_pos(h, cfg, i);
+					const uint64_t byte = p >> 3;
+					atomicOr(reinterpret_cast<unsigned*>(bits + (byte & ~3ULL)), 1u << ((p & 7) + 8 * (byte & 3)));
+					mn = min(mn, (unsigned)__ldcg(counters + p));
+				}
+				cov += mn;
+			}
+			for (int d = 16; d; d >>= 1)
+				cov += __shfl_down_sync(0xffffffffu, cov, d);
+			if ((tid & 31) == 0 && cov)
+				atomicAdd(&s_cov, cov);
+			__threadfence();
+			__syncthreads();
+			if (tid == 0) {
+				io.caccept[c] = 1;
+				io.ccov[c] = s_cov;
+			}
+			__syncthreads();
+		}
+	}
+}
+
+} // namespace abb
+
+using namespace abb;
+
+// =============================================================================================
+// host side
+// =============================================================================================
 struct abb_assembler {
 	abb_filter* solid = nullptr;
+	abb_filter* assembled = nullptr;
 	abb_assembly_params params = {};
 	abb_assembly_counters counters = {};
+	cudaStream_t stream = nullptr;
+	uint64_t reads_seen = 0;
+	int kw = 0;
+
+	// batch state (device)
+	DevBuf<uint8_t> bases, valid, codes, vis, scan_tmp, cseq, cvalid, rcode, caccept;
+	DevBuf<uint64_t> offs, slot_offs, h0, coffs, cslot, ch0;
+	DevBuf<unsigned> cand, spec, spec_cbeg, clen, ccov, status;
+	DevBuf<ContigRec> recs, recs_sorted;
+	DevBuf<Frame> frames;
+	DevBuf<uint64_t> look;
+	unsigned scratch_warps = 0;
+	uint8_t* d_arena = nullptr;
+	unsigned long long arena_size = 0;
+	unsigned long long* d_arena_top = nullptr;
+	unsigned* d_nrecs = nullptr;
+	// contigEndKmers
+	unsigned long long* d_ends = nullptr;
+	unsigned ends_cap = 0;
+	unsigned* d_ends_n = nullptr;
+	uint64_t ends_upper = 0; // upper bound on entries
+
+	// speculation control
+	unsigned spec_target = 256;
+	// host outputs of the last batch
+	std::vector<abb_contig> out_contigs;
+	std::vector<char> out_seqs;
+	std::vector<uint8_t> out_codes;
+	// statistics
+	uint64_t st_iterations = 0, st_speculated = 0, st_wasted = 0, st_launches = 0;
 };
+
+namespace {
+
+constexpr unsigned kMaxSpec = 4096;
+constexpr unsigned long long kArenaDefault = 2ULL << 30;
+constexpr unsigned long long kArenaMax = 64ULL << 30;
+
+int ensure_scratch(abb_assembler* a, unsigned warps)
+{
+	if (warps <= a->scratch_warps)
+		return ABB_OK;
+	ABB_CHECK(a->frames.reserve((size_t)warps * kFrameCap));
+	ABB_CHECK(a->look.reserve((size_t)warps * kLookCap));
+	a->scratch_warps = warps;
+	return ABB_OK;
+}
+
+int ensure_arena(abb_assembler* a, unsigned long long bytes)
+{
+	if (a->d_arena && a->arena_size >= bytes)
+		return ABB_OK;
+	if (a->d_arena)
+		cudaFree(a->d_arena);
+	a->d_arena = nullptr;
+	a->arena_size = 0;
+	ABB_CUDA(cudaMalloc((void**)&a->d_arena, bytes));
+	a->arena_size = bytes;
+	return ABB_OK;
+}
+
+int ensure_endset(abb_assembler* a, uint64_t extra)
+{
+	const uint64_t need = (a->ends_upper + extra) * 2 + 16;
+	if (a->d_ends && need <= a->ends_cap)
+		return ABB_OK;
+	uint64_t ncap = a->ends_cap ? a->ends_cap : 1024;
+	while (ncap < need)
+		ncap <<= 1;
+	ABB_REQUIRE(ncap <= (1ULL << 31), "contigEndKmers table too large");
+	unsigned long long* nt = nullptr;
+	ABB_CUDA(cudaMalloc((void**)&nt, ncap * sizeof(unsigned long long)));
+	ABB_CUDA(cudaMemsetAsync(nt, 0, ncap * sizeof(unsigned long long), a->stream));
+	if (a->d_ends) {
+		k_endset_rehash<<<256, 256, 0, a->stream>>>(a->d_ends, a->ends_cap, nt, (unsigned)ncap);
+		ABB_CUDA(cudaGetLastError());
+		ABB_CUDA(cudaStreamSynchronize(a->stream));
+		cudaFree(a->d_ends);
+	}
+	a->d_ends = nt;
+	a->ends_cap = (unsigned)ncap;
+	return ABB_OK;
+}
+
+WalkCfg walk_cfg(const abb_assembler* a)
+{
+	WalkCfg w;
+	w.k = a->solid->k;
+	w.trim = a->params.trim;
+	w.threshold = a->solid->threshold;
+	w.rt = make_rolltab(a->solid->k);
+	w.counters = a->solid->d_data;
+	return w;
+}
+
+#define ABB_DISPATCH_KW(kw, ...)              \
+	do {                                      \
+		switch (kw) {                         \
+		case 1: { constexpr int KW = 1; __VA_ARGS__; } break; \
+		case 2: { constexpr int KW = 2; __VA_ARGS__; } break; \
+		case 3: { constexpr int KW = 3; __VA_ARGS__; } break; \
+		case 4: { constexpr int KW = 4; __VA_ARGS__; } break; \
+		default: { constexpr int KW = 6; __VA_ARGS__; } break; \
+		}                                     \
+	} while (0)
+
+template <typename T>
+int h2d(DevBuf<T>& d, const std::vector<T>& h, cudaStream_t s)
+{
+	ABB_CHECK(d.reserve(h.size() + 1));
+	if (!h.empty())
+		ABB_CUDA(cudaMemcpyAsync(d.p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+	return ABB_OK;
+}
+
+/** one speculation round over candidates starting at *cursor; appends accepted contigs */
+int speculate_round(abb_assembler* a, const std::vector<unsigned>& cand, size_t* cursor, uint64_t n_reads)
+{
+	abb_filter* f = a->solid;
+	cudaStream_t st = a->stream;
+	const size_t ncand = cand.size();
+	// ---- K3b over a chunk of candidates; pick the first spec_target uncovered ones
+	std::vector<unsigned> spec;
+	size_t pos = *cursor;
+	size_t chunk = std::max<size_t>(a->spec_target, 1024);
+	while (pos < ncand && spec.size() < a->spec_target) {
+		const unsigned n = (unsigned)std::min(chunk, ncand - pos);
+		ABB_CHECK(a->vis.reserve(n));
+		k_visited<<<blocks_for((uint64_t)n * 32, 256), 256, 0, st>>>(a->cand.p, (unsigned)pos, n, a->slot_offs.p, a->h0.p, f->cfg,
+		                                                            a->assembled->d_data, a->vis.p);
+		ABB_CUDA(cudaGetLastError());
+		++a->st_launches;
+		std::vector<uint8_t> vis(n);
+		ABB_CUDA(cudaMemcpyAsync(vis.data(), a->vis.p, n, cudaMemcpyDeviceToHost, st));
+		ABB_CUDA(cudaStreamSynchronize(st));
+		size_t i = 0;
+		for (; i < n && spec.size() < a->spec_target; ++i) {
+			if (vis[i]) {
+				a->out_codes[cand[pos + i]] = RC_ALL_KMERS_VISITED;
+				++a->counters.visited_reads;
+			} else
+				spec.push_back(cand[pos + i]);
+		}
+		pos += i;
+		chunk = std::min<size_t>(chunk * 4, 1u << 22);
+	}
+	*cursor = pos;
+	if (spec.empty())
+		return ABB_OK;
+	++a->st_iterations;
+	a->st_speculated += spec.size();
+
+	// ---- K4: extend all speculated reads
+	const unsigned n_spec = (unsigned)spec.size();
+	ABB_CHECK(h2d(a->spec, spec, st));
+	ABB_CHECK(ensure_scratch(a, n_spec));
+	ABB_CHECK(a->status.reserve(n_spec));
+	unsigned rec_cap = std::max<unsigned>(n_spec * 8, 4096);
+	std::vector<ContigRec> recs;
+	std::vector<unsigned> status(n_spec);
+	unsigned n_ok = n_spec; // speculated reads [0, n_ok) completed
+	for (;;) {
+		ABB_CHECK(a->recs.reserve(rec_cap));
+		ABB_CHECK(ensure_arena(a, a->arena_size ? a->arena_size : kArenaDefault));
+		ABB_CUDA(cudaMemsetAsync(a->d_arena_top, 0, sizeof(unsigned long long), st));
+		ABB_CUDA(cudaMemsetAsync(a->d_nrecs, 0, sizeof(unsigned), st));
+		const WalkCfg w = walk_cfg(a);
+		ABB_DISPATCH_KW(a->kw, (k_extend<KW><<<blocks_for(n_spec, kWalkWarps), kWalkWarps * 32, 0, st>>>(
+		                           a->bases.p, a->offs.p, a->spec.p, n_spec, w, f->cfg, a->frames.p, a->look.p, a->d_arena, a->arena_size,
+		                           a->d_arena_top, a->recs.p, a->d_nrecs, rec_cap, a->status.p)));
+		ABB_CUDA(cudaGetLastError());
+		++a->st_launches;
+		unsigned nrecs = 0;
+		ABB_CUDA(cudaMemcpyAsync(&nrecs, a->d_nrecs, sizeof nrecs, cudaMemcpyDeviceToHost, st));
+		ABB_CUDA(cudaMemcpyAsync(status.data(), a->status.p, n_spec * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+		ABB_CUDA(cudaStreamSynchronize(st));
+		if (nrecs > rec_cap) { // record buffer too small: rerun with room for everything
+			rec_cap = nrecs + nrecs / 4 + 16;
+			continue;
+		}
+		n_ok = n_spec;
+		for (unsigned i = 0; i < n_spec; ++i)
+			if (status[i] != 0) {
+				n_ok = i;
+				break;
+			}
+		if (n_ok == 0) {
+			// the very first read ran out of scratch: give it a bigger arena and try again
+			if (status[0] & ((1u << 1) | (1u << 2))) {
+				set_error("graph traversal exceeded the per-warp scratch bounds (lookAhead %u / trueBranch %u frames)", kLookCap, kFrameCap);
+				return ABB_ENOMEM;
+			}
+			const unsigned long long bigger = a->arena_size * 2;
+			if (bigger > kArenaMax) {
+				set_error("unitig scratch arena would exceed %llu bytes", kArenaMax);
+				return ABB_ENOMEM;
+			}
+			ABB_CHECK(ensure_arena(a, bigger));
+			continue;
+		}
+		recs.resize(nrecs);
+		if (nrecs)
+			ABB_CUDA(cudaMemcpyAsync(recs.data(), a->recs.p, nrecs * sizeof(ContigRec), cudaMemcpyDeviceToHost, st));
+		ABB_CUDA(cudaStreamSynchronize(st));
+		break;
+	}
+	if (n_ok < n_spec) {
+		// reads from the first failure on go back to the queue; speculate less next time.
+		// Candidates after the failed read that this round already labelled "visited" are re-examined
+		// when the scan resumes there (monotone, so the label will be the same): undo the bookkeeping.
+		const unsigned failed_read = spec[n_ok];
+		const size_t p = std::lower_bound(cand.begin(), cand.end(), failed_read) - cand.begin();
+		for (size_t i = p; i < *cursor; ++i)
+			if (a->out_codes[cand[i]] == RC_ALL_KMERS_VISITED) {
+				a->out_codes[cand[i]] = RC_CANDIDATE;
+				--a->counters.visited_reads;
+			}
+		*cursor = p;
+		a->spec_target = std::max(1u, n_ok);
+		spec.resize(n_ok);
+	}
+
+	// ---- order the records: by speculated read, then by ordinal; drop those of abandoned reads
+	recs.erase(std::remove_if(recs.begin(), recs.end(), [&](const ContigRec& r) { return r.spec >= n_ok; }), recs.end());
+	std::sort(recs.begin(), recs.end(), [](const ContigRec& x, const ContigRec& y) {
+		return x.spec != y.spec ? x.spec < y.spec : x.ordinal < y.ordinal;
+	});
+	const unsigned nc = (unsigned)recs.size();
+	std::vector<unsigned> spec_cbeg(n_ok + 1, 0), clen(nc);
+	std::vector<uint64_t> coffs(nc + 1, 0), cslot(nc + 1, 0);
+	for (unsigned c = 0; c < nc; ++c) {
+		++spec_cbeg[recs[c].spec + 1];
+		clen[c] = recs[c].len;
+		coffs[c + 1] = coffs[c] + recs[c].len;
+		cslot[c + 1] = cslot[c] + (recs[c].len - f->k + 1);
+	}
+	for (unsigned s = 0; s < n_ok; ++s)
+		spec_cbeg[s + 1] += spec_cbeg[s];
+
+	std::vector<uint8_t> rcode(n_ok), caccept(nc);
+	std::vector<unsigned> ccov(nc);
+	std::vector<char> seqs(coffs[nc]);
+	{
+		ABB_CHECK(h2d(a->recs_sorted, recs, st));
+		ABB_CHECK(h2d(a->spec_cbeg, spec_cbeg, st));
+		ABB_CHECK(h2d(a->clen, clen, st));
+		ABB_CHECK(h2d(a->coffs, coffs, st));
+		ABB_CHECK(h2d(a->cslot, cslot, st));
+		ABB_CHECK(a->cseq.reserve(coffs[nc] + 16));
+		ABB_CHECK(a->ch0.reserve(cslot[nc] + 1));
+		ABB_CHECK(a->cvalid.reserve(cslot[nc] + 1));
+		ABB_CHECK(a->rcode.reserve(n_ok));
+		ABB_CHECK(a->caccept.reserve(nc + 1));
+		ABB_CHECK(a->ccov.reserve(nc + 1));
+		if (nc) {
+			k_gather<<<std::min<unsigned>(nc, 148 * 8), 256, 0, st>>>(a->recs_sorted.p, nc, a->coffs.p, a->cseq.p);
+			ABB_CUDA(cudaGetLastError());
+			ABB_CHECK(launch_hash(nullptr, f->k, nullptr, a->cseq.p, a->coffs.p, a->cslot.p, 0, nc, 0, a->ch0.p, a->cvalid.p, st, nullptr));
+			a->st_launches += 2;
+		}
+		ABB_CHECK(ensure_endset(a, 2ull * nc));
+		a->ends_upper += 2ull * nc;
+		ReplayIO io;
+		io.spec = a->spec.p;
+		io.spec_cbeg = a->spec_cbeg.p;
+		io.n_spec = n_ok;
+		io.slot_offs = a->slot_offs.p;
+		io.h0 = a->h0.p;
+		io.cslot = a->cslot.p;
+		io.ch0 = a->ch0.p;
+		io.clen = a->clen.p;
+		io.rcode = a->rcode.p;
+		io.caccept = a->caccept.p;
+		io.ccov = a->ccov.p;
+		EndSet ends = { a->d_ends, a->ends_cap, a->d_ends_n };
+		k_replay<<<1, 1024, 0, st>>>(io, f->cfg, f->k, f->d_data, a->assembled->d_data, ends);
+		ABB_CUDA(cudaGetLastError());
+		++a->st_launches;
+		ABB_CUDA(cudaMemcpyAsync(rcode.data(), a->rcode.p, n_ok, cudaMemcpyDeviceToHost, st));
+		if (nc) {
+			ABB_CUDA(cudaMemcpyAsync(caccept.data(), a->caccept.p, nc, cudaMemcpyDeviceToHost, st));
+			ABB_CUDA(cudaMemcpyAsync(ccov.data(), a->ccov.p, nc * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+			ABB_CUDA(cudaMemcpyAsync(seqs.data(), a->cseq.p, coffs[nc], cudaMemcpyDeviceToHost, st));
+		}
+		ABB_CUDA(cudaStreamSynchronize(st));
+	}
+
+	// ---- collect
+	unsigned wasted = 0;
+	for (unsigned s = 0; s < n_ok; ++s) {
+		a->out_codes[spec[s]] = rcode[s];
+		if (rcode[s] == RC_ALL_KMERS_VISITED) {
+			++a->counters.visited_reads;
+			++wasted;
+			continue;
+		}
+		for (unsigned c = spec_cbeg[s]; c < spec_cbeg[s + 1]; ++c) {
+			if (!caccept[c])
+				continue;
+			abb_contig oc;
+			oc.seed_read = a->reads_seen + spec[s];
+			oc.seq_offset = a->out_seqs.size();
+			oc.length = clen[c];
+			oc.coverage = ccov[c];
+			a->out_contigs.push_back(oc);
+			a->out_seqs.insert(a->out_seqs.end(), seqs.begin() + coffs[c], seqs.begin() + coffs[c] + clen[c]);
+			a->out_seqs.push_back('\0');
+			++a->counters.contig_id;
+			a->counters.bases_assembled += clen[c];
+		}
+	}
+	a->st_wasted += wasted;
+	// adapt the amount of speculation: grow while most speculated reads were really needed
+	if (n_ok == n_spec) {
+		if (wasted * 4 <= n_ok)
+			a->spec_target = std::min(kMaxSpec, a->spec_target * 2);
+		else if (wasted * 2 > n_ok)
+			a->spec_target = std::max(32u, a->spec_target / 2);
+	}
+	(void)n_reads;
+	return ABB_OK;
+}
+
+} // namespace
 
 extern "C" {
 
@@ -14,26 +852,155 @@ int abb_assembler_create(abb_assembler** out, abb_filter* solid, const abb_assem
 {
 	ABB_REQUIRE(out && solid && params, "NULL argument");
 	*out = nullptr;
-	abb::set_error("abb_assembler_create: pass 2 is not implemented in this build");
-	return ABB_ESTATE;
+	if (solid->kind != ABB_COUNTING) {
+		set_error("the assembler needs a counting filter (CountingBloomFilter<uint8_t>), like abyss-bloom-dbg");
+		return ABB_ESTATE;
+	}
+	if (!solid->mask.empty()) {
+		set_error("spaced seeds are not supported by the unitig extension stage yet");
+		return ABB_ESTATE;
+	}
+	ABB_REQUIRE(solid->k >= 2, "k must be at least 2 for graph traversal");
+	ABB_CUDA(cudaSetDevice(solid->device));
+	abb_assembler* a = new (std::nothrow) abb_assembler();
+	if (!a) {
+		set_error("out of host memory");
+		return ABB_ENOMEM;
+	}
+	a->solid = solid;
+	a->params = *params;
+	if (a->params.trim == 0xffffffffu)
+		a->params.trim = solid->k; // bloom-dbg.cc:518-520
+	a->kw = (int)((2 * solid->k + 63) / 64);
+	// BloomFilter assembledKmerSet(solid.size(), solid.getHashNum(), solid.getKmerSize()) (bloom-dbg.h:910-911)
+	int rc = abb_filter_create(&a->assembled, ABB_BIT, solid->size, solid->H, solid->k, 0, "", solid->device);
+	if (rc != ABB_OK) {
+		delete a;
+		return rc;
+	}
+	auto fail = [&](cudaError_t e, const char* what) {
+		set_error("%s: %s", what, cudaGetErrorString(e));
+		abb_assembler_destroy(a);
+		return e == cudaErrorMemoryAllocation ? ABB_ENOMEM : ABB_ECUDA;
+	};
+	cudaError_t e;
+	if ((e = cudaStreamCreateWithFlags(&a->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
+	if ((e = cudaMalloc((void**)&a->d_arena_top, sizeof(unsigned long long))) != cudaSuccess) return fail(e, "cudaMalloc");
+	if ((e = cudaMalloc((void**)&a->d_nrecs, sizeof(unsigned))) != cudaSuccess) return fail(e, "cudaMalloc");
+	if ((e = cudaMalloc((void**)&a->d_ends_n, 2 * sizeof(unsigned))) != cudaSuccess) return fail(e, "cudaMalloc");
+	if ((e = cudaMemset(a->d_ends_n, 0, 2 * sizeof(unsigned))) != cudaSuccess) return fail(e, "cudaMemset");
+	*out = a;
+	return ABB_OK;
 }
-int abb_assembler_destroy(abb_assembler* a) { delete a; return ABB_OK; }
-int abb_assembler_process_reads(abb_assembler*, const char*, const uint64_t*, uint64_t, const abb_contig**, uint64_t*, const char**)
+
+int abb_assembler_destroy(abb_assembler* a)
 {
-	abb::set_error("pass 2 is not implemented in this build");
-	return ABB_ESTATE;
+	if (!a)
+		return ABB_OK;
+	if (a->solid)
+		cudaSetDevice(a->solid->device);
+	if (a->stream)
+		cudaStreamSynchronize(a->stream);
+	abb_filter_destroy(a->assembled);
+	a->bases.release(); a->valid.release(); a->codes.release(); a->vis.release(); a->scan_tmp.release();
+	a->cseq.release(); a->cvalid.release(); a->rcode.release(); a->caccept.release();
+	a->offs.release(); a->slot_offs.release(); a->h0.release(); a->coffs.release(); a->cslot.release(); a->ch0.release();
+	a->cand.release(); a->spec.release(); a->spec_cbeg.release(); a->clen.release(); a->ccov.release(); a->status.release();
+	a->recs.release(); a->recs_sorted.release(); a->frames.release(); a->look.release();
+	cudaFree(a->d_arena);
+	cudaFree(a->d_arena_top);
+	cudaFree(a->d_nrecs);
+	cudaFree(a->d_ends);
+	cudaFree(a->d_ends_n);
+	if (a->stream)
+		cudaStreamDestroy(a->stream);
+	delete a;
+	return ABB_OK;
 }
+
+int abb_assembler_process_reads(abb_assembler* a, const char* bases, const uint64_t* offsets, uint64_t n_reads,
+                                const abb_contig** contigs, uint64_t* n_contigs, const char** seqs)
+{
+	ABB_REQUIRE(a, "NULL assembler");
+	a->out_contigs.clear();
+	a->out_seqs.clear();
+	a->out_codes.assign(n_reads, RC_SHORTER_THAN_K);
+	if (contigs) *contigs = nullptr;
+	if (n_contigs) *n_contigs = 0;
+	if (seqs) *seqs = nullptr;
+	if (n_reads == 0)
+		return ABB_OK;
+	ABB_REQUIRE(bases && offsets, "NULL read buffers");
+	ABB_REQUIRE(offsets[0] == 0, "offsets[0] must be 0");
+	ABB_REQUIRE(n_reads < (1ULL << 32), "at most 2^32-1 reads per batch");
+	abb_filter* f = a->solid;
+	cudaStream_t st = a->stream;
+	ABB_CUDA(cudaSetDevice(f->device));
+	// the filters may have been written on their own streams
+	ABB_CUDA(cudaStreamSynchronize(f->stream));
+	ABB_CUDA(cudaStreamSynchronize(a->assembled->stream));
+
+	const uint64_t n_bases = offsets[n_reads];
+	ABB_CHECK(a->bases.reserve(n_bases + 16));
+	ABB_CHECK(a->offs.reserve(n_reads + 1));
+	ABB_CUDA(cudaMemcpyAsync(a->bases.p, bases, n_bases, cudaMemcpyHostToDevice, st));
+	ABB_CUDA(cudaMemcpyAsync(a->offs.p, offsets, (n_reads + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+	uint64_t total = 0;
+	ABB_CHECK(compute_slot_offsets(f->k, a->offs.p, n_reads, a->slot_offs, a->scan_tmp, st, &total, &a->st_launches));
+	ABB_CHECK(a->h0.reserve(total + 1));
+	ABB_CHECK(a->valid.reserve(total + 1));
+	ABB_CHECK(a->codes.reserve(n_reads));
+	if (total)
+		ABB_CHECK(launch_hash(nullptr, f->k, nullptr, a->bases.p, a->offs.p, a->slot_offs.p, 0, n_reads, 0, a->h0.p, a->valid.p, st,
+		                      &a->st_launches));
+	// ---- K3a
+	int sms = 148;
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, f->device);
+	const unsigned grid = (unsigned)std::min<uint64_t>(blocks_for(n_reads, kWalkWarps), (uint64_t)sms * 8);
+	ABB_CHECK(ensure_scratch(a, grid * kWalkWarps));
+	const WalkCfg w = walk_cfg(a);
+	ABB_DISPATCH_KW(a->kw, (k_classify<KW><<<grid, kWalkWarps * 32, 0, st>>>(a->bases.p, a->offs.p, a->slot_offs.p, a->h0.p, a->valid.p,
+	                                                                        n_reads, w, f->cfg, a->look.p, (int)a->params.read_log,
+	                                                                        a->codes.p)));
+	ABB_CUDA(cudaGetLastError());
+	++a->st_launches;
+	ABB_CUDA(cudaMemcpyAsync(a->out_codes.data(), a->codes.p, n_reads, cudaMemcpyDeviceToHost, st));
+	ABB_CUDA(cudaStreamSynchronize(st));
+
+	std::vector<unsigned> cand;
+	for (uint64_t r = 0; r < n_reads; ++r)
+		if (a->out_codes[r] == RC_CANDIDATE)
+			cand.push_back((unsigned)r);
+	a->counters.solid_reads += cand.size();
+	ABB_CHECK(h2d(a->cand, cand, st));
+
+	size_t cursor = 0;
+	while (cursor < cand.size())
+		ABB_CHECK(speculate_round(a, cand, &cursor, n_reads));
+
+	a->counters.reads_processed += n_reads;
+	a->reads_seen += n_reads;
+	if (contigs) *contigs = a->out_contigs.data();
+	if (n_contigs) *n_contigs = a->out_contigs.size();
+	if (seqs) *seqs = a->out_seqs.data();
+	return ABB_OK;
+}
+
 int abb_assembler_counters(const abb_assembler* a, abb_assembly_counters* out)
 {
 	ABB_REQUIRE(a && out, "NULL argument");
 	*out = a->counters;
 	return ABB_OK;
 }
-int abb_assembler_read_results(const abb_assembler*, const uint8_t**, uint64_t*)
+
+int abb_assembler_read_results(const abb_assembler* a, const uint8_t** codes, uint64_t* n)
 {
-	abb::set_error("pass 2 is not implemented in this build");
-	return ABB_ESTATE;
+	ABB_REQUIRE(a && codes && n, "NULL argument");
+	*codes = a->out_codes.data();
+	*n = a->out_codes.size();
+	return ABB_OK;
 }
-abb_filter* abb_assembler_assembled_filter(abb_assembler*) { return nullptr; }
+
+abb_filter* abb_assembler_assembled_filter(abb_assembler* a) { return a ? a->assembled : nullptr; }
 
 } // extern "C"

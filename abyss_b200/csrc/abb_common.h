@@ -66,7 +66,21 @@ struct DevBuf {
 
 inline unsigned blocks_for(uint64_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
 
+// host helpers implemented in abb_api.cu, shared with abb_assemble.cu
+int select_device(int device);
+/** slot_offs[0..n_reads] = exclusive prefix sum of per-read k-mer window counts; *total = sum */
+int compute_slot_offsets(unsigned k, const uint64_t* d_offs, uint64_t n_reads, DevBuf<uint64_t>& slot_offs,
+                         DevBuf<uint8_t>& tmp, cudaStream_t stream, uint64_t* total, uint64_t* launches);
+
 } // namespace abb
+
+struct abb_filter;
+namespace abb {
+/** K1 for reads [r0, r1): h0/valid index = slot_offs[r] + j - slot_base */
+int launch_hash(abb_filter* f, unsigned k, const uint8_t* d_care, const uint8_t* d_bases, const uint64_t* d_offs,
+                const uint64_t* d_slot_offs, uint64_t r0, uint64_t r1, uint64_t slot_base, uint64_t* d_h0, uint8_t* d_valid,
+                cudaStream_t stream, uint64_t* launches);
+}
 
 /** The filter handle (opaque in the C ABI). */
 struct abb_filter {

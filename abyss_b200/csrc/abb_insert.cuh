@@ -175,7 +175,7 @@ ABB_D uint64_t shfl64(uint64_t v, int src)
  * P_i = XOR_{t<=i} R^{-t}(seed(c_t)), Q_i = XOR_{t<=i} R^{t}(seed(comp c_t)):
  *   fwd(j) = R^{j+k-1}(P_{j+k-1} ^ P_{j-1}),  rc(j) = R^{-j}(Q_{j+k-1} ^ Q_{j-1}).
  */
-__global__ void __launch_bounds__(kHashWarps * 32)
+static __global__ void __launch_bounds__(kHashWarps * 32)
 k_hash_reads(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offs,
              const uint64_t* __restrict__ slot_offs, uint64_t slot_base, uint64_t n_reads, unsigned k,
              uint64_t* __restrict__ h0_out, uint8_t* __restrict__ valid_out)
@@ -249,7 +249,7 @@ k_hash_reads(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ off
 /** spaced-seed variant: canonical hash over the '1' positions only (maskHash, nthash.hpp:537-547;
  *  a window is bad only if a non-ACGT base sits on a '1' position, RollingHashIterator.h:58-73).
  *  One warp per read, lanes stride over windows; O(k) per window (config 4 path). */
-__global__ void __launch_bounds__(kHashWarps * 32)
+static __global__ void __launch_bounds__(kHashWarps * 32)
 k_hash_reads_masked(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offs,
                     const uint64_t* __restrict__ slot_offs, uint64_t slot_base, uint64_t n_reads, unsigned k,
                     const uint8_t* __restrict__ care /* k bytes: 1 where mask == '1' */,
@@ -284,7 +284,7 @@ k_hash_reads_masked(const uint8_t* __restrict__ bases, const uint64_t* __restric
 }
 
 /** per-read window counts -> (exclusive scan done by the caller with cub-free two-pass code) */
-__global__ void k_window_counts(const uint64_t* __restrict__ offs, uint64_t n_reads, unsigned k,
+static __global__ void k_window_counts(const uint64_t* __restrict__ offs, uint64_t n_reads, unsigned k,
                                 uint64_t* __restrict__ counts)
 {
 	uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -538,7 +538,7 @@ k_query(const uint64_t* __restrict__ hashes, uint64_t n, HashCfg cfg, FilterView
 }
 
 /** popCount / filtered_popcount (CountingBloomFilter.hpp:219-244) and getPop (BloomFilter.hpp:313-320) */
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 k_popcount(const uint8_t* __restrict__ data, uint64_t nbytes, int counting, unsigned threshold,
            unsigned long long* __restrict__ out /* [2] */)
 {

@@ -119,6 +119,9 @@ int abb_filter_popcount(abb_filter* f, uint64_t* nonzero, uint64_t* at_or_above_
 typedef struct abb_assembly_params {
 	unsigned trim;      /* AssemblyParams::trim (AssemblyParams.h:67), default k */
 	unsigned verbose;
+	unsigned read_log;  /* 1: per-read outcome codes are exact (`--read-log`); 0: a read that fails the
+	                       solid test is reported NOT_SOLID without the (more expensive) blunt-end test */
+	unsigned reserved;
 } abb_assembly_params;
 
 typedef struct abb_contig {
