@@ -28,6 +28,8 @@ def _sources():
     out = []
     for d, _, fs in os.walk(CSRC):
         out += [os.path.join(d, f) for f in fs if f.endswith((".cu", ".cuh", ".h"))]
+    for d, _, fs in os.walk(os.path.join(ROOT, "host")):
+        out += [os.path.join(d, f) for f in fs if f.endswith((".cc", ".h"))]
     out.append(os.path.join(ROOT, "..", "include", "abyss_b200.h"))
     return out
 
@@ -50,7 +52,19 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
     if verbose:
         print(r.stderr)
+    build_cli()
     return LIB
+
+
+def build_cli() -> None:
+    """the C++ host programs (abyss-bloom-dbg, abyss-bloom) that link the C-ABI library"""
+    host = os.path.join(ROOT, "host")
+    for exe, src in (("abyss-bloom-dbg", "abyss_bloom_dbg.cc"), ("abyss-bloom", "abyss_bloom.cc")):
+        cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-o", os.path.join(LIBDIR, exe), os.path.join(host, src),
+               "-L" + LIBDIR, "-labyssb200", "-Wl,-rpath,$ORIGIN"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("g++ failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
 
 
 if __name__ == "__main__":

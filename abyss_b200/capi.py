@@ -27,7 +27,8 @@ class AbbError(RuntimeError):
 class InsertStats(C.Structure):
     _fields_ = [("kmers", C.c_uint64), ("slots", C.c_uint64), ("windows", C.c_uint64),
                 ("deferred", C.c_uint64), ("launches", C.c_uint64),
-                ("ms_hash", C.c_float), ("ms_insert", C.c_float)]
+                ("ms_hash", C.c_float), ("ms_insert", C.c_float), ("ms_commit", C.c_float),
+                ("commit_launches", C.c_uint64)]
 
 
 class Contig(C.Structure):
@@ -37,6 +38,12 @@ class Contig(C.Structure):
 
 class AssemblyParams(C.Structure):
     _fields_ = [("trim", C.c_uint), ("verbose", C.c_uint), ("read_log", C.c_uint), ("reserved", C.c_uint)]
+
+
+class AssemblyStats(C.Structure):
+    _fields_ = [("rounds", C.c_uint64), ("speculated_reads", C.c_uint64), ("wasted_reads", C.c_uint64),
+                ("candidates", C.c_uint64), ("contigs_tried", C.c_uint64), ("launches", C.c_uint64),
+                ("ms_classify", C.c_float), ("ms_visited", C.c_float), ("ms_extend", C.c_float), ("ms_replay", C.c_float)]
 
 
 class AssemblyCounters(C.Structure):
@@ -76,11 +83,15 @@ SIGNATURES = {
     "abb_assembler_create": (C.c_int, [C.POINTER(_vp), _vp, C.POINTER(AssemblyParams)]),
     "abb_assembler_destroy": (C.c_int, [_vp]),
     "abb_assembler_process_reads": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.POINTER(C.POINTER(Contig)), _u64p, C.POINTER(C.c_char_p)]),
+    "abb_assembler_process_reads_dev": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.POINTER(C.POINTER(Contig)), _u64p, C.POINTER(C.c_char_p)]),
+    "abb_assembler_stats": (C.c_int, [_vp, C.POINTER(AssemblyStats)]),
     "abb_assembler_counters": (C.c_int, [_vp, C.POINTER(AssemblyCounters)]),
     "abb_assembler_read_results": (C.c_int, [_vp, C.POINTER(_u8p), _u64p]),
     "abb_assembler_assembled_filter": (_vp, [_vp]),
     "abb_filter_insert_stats": (C.c_int, [_vp, C.POINTER(InsertStats), C.c_int]),
     "abb_filter_set_window": (C.c_int, [_vp, C.c_uint64]),
+    "abb_filter_set_profiling": (C.c_int, [_vp, C.c_int]),
+    "abb_filter_stream": (_vp, [_vp]),
 }
 
 _lib = None
@@ -183,6 +194,8 @@ class Filter:
     def levels(self): return self._lib.abb_filter_levels(self._h)
     def set_threshold(self, t): check(self._lib.abb_filter_set_threshold(self._h, t))
     def set_window(self, w): check(self._lib.abb_filter_set_window(self._h, w))
+    def set_profiling(self, on=True): check(self._lib.abb_filter_set_profiling(self._h, int(on)))
+    def stream(self) -> int: return self._lib.abb_filter_stream(self._h) or 0
 
     @property
     def handle(self):
@@ -291,11 +304,21 @@ class Assembler:
     def process_reads(self, seqs_or_arrays):
         """returns list of (seed_read_index, sequence str, coverage)"""
         bases, offs = seqs_or_arrays if isinstance(seqs_or_arrays, tuple) else pack_reads(seqs_or_arrays)
+        return self._run(self._lib.abb_assembler_process_reads, _ptr(bases), _ptr(offs), len(offs) - 1)
+
+    def process_reads_dev(self, d_bases_ptr: int, d_offs_ptr: int, n_reads: int):
+        return self._run(self._lib.abb_assembler_process_reads_dev, _vp(d_bases_ptr), _vp(d_offs_ptr), n_reads)
+
+    def stats(self) -> AssemblyStats:
+        st = AssemblyStats()
+        check(self._lib.abb_assembler_stats(self._h, C.byref(st)))
+        return st
+
+    def _run(self, fn, bases_p, offs_p, n_reads):
         contigs = C.POINTER(Contig)()
         n = C.c_uint64(0)
         seqs = C.c_char_p()
-        check(self._lib.abb_assembler_process_reads(self._h, _ptr(bases), _ptr(offs), len(offs) - 1, C.byref(contigs),
-                                                    C.byref(n), C.byref(seqs)))
+        check(fn(self._h, bases_p, offs_p, n_reads, C.byref(contigs), C.byref(n), C.byref(seqs)))
         out = []
         if n.value:
             base = C.cast(seqs, C.c_void_p).value

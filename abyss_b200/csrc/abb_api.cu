@@ -119,8 +119,12 @@ static int ordered_insert(abb_filter* f, const uint64_t* d_hashes, const uint8_t
 		ABB_DISPATCH_H(f->H, {
 			k_reserve<LITERAL, MAXH><<<grid, 256, 0, f->stream>>>(d_hashes, d_valid, w0, n, f->cfg, tab, epoch);
 			if (f->kind == ABB_COUNTING) {
+				if (f->profile && f->prof_used + 2 <= f->prof_ev.size())
+					cudaEventRecord(f->prof_ev[f->prof_used++], f->stream);
 				k_commit<0, LITERAL, MAXH><<<grid, 256, 0, f->stream>>>(d_hashes, d_valid, w0, n, f->cfg, tab, epoch, fv,
 				                                                       f->d_deferred, f->d_ndef);
+				if (f->profile && (f->prof_used & 1))
+					cudaEventRecord(f->prof_ev[f->prof_used++], f->stream);
 				k_resolve<0, LITERAL, MAXH><<<1, 1024, 0, f->stream>>>(d_hashes, w0, f->cfg, tab, epoch, fv,
 				                                                      f->d_deferred, f->d_ndef, f->d_stats);
 			} else {
@@ -134,6 +138,16 @@ static int ordered_insert(abb_filter* f, const uint64_t* d_hashes, const uint8_t
 		f->st.windows += 1;
 	}
 	ABB_CUDA(cudaGetLastError());
+	if (f->profile && f->prof_used) { // fold the per-launch k_commit times into the statistics
+		ABB_CUDA(cudaStreamSynchronize(f->stream));
+		for (size_t i = 0; i + 1 < f->prof_used; i += 2) {
+			float ms = 0;
+			cudaEventElapsedTime(&ms, f->prof_ev[i], f->prof_ev[i + 1]);
+			f->st.ms_commit += ms;
+			f->st.commit_launches += 1;
+		}
+		f->prof_used = 0;
+	}
 	return ABB_OK;
 }
 
@@ -422,6 +436,8 @@ int abb_filter_destroy(abb_filter* f)
 	f->valid.release();
 	f->scan_tmp.release();
 	f->out8.release();
+	for (auto e : f->prof_ev)
+		cudaEventDestroy(e);
 	if (f->ev0)
 		cudaEventDestroy(f->ev0);
 	if (f->ev1)
@@ -447,6 +463,19 @@ int abb_filter_set_threshold(abb_filter* f, unsigned threshold)
 		return ABB_ESTATE;
 	}
 	f->threshold = threshold;
+	return ABB_OK;
+}
+
+int abb_filter_set_profiling(abb_filter* f, int on)
+{
+	ABB_REQUIRE(f, "NULL filter");
+	ABB_CUDA(cudaSetDevice(f->device));
+	f->profile = on != 0;
+	if (f->profile && f->prof_ev.empty()) {
+		f->prof_ev.resize(256);
+		for (auto& e : f->prof_ev)
+			ABB_CUDA(cudaEventCreate(&e));
+	}
 	return ABB_OK;
 }
 
@@ -651,6 +680,8 @@ int abb_filter_popcount(abb_filter* f, uint64_t* nonzero, uint64_t* at_or_above_
 		*at_or_above_threshold = f->kind == ABB_COUNTING ? h[1] : h[0];
 	return ABB_OK;
 }
+
+void* abb_filter_stream(abb_filter* f) { return f ? (void*)f->stream : nullptr; }
 
 int abb_filter_insert_stats(abb_filter* f, abb_insert_stats* out, int reset)
 {

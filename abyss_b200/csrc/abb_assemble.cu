@@ -50,16 +50,25 @@ struct WarpCtx {
 	/** bits 0-3: out-neighbours (append A,C,G,T) present in the solid filter; bits 4-7: in-neighbours
 	 *  (prepend).  Lane = 4 * neighbour + hash slot: 8 neighbours x 4 hash functions per round trip
 	 *  (out/in_edge_iterator::next + vertex_exists, RollingBloomDBG.h:302-327,357-383,436-445). */
+	struct Probe {
+		bool ok;
+	};
 	template <int KW>
-	__device__ unsigned neighbors(const Vtx<KW>& v) const
+	__device__ Probe neighbors_issue(const Vtx<KW>& v) const
 	{
 		const unsigned n = lane >> 2, hs = lane & 3;
 		const HashPair h = n < 4 ? roll_right(v.h, rt, kmer_first(v.km, k), n) : roll_left(v.h, rt, kmer_last(v.km), n - 4);
 		const uint64_t h0 = h.canonical();
-		bool ok = true;
+		unsigned mn = 255;
 		for (unsigned i = hs; i < cfg->H; i += 4)
-			ok &= __ldcg(counters + nth_pos(h0, *cfg, i)) >= threshold;
-		unsigned b = __ballot_sync(0xffffffffu, ok);
+			mn = min(mn, (unsigned)__ldcg(counters + nth_pos(h0, *cfg, i)));
+		Probe p;
+		p.ok = mn >= threshold;
+		return p;
+	}
+	__device__ unsigned neighbors_finish(const Probe& p) const
+	{
+		unsigned b = __ballot_sync(0xffffffffu, p.ok);
 		b &= b >> 1;
 		b &= b >> 2; // bit 4n = AND of the four lanes of neighbour n
 		unsigned r = 0;
@@ -67,6 +76,11 @@ struct WarpCtx {
 		for (int j = 0; j < 8; ++j)
 			r |= ((b >> (4 * j)) & 1u) << j;
 		return r;
+	}
+	template <int KW>
+	__device__ unsigned neighbors(const Vtx<KW>& v) const
+	{
+		return neighbors_finish(neighbors_issue(v));
 	}
 	// scratch accesses: every lane stores the same value to the same address and reads back its own
 	// store, so no intra-warp synchronisation is needed for uniform data
@@ -407,39 +421,55 @@ struct ReplayIO {
 	unsigned* ccov;              // per contig: coverage
 };
 
+/** contigs with at least this many k-mers are replayed by whole-grid kernels (k_big_*) */
+constexpr unsigned kBigContig = 1u << 15;
+
+/**
+ * Replays reads s0.. in file order with ONE CTA, starting at contig index cs and stopping before
+ * contig index ce (a "big" contig that the host hands to k_big_check / k_big_apply, or the end).
+ * A read whose first contig is >= cs has not been started: its "all k-mers assembled" test runs
+ * here; otherwise its verdict is already in rcode[].
+ */
 __global__ void __launch_bounds__(1024)
-k_replay(ReplayIO io, const __grid_constant__ HashCfg cfg, unsigned k, const uint8_t* __restrict__ counters, uint8_t* bits,
-         EndSet ends)
+k_replay(ReplayIO io, unsigned s0, unsigned cs, unsigned ce, const __grid_constant__ HashCfg cfg, unsigned k,
+         const uint8_t* __restrict__ counters, uint8_t* bits, EndSet ends)
 {
 	__shared__ unsigned s_cov;
 	__shared__ int s_flag;
 	const unsigned tid = threadIdx.x, nt = blockDim.x;
-	for (unsigned s = 0; s < io.n_spec; ++s) {
-		const unsigned r = io.spec[s];
-		const uint64_t rs0 = io.slot_offs[r];
-		const unsigned rnk = (unsigned)(io.slot_offs[r + 1] - rs0);
-		// skip reads in previously assembled regions (bloom-dbg.h:823-827)
-		int all = 1;
-		for (unsigned base = 0; base < rnk && all; base += nt) {
-			const unsigned j = base + tid;
-			int ok = 1;
-			if (j < rnk) {
-				const uint64_t h = io.h0[rs0 + j];
-				for (unsigned i = 0; i < cfg.H; ++i) {
-					const uint64_t p = nth_pos(h, cfg, i);
-					ok &= (__ldcg(bits + (p >> 3)) >> (p & 7)) & 1;
+	for (unsigned s = s0; s < io.n_spec; ++s) {
+		const unsigned cb = io.spec_cbeg[s], cend = io.spec_cbeg[s + 1];
+		if (cb > ce || (cb == ce && cs > cb))
+			return;
+		if (cb >= cs) {
+			const unsigned r = io.spec[s];
+			const uint64_t rs0 = io.slot_offs[r];
+			const unsigned rnk = (unsigned)(io.slot_offs[r + 1] - rs0);
+			// skip reads in previously assembled regions (bloom-dbg.h:823-827)
+			int all = 1;
+			for (unsigned base = 0; base < rnk && all; base += nt) {
+				const unsigned j = base + tid;
+				int ok = 1;
+				if (j < rnk) {
+					const uint64_t h = io.h0[rs0 + j];
+					for (unsigned i = 0; i < cfg.H; ++i) {
+						const uint64_t p = nth_pos(h, cfg, i);
+						ok &= (__ldcg(bits + (p >> 3)) >> (p & 7)) & 1;
+					}
 				}
+				all = __syncthreads_and(ok);
 			}
-			all = __syncthreads_and(ok);
-		}
-		if (all) {
 			if (tid == 0)
-				io.rcode[s] = RC_ALL_KMERS_VISITED;
-			continue;
+				io.rcode[s] = all ? RC_ALL_KMERS_VISITED : RC_GENERATED_CONTIGS;
+			if (all)
+				continue;
+		} else {
+			if (__ldcg(io.rcode + s) == RC_ALL_KMERS_VISITED)
+				continue;
 		}
-		if (tid == 0)
-			io.rcode[s] = RC_GENERATED_CONTIGS;
-		for (unsigned c = io.spec_cbeg[s]; c < io.spec_cbeg[s + 1]; ++c) {
+		for (unsigned c = cb > cs ? cb : cs; c < cend; ++c) {
+			if (c >= ce)
+				return;
 			const uint64_t c0 = io.cslot[c];
 			const unsigned nk = (unsigned)(io.cslot[c + 1] - c0);
 			const unsigned len = io.clen[c];
@@ -509,6 +539,55 @@ k_replay(ReplayIO io, const __grid_constant__ HashCfg cfg, unsigned k, const uin
 	}
 }
 
+/** big contig c of speculated read s, step 1: redundant unless some k-mer is not yet assembled.
+ *  caccept[c] was zeroed by the host; any thread that finds a missing k-mer sets it. */
+__global__ void __launch_bounds__(256)
+k_big_check(ReplayIO io, unsigned s, unsigned c, const __grid_constant__ HashCfg cfg, const uint8_t* __restrict__ bits)
+{
+	if (__ldcg(io.rcode + s) != RC_GENERATED_CONTIGS)
+		return;
+	const uint64_t c0 = io.cslot[c];
+	const unsigned nk = (unsigned)(io.cslot[c + 1] - c0);
+	bool missing = false;
+	for (unsigned j = blockIdx.x * blockDim.x + threadIdx.x; j < nk; j += gridDim.x * blockDim.x) {
+		const uint64_t h = io.ch0[c0 + j];
+		bool ok = true;
+		for (unsigned i = 0; i < cfg.H; ++i) {
+			const uint64_t p = nth_pos(h, cfg, i);
+			ok &= (__ldcg(bits + (p >> 3)) >> (p & 7)) & 1;
+		}
+		missing |= !ok;
+	}
+	if (__any_sync(0xffffffffu, missing) && (threadIdx.x & 31) == 0)
+		io.caccept[c] = 1;
+}
+/** step 2: if not redundant, mark its k-mers assembled and sum their counts (ccov[c] zeroed by the host) */
+__global__ void __launch_bounds__(256)
+k_big_apply(ReplayIO io, unsigned s, unsigned c, const __grid_constant__ HashCfg cfg, const uint8_t* __restrict__ counters,
+            uint8_t* bits)
+{
+	if (__ldcg(io.rcode + s) != RC_GENERATED_CONTIGS || __ldcg(io.caccept + c) == 0)
+		return;
+	const uint64_t c0 = io.cslot[c];
+	const unsigned nk = (unsigned)(io.cslot[c + 1] - c0);
+	unsigned cov = 0;
+	for (unsigned j = blockIdx.x * blockDim.x + threadIdx.x; j < nk; j += gridDim.x * blockDim.x) {
+		const uint64_t h = io.ch0[c0 + j];
+		unsigned mn = 255;
+		for (unsigned i = 0; i < cfg.H; ++i) {
+			const uint64_t p = nth_pos(h, cfg, i);
+			const uint64_t byte = p >> 3;
+			atomicOr(reinterpret_cast<unsigned*>(bits + (byte & ~3ULL)), 1u << ((p & 7) + 8 * (byte & 3)));
+			mn = min(mn, (unsigned)__ldcg(counters + p));
+		}
+		cov += mn;
+	}
+	for (int d = 16; d; d >>= 1)
+		cov += __shfl_down_sync(0xffffffffu, cov, d);
+	if ((threadIdx.x & 31) == 0 && cov)
+		atomicAdd(io.ccov + c, cov);
+}
+
 } // namespace abb
 
 using namespace abb;
@@ -524,6 +603,8 @@ struct abb_assembler {
 	cudaStream_t stream = nullptr;
 	uint64_t reads_seen = 0;
 	int kw = 0;
+	const uint8_t* cur_bases = nullptr; // device reads of the batch being processed
+	const uint64_t* cur_offs = nullptr;
 
 	// batch state (device)
 	DevBuf<uint8_t> bases, valid, codes, vis, scan_tmp, cseq, cvalid, rcode, caccept;
@@ -544,20 +625,37 @@ struct abb_assembler {
 	uint64_t ends_upper = 0; // upper bound on entries
 
 	// speculation control
-	unsigned spec_target = 256;
+	unsigned spec_target = 1024;
 	// host outputs of the last batch
 	std::vector<abb_contig> out_contigs;
 	std::vector<char> out_seqs;
 	std::vector<uint8_t> out_codes;
 	// statistics
-	uint64_t st_iterations = 0, st_speculated = 0, st_wasted = 0, st_launches = 0;
+	uint64_t st_iterations = 0, st_speculated = 0, st_wasted = 0, st_launches = 0, st_candidates = 0, st_contigs_tried = 0;
+	float ms_classify = 0, ms_visited = 0, ms_extend = 0, ms_replay = 0;
+	cudaEvent_t ev[2] = { nullptr, nullptr };
 };
 
 namespace {
 
-constexpr unsigned kMaxSpec = 4096;
-constexpr unsigned long long kArenaDefault = 2ULL << 30;
-constexpr unsigned long long kArenaMax = 64ULL << 30;
+struct PhaseTimer { // CUDA-event time of a phase on the assembler stream
+	abb_assembler* a;
+	float* acc;
+	PhaseTimer(abb_assembler* a_, float* acc_) : a(a_), acc(acc_) { cudaEventRecord(a->ev[0], a->stream); }
+	void stop()
+	{
+		cudaEventRecord(a->ev[1], a->stream);
+		cudaEventSynchronize(a->ev[1]);
+		float ms = 0;
+		cudaEventElapsedTime(&ms, a->ev[0], a->ev[1]);
+		*acc += ms;
+	}
+};
+
+constexpr unsigned kMaxSpec = 2048;  // about one resident wave of walking warps on 148 SMs
+constexpr unsigned kMinSpec = 512;   // speculation is cheap (parallel), latency is not: never go narrow
+constexpr unsigned long long kArenaDefault = 4ULL << 30;
+constexpr unsigned long long kArenaMax = 96ULL << 30;
 
 int ensure_scratch(abb_assembler* a, unsigned warps)
 {
@@ -646,6 +744,7 @@ int speculate_round(abb_assembler* a, const std::vector<unsigned>& cand, size_t*
 	std::vector<unsigned> spec;
 	size_t pos = *cursor;
 	size_t chunk = std::max<size_t>(a->spec_target, 1024);
+	PhaseTimer tv(a, &a->ms_visited);
 	while (pos < ncand && spec.size() < a->spec_target) {
 		const unsigned n = (unsigned)std::min(chunk, ncand - pos);
 		ABB_CHECK(a->vis.reserve(n));
@@ -668,6 +767,7 @@ int speculate_round(abb_assembler* a, const std::vector<unsigned>& cand, size_t*
 		chunk = std::min<size_t>(chunk * 4, 1u << 22);
 	}
 	*cursor = pos;
+	tv.stop();
 	if (spec.empty())
 		return ABB_OK;
 	++a->st_iterations;
@@ -682,6 +782,7 @@ int speculate_round(abb_assembler* a, const std::vector<unsigned>& cand, size_t*
 	std::vector<ContigRec> recs;
 	std::vector<unsigned> status(n_spec);
 	unsigned n_ok = n_spec; // speculated reads [0, n_ok) completed
+	PhaseTimer te(a, &a->ms_extend);
 	for (;;) {
 		ABB_CHECK(a->recs.reserve(rec_cap));
 		ABB_CHECK(ensure_arena(a, a->arena_size ? a->arena_size : kArenaDefault));
@@ -689,7 +790,7 @@ int speculate_round(abb_assembler* a, const std::vector<unsigned>& cand, size_t*
 		ABB_CUDA(cudaMemsetAsync(a->d_nrecs, 0, sizeof(unsigned), st));
 		const WalkCfg w = walk_cfg(a);
 		ABB_DISPATCH_KW(a->kw, (k_extend<KW><<<blocks_for(n_spec, kWalkWarps), kWalkWarps * 32, 0, st>>>(
-		                           a->bases.p, a->offs.p, a->spec.p, n_spec, w, f->cfg, a->frames.p, a->look.p, a->d_arena, a->arena_size,
+		                           a->cur_bases, a->cur_offs, a->spec.p, n_spec, w, f->cfg, a->frames.p, a->look.p, a->d_arena, a->arena_size,
 		                           a->d_arena_top, a->recs.p, a->d_nrecs, rec_cap, a->status.p)));
 		ABB_CUDA(cudaGetLastError());
 		++a->st_launches;
@@ -707,19 +808,27 @@ int speculate_round(abb_assembler* a, const std::vector<unsigned>& cand, size_t*
 				n_ok = i;
 				break;
 			}
-		if (n_ok == 0) {
-			// the very first read ran out of scratch: give it a bigger arena and try again
-			if (status[0] & ((1u << 1) | (1u << 2))) {
-				set_error("graph traversal exceeded the per-warp scratch bounds (lookAhead %u / trueBranch %u frames)", kLookCap, kFrameCap);
-				return ABB_ENOMEM;
+		if (n_ok < n_spec) {
+			if (status[n_ok] & ((1u << 1) | (1u << 2))) {
+				if (n_ok == 0) {
+					set_error("graph traversal exceeded the per-warp scratch bounds (lookAhead %u / trueBranch %u frames)", kLookCap, kFrameCap);
+					return ABB_ENOMEM;
+				}
+			} else {
+				// out of unitig scratch: grow the arena (free memory permitting) and rerun the round
+				size_t free_b = 0, total_b = 0;
+				cudaMemGetInfo(&free_b, &total_b);
+				const unsigned long long room = a->arena_size + (unsigned long long)(free_b * 0.8);
+				const unsigned long long bigger = std::min<unsigned long long>(std::min(kArenaMax, room), a->arena_size * 4);
+				if (bigger > a->arena_size + (1ULL << 28)) {
+					ABB_CHECK(ensure_arena(a, bigger));
+					continue;
+				}
+				if (n_ok == 0) {
+					set_error("unitig scratch arena exhausted at %llu bytes", a->arena_size);
+					return ABB_ENOMEM;
+				}
 			}
-			const unsigned long long bigger = a->arena_size * 2;
-			if (bigger > kArenaMax) {
-				set_error("unitig scratch arena would exceed %llu bytes", kArenaMax);
-				return ABB_ENOMEM;
-			}
-			ABB_CHECK(ensure_arena(a, bigger));
-			continue;
 		}
 		recs.resize(nrecs);
 		if (nrecs)
@@ -727,6 +836,7 @@ int speculate_round(abb_assembler* a, const std::vector<unsigned>& cand, size_t*
 		ABB_CUDA(cudaStreamSynchronize(st));
 		break;
 	}
+	te.stop();
 	if (n_ok < n_spec) {
 		// reads from the first failure on go back to the queue; speculate less next time.
 		// Candidates after the failed read that this round already labelled "visited" are re-examined
@@ -763,7 +873,9 @@ int speculate_round(abb_assembler* a, const std::vector<unsigned>& cand, size_t*
 	std::vector<uint8_t> rcode(n_ok), caccept(nc);
 	std::vector<unsigned> ccov(nc);
 	std::vector<char> seqs(coffs[nc]);
+	a->st_contigs_tried += nc;
 	{
+		PhaseTimer tr(a, &a->ms_replay);
 		ABB_CHECK(h2d(a->recs_sorted, recs, st));
 		ABB_CHECK(h2d(a->spec_cbeg, spec_cbeg, st));
 		ABB_CHECK(h2d(a->clen, clen, st));
@@ -796,9 +908,32 @@ int speculate_round(abb_assembler* a, const std::vector<unsigned>& cand, size_t*
 		io.caccept = a->caccept.p;
 		io.ccov = a->ccov.p;
 		EndSet ends = { a->d_ends, a->ends_cap, a->d_ends_n };
-		k_replay<<<1, 1024, 0, st>>>(io, f->cfg, f->k, f->d_data, a->assembled->d_data, ends);
+		if (nc) {
+			ABB_CUDA(cudaMemsetAsync(a->caccept.p, 0, nc, st));
+			ABB_CUDA(cudaMemsetAsync(a->ccov.p, 0, nc * sizeof(unsigned), st));
+		}
+		// one-CTA replay between big contigs; big contigs use the whole grid
+		unsigned seg_s = 0, seg_c = 0; // next read / contig to replay
+		unsigned s_of = 0;             // read owning contig c while scanning
+		for (unsigned c = 0; c <= nc; ++c) {
+			const bool big = c < nc && clen[c] - f->k + 1 >= kBigContig;
+			if (!big && c < nc)
+				continue;
+			k_replay<<<1, 1024, 0, st>>>(io, seg_s, seg_c, c, f->cfg, f->k, f->d_data, a->assembled->d_data, ends);
+			++a->st_launches;
+			if (c == nc)
+				break;
+			while (spec_cbeg[s_of + 1] <= c)
+				++s_of;
+			const unsigned nkm = clen[c] - f->k + 1;
+			const unsigned g = std::min<unsigned>(blocks_for(nkm, 256), 148 * 8);
+			k_big_check<<<g, 256, 0, st>>>(io, s_of, c, f->cfg, a->assembled->d_data);
+			k_big_apply<<<g, 256, 0, st>>>(io, s_of, c, f->cfg, f->d_data, a->assembled->d_data);
+			a->st_launches += 2;
+			seg_s = s_of;
+			seg_c = c + 1;
+		}
 		ABB_CUDA(cudaGetLastError());
-		++a->st_launches;
 		ABB_CUDA(cudaMemcpyAsync(rcode.data(), a->rcode.p, n_ok, cudaMemcpyDeviceToHost, st));
 		if (nc) {
 			ABB_CUDA(cudaMemcpyAsync(caccept.data(), a->caccept.p, nc, cudaMemcpyDeviceToHost, st));
@@ -806,6 +941,7 @@ int speculate_round(abb_assembler* a, const std::vector<unsigned>& cand, size_t*
 			ABB_CUDA(cudaMemcpyAsync(seqs.data(), a->cseq.p, coffs[nc], cudaMemcpyDeviceToHost, st));
 		}
 		ABB_CUDA(cudaStreamSynchronize(st));
+		tr.stop();
 	}
 
 	// ---- collect
@@ -835,10 +971,10 @@ int speculate_round(abb_assembler* a, const std::vector<unsigned>& cand, size_t*
 	a->st_wasted += wasted;
 	// adapt the amount of speculation: grow while most speculated reads were really needed
 	if (n_ok == n_spec) {
-		if (wasted * 4 <= n_ok)
+		if (wasted * 2 <= n_ok)
 			a->spec_target = std::min(kMaxSpec, a->spec_target * 2);
-		else if (wasted * 2 > n_ok)
-			a->spec_target = std::max(32u, a->spec_target / 2);
+		else if (wasted * 10 > n_ok * 9)
+			a->spec_target = std::max(kMinSpec, a->spec_target / 2);
 	}
 	(void)n_reads;
 	return ABB_OK;
@@ -884,7 +1020,9 @@ int abb_assembler_create(abb_assembler** out, abb_filter* solid, const abb_assem
 		return e == cudaErrorMemoryAllocation ? ABB_ENOMEM : ABB_ECUDA;
 	};
 	cudaError_t e;
-	if ((e = cudaStreamCreateWithFlags(&a->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
+	a->stream = solid->stream; // one stream carries pass 1 and pass 2 of a filter
+	if ((e = cudaEventCreate(&a->ev[0])) != cudaSuccess) return fail(e, "cudaEventCreate");
+	if ((e = cudaEventCreate(&a->ev[1])) != cudaSuccess) return fail(e, "cudaEventCreate");
 	if ((e = cudaMalloc((void**)&a->d_arena_top, sizeof(unsigned long long))) != cudaSuccess) return fail(e, "cudaMalloc");
 	if ((e = cudaMalloc((void**)&a->d_nrecs, sizeof(unsigned))) != cudaSuccess) return fail(e, "cudaMalloc");
 	if ((e = cudaMalloc((void**)&a->d_ends_n, 2 * sizeof(unsigned))) != cudaSuccess) return fail(e, "cudaMalloc");
@@ -912,46 +1050,27 @@ int abb_assembler_destroy(abb_assembler* a)
 	cudaFree(a->d_nrecs);
 	cudaFree(a->d_ends);
 	cudaFree(a->d_ends_n);
-	if (a->stream)
-		cudaStreamDestroy(a->stream);
+	if (a->ev[0]) cudaEventDestroy(a->ev[0]);
+	if (a->ev[1]) cudaEventDestroy(a->ev[1]);
 	delete a;
 	return ABB_OK;
 }
 
-int abb_assembler_process_reads(abb_assembler* a, const char* bases, const uint64_t* offsets, uint64_t n_reads,
-                                const abb_contig** contigs, uint64_t* n_contigs, const char** seqs)
+static int process_batch(abb_assembler* a, const uint8_t* d_bases, const uint64_t* d_offs, uint64_t n_reads,
+                         const abb_contig** contigs, uint64_t* n_contigs, const char** seqs)
 {
-	ABB_REQUIRE(a, "NULL assembler");
-	a->out_contigs.clear();
-	a->out_seqs.clear();
-	a->out_codes.assign(n_reads, RC_SHORTER_THAN_K);
-	if (contigs) *contigs = nullptr;
-	if (n_contigs) *n_contigs = 0;
-	if (seqs) *seqs = nullptr;
-	if (n_reads == 0)
-		return ABB_OK;
-	ABB_REQUIRE(bases && offsets, "NULL read buffers");
-	ABB_REQUIRE(offsets[0] == 0, "offsets[0] must be 0");
-	ABB_REQUIRE(n_reads < (1ULL << 32), "at most 2^32-1 reads per batch");
 	abb_filter* f = a->solid;
 	cudaStream_t st = a->stream;
-	ABB_CUDA(cudaSetDevice(f->device));
-	// the filters may have been written on their own streams
-	ABB_CUDA(cudaStreamSynchronize(f->stream));
-	ABB_CUDA(cudaStreamSynchronize(a->assembled->stream));
-
-	const uint64_t n_bases = offsets[n_reads];
-	ABB_CHECK(a->bases.reserve(n_bases + 16));
-	ABB_CHECK(a->offs.reserve(n_reads + 1));
-	ABB_CUDA(cudaMemcpyAsync(a->bases.p, bases, n_bases, cudaMemcpyHostToDevice, st));
-	ABB_CUDA(cudaMemcpyAsync(a->offs.p, offsets, (n_reads + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+	a->cur_bases = d_bases;
+	a->cur_offs = d_offs;
+	PhaseTimer tc(a, &a->ms_classify);
 	uint64_t total = 0;
-	ABB_CHECK(compute_slot_offsets(f->k, a->offs.p, n_reads, a->slot_offs, a->scan_tmp, st, &total, &a->st_launches));
+	ABB_CHECK(compute_slot_offsets(f->k, d_offs, n_reads, a->slot_offs, a->scan_tmp, st, &total, &a->st_launches));
 	ABB_CHECK(a->h0.reserve(total + 1));
 	ABB_CHECK(a->valid.reserve(total + 1));
 	ABB_CHECK(a->codes.reserve(n_reads));
 	if (total)
-		ABB_CHECK(launch_hash(nullptr, f->k, nullptr, a->bases.p, a->offs.p, a->slot_offs.p, 0, n_reads, 0, a->h0.p, a->valid.p, st,
+		ABB_CHECK(launch_hash(nullptr, f->k, nullptr, d_bases, d_offs, a->slot_offs.p, 0, n_reads, 0, a->h0.p, a->valid.p, st,
 		                      &a->st_launches));
 	// ---- K3a
 	int sms = 148;
@@ -959,19 +1078,20 @@ int abb_assembler_process_reads(abb_assembler* a, const char* bases, const uint6
 	const unsigned grid = (unsigned)std::min<uint64_t>(blocks_for(n_reads, kWalkWarps), (uint64_t)sms * 8);
 	ABB_CHECK(ensure_scratch(a, grid * kWalkWarps));
 	const WalkCfg w = walk_cfg(a);
-	ABB_DISPATCH_KW(a->kw, (k_classify<KW><<<grid, kWalkWarps * 32, 0, st>>>(a->bases.p, a->offs.p, a->slot_offs.p, a->h0.p, a->valid.p,
-	                                                                        n_reads, w, f->cfg, a->look.p, (int)a->params.read_log,
-	                                                                        a->codes.p)));
+	ABB_DISPATCH_KW(a->kw, (k_classify<KW><<<grid, kWalkWarps * 32, 0, st>>>(d_bases, d_offs, a->slot_offs.p, a->h0.p, a->valid.p, n_reads, w,
+	                                                                        f->cfg, a->look.p, (int)a->params.read_log, a->codes.p)));
 	ABB_CUDA(cudaGetLastError());
 	++a->st_launches;
 	ABB_CUDA(cudaMemcpyAsync(a->out_codes.data(), a->codes.p, n_reads, cudaMemcpyDeviceToHost, st));
 	ABB_CUDA(cudaStreamSynchronize(st));
+	tc.stop();
 
 	std::vector<unsigned> cand;
 	for (uint64_t r = 0; r < n_reads; ++r)
 		if (a->out_codes[r] == RC_CANDIDATE)
 			cand.push_back((unsigned)r);
 	a->counters.solid_reads += cand.size();
+	a->st_candidates += cand.size();
 	ABB_CHECK(h2d(a->cand, cand, st));
 
 	size_t cursor = 0;
@@ -983,6 +1103,65 @@ int abb_assembler_process_reads(abb_assembler* a, const char* bases, const uint6
 	if (contigs) *contigs = a->out_contigs.data();
 	if (n_contigs) *n_contigs = a->out_contigs.size();
 	if (seqs) *seqs = a->out_seqs.data();
+	return ABB_OK;
+}
+
+static int begin_batch(abb_assembler* a, uint64_t n_reads, const abb_contig** contigs, uint64_t* n_contigs, const char** seqs)
+{
+	ABB_REQUIRE(a, "NULL assembler");
+	a->out_contigs.clear();
+	a->out_seqs.clear();
+	a->out_codes.assign(n_reads, RC_SHORTER_THAN_K);
+	if (contigs) *contigs = nullptr;
+	if (n_contigs) *n_contigs = 0;
+	if (seqs) *seqs = nullptr;
+	ABB_REQUIRE(n_reads < (1ULL << 32), "at most 2^32-1 reads per batch");
+	ABB_CUDA(cudaSetDevice(a->solid->device));
+	// the filters may have been written on their own streams
+	ABB_CUDA(cudaStreamSynchronize(a->solid->stream));
+	ABB_CUDA(cudaStreamSynchronize(a->assembled->stream));
+	return ABB_OK;
+}
+
+int abb_assembler_process_reads(abb_assembler* a, const char* bases, const uint64_t* offsets, uint64_t n_reads,
+                                const abb_contig** contigs, uint64_t* n_contigs, const char** seqs)
+{
+	ABB_CHECK(begin_batch(a, n_reads, contigs, n_contigs, seqs));
+	if (n_reads == 0)
+		return ABB_OK;
+	ABB_REQUIRE(bases && offsets, "NULL read buffers");
+	ABB_REQUIRE(offsets[0] == 0, "offsets[0] must be 0");
+	const uint64_t n_bases = offsets[n_reads];
+	ABB_CHECK(a->bases.reserve(n_bases + 16));
+	ABB_CHECK(a->offs.reserve(n_reads + 1));
+	ABB_CUDA(cudaMemcpyAsync(a->bases.p, bases, n_bases, cudaMemcpyHostToDevice, a->stream));
+	ABB_CUDA(cudaMemcpyAsync(a->offs.p, offsets, (n_reads + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, a->stream));
+	return process_batch(a, a->bases.p, a->offs.p, n_reads, contigs, n_contigs, seqs);
+}
+
+int abb_assembler_process_reads_dev(abb_assembler* a, const char* d_bases, const uint64_t* d_offsets, uint64_t n_reads,
+                                    const abb_contig** contigs, uint64_t* n_contigs, const char** seqs)
+{
+	ABB_CHECK(begin_batch(a, n_reads, contigs, n_contigs, seqs));
+	if (n_reads == 0)
+		return ABB_OK;
+	ABB_REQUIRE(d_bases && d_offsets, "NULL read buffers");
+	return process_batch(a, (const uint8_t*)d_bases, d_offsets, n_reads, contigs, n_contigs, seqs);
+}
+
+int abb_assembler_stats(const abb_assembler* a, abb_assembly_stats* out)
+{
+	ABB_REQUIRE(a && out, "NULL argument");
+	out->rounds = a->st_iterations;
+	out->speculated_reads = a->st_speculated;
+	out->wasted_reads = a->st_wasted;
+	out->candidates = a->st_candidates;
+	out->contigs_tried = a->st_contigs_tried;
+	out->launches = a->st_launches;
+	out->ms_classify = a->ms_classify;
+	out->ms_visited = a->ms_visited;
+	out->ms_extend = a->ms_extend;
+	out->ms_replay = a->ms_replay;
 	return ABB_OK;
 }
 

@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <string>
+#include <vector>
 
 namespace abb {
 
@@ -112,4 +113,7 @@ struct abb_filter {
 
 	// statistics
 	abb_insert_stats st = {};
+	bool profile = false; // time every k_commit launch with CUDA events
+	std::vector<cudaEvent_t> prof_ev;
+	size_t prof_used = 0;
 };

@@ -43,9 +43,16 @@ ABB_HD unsigned base_code(unsigned char c)
 }
 
 /** seed of a 2-bit code; code 4 (non-ACGT) hashes as 0 like seedTab['N'] (nthash.hpp:29,40). */
+#if defined(__CUDACC__)
+static __device__ __constant__ uint64_t kSeedTabDev[8] = { kSeedA, kSeedC, kSeedG, kSeedT, 0, 0, 0, 0 };
+#endif
 ABB_HD uint64_t seed_of(unsigned code)
 {
+#if defined(__CUDA_ARCH__)
+	return kSeedTabDev[code & 7]; // constant-bank lookup: one LDC instead of a chain of 64-bit selects
+#else
 	return code == 0 ? kSeedA : code == 1 ? kSeedC : code == 2 ? kSeedG : code == 3 ? kSeedT : 0ULL;
+#endif
 }
 
 /** R^n with n given as (n % 33, n % 31). */

@@ -214,6 +214,7 @@ ABB_HD unsigned ctz4(unsigned m) { return (m & 1) ? 0 : (m & 2) ? 1 : (m & 4) ? 
  * Ctx concept (device: WarpCtx in abb_assemble.cu; host emulation: tests/host_walk):
  *   unsigned k, trim; RollTab rt;
  *   template<int KW> unsigned neighbors(const Vtx<KW>&)   bits 0-3: out-neighbours A,C,G,T exist; 4-7: in-neighbours
+ *   Probe neighbors_issue(v) / unsigned neighbors_finish(Probe)   the same, split so that other loads can be in flight
  *   uint64_t rd64(const uint64_t*), void wr64(uint64_t*, uint64_t), uint8_t rd8(const uint8_t*), void wr8(uint8_t*, uint8_t)
  *   void sync()                      make lane-0 writes visible to the warp
  *   bool find64(const uint64_t* a, unsigned n, uint64_t key, unsigned stride_words)   cooperative linear search
@@ -387,7 +388,18 @@ template <int KW, class Ctx>
 ABB_HD ExtCode successor(Ctx& c, const Vtx<KW>& u, unsigned nbmask, Dir dir, unsigned* vbase)
 {
 	const unsigned m = dir == FWD ? (nbmask & 15) : (nbmask >> 4);
-	for (unsigned i = 0;; i = (i == 0) ? 1 : (2 * i < c.trim ? 2 * i : c.trim)) {
+	// i = 0: every existing neighbour is a true branch (depth 0 >= trim 0), so the count is the degree
+	if (m == 0)
+		return ER_DEAD_END;
+	if ((m & (m - 1)) == 0) {
+		*vbase = ctz4(m);
+		return ER_LENGTH_LIMIT;
+	}
+	if (c.trim == 0) {
+		*vbase = ctz4(m & (m - 1)); // the second true branch is the one left in `v`
+		return ER_AMBI_OUT;
+	}
+	for (unsigned i = 1;; i = (2 * i < c.trim ? 2 * i : c.trim)) {
 		unsigned cnt = 0;
 		for (unsigned mm = m; mm; mm &= mm - 1) {
 			const unsigned b = ctz4(mm);
@@ -431,7 +443,7 @@ ABB_HD bool ambiguous_expected(Ctx& c, const Vtx<KW>& u, uint64_t expected_canon
 
 // ------------------------------------------------------------------------------------------
 // exact set of the canonical hashes of the path vertices (extendPath's `visited`, ExtendPath.h:699-703)
-// open addressing in arena memory, doubled when more than 1/4 full; key 0 is tracked separately
+// open addressing in arena memory, doubled when more than 1/2 full; key 0 is tracked separately
 // ------------------------------------------------------------------------------------------
 struct PathSet {
 	uint64_t* tab;
@@ -473,7 +485,7 @@ ABB_HD bool pathset_insert(Ctx& c, PathSet& ps, uint64_t key, bool* ok)
 		ps.has_zero = true;
 		return fresh;
 	}
-	if ((ps.n + 1) * 4 > ps.cap) { // grow: re-insert everything into a table twice the size
+	if ((ps.n + 1) * 2 > ps.cap) { // grow: re-insert everything into a table twice the size
 		PathSet big;
 		if (!pathset_init(c, big, ps.cap * 2)) {
 			*ok = false;
@@ -532,8 +544,8 @@ ABB_HD ExtCode extend_dir(Ctx& c, Vtx<KW>& head, Dir dir, unsigned* psize, ByteV
 {
 	bool look_behind = false; // lookBehindStartVertex
 	uint64_t prev_h = 0;
+	unsigned nb = c.neighbors(head);
 	for (;;) {
-		const unsigned nb = c.neighbors(head);
 		unsigned b = 0;
 		if (look_behind) { // extendPathBySingleVertex, ExtendPath.h:419-446
 			const ExtCode r = successor(c, head, nb, opposite(dir), &b);
@@ -542,9 +554,10 @@ ABB_HD ExtCode extend_dir(Ctx& c, Vtx<KW>& head, Dir dir, unsigned* psize, ByteV
 			if (*psize > 1) {
 				if (r == ER_DEAD_END)
 					return ER_AMBI_IN;
-				Vtx<KW> t = head;
-				vtx_step(t, c.k, c.rt, opposite(dir), b);
-				if (t.canon() != prev_h) // we are on a tip rejoining the graph
+				// canonical hash of the unique predecessor t (hash only: no need to build its k-mer)
+				const HashPair th = dir == FWD ? roll_left(head.h, c.rt, kmer_last(head.km), b)
+				                               : roll_right(head.h, c.rt, kmer_first(head.km, c.k), b);
+				if (th.canonical() != prev_h) // we are on a tip rejoining the graph
 					return ER_AMBI_IN;
 			}
 		}
@@ -553,6 +566,9 @@ ABB_HD ExtCode extend_dir(Ctx& c, Vtx<KW>& head, Dir dir, unsigned* psize, ByteV
 			return r;
 		const uint64_t old_h = head.canon();
 		const unsigned out = vtx_step(head, c.k, c.rt, dir, b);
+		// issue the Bloom probes of the new head before the visited-set probe so that the two
+		// memory round trips of a step overlap
+		const typename Ctx::Probe pr = c.neighbors_issue(head);
 		if (!pathset_insert(c, ps, head.canon(), ok)) { // visited.insert(head) failed: ER_CYCLE, pop
 			vtx_unstep(head, c.k, c.rt, dir, out);
 			return *ok ? ER_CYCLE : ER_DEAD_END;
@@ -566,6 +582,7 @@ ABB_HD ExtCode extend_dir(Ctx& c, Vtx<KW>& head, Dir dir, unsigned* psize, ByteV
 		look_behind = true; // params.lookBehind
 		if (c.failed())
 			return ER_DEAD_END;
+		nb = c.neighbors_finish(pr);
 	}
 }
 

@@ -1,0 +1,396 @@
+// abyss-bloom-dbg (B200) -- the reference's command line (BloomDBG/bloom-dbg.cc:44-558) over
+// libabyssb200: same options, same AssemblyParams surface, same output, GPU underneath.
+//
+//   abyss-bloom-dbg -b <bloom_size> -H <bloom_hashes> -k <kmer_size> [options] <FASTQ>... > assembly.fasta
+//
+// Flow (countingBloomAssembly, bloom-dbg.cc:347-386): size the counting filter from -b, pass 1
+// = abb_insert_reads over every input file in order, pass 2 = abb_assembler_process_reads over
+// the same files again, FASTA records `>ID LEN COV read:READID` (printContig, bloom-dbg.h:455-487).
+// -i FILE loads a [BTLCountingBloomFilter_v1] file instead of pass 1 (prebuiltBloomAssembly,
+// :301-345).  Not supported (exit with a message): -g, -C/-R, -T, --checkpoint (debug / experimental
+// outputs of the reference).
+#include "../../include/abyss_b200.h"
+#include "bloom_file.h"
+#include "reads.h"
+#include <getopt.h>
+#include <climits>
+#include <cmath>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <sstream>
+
+#define PROGRAM "abyss-bloom-dbg"
+#define MAX_KMER 192
+#define MAX_HASHES 32
+
+using namespace host;
+
+/** BloomDBG::AssemblyParams (BloomDBG/AssemblyParams.h:13-121) */
+struct AssemblyParams {
+	uint64_t bloomSize = 0;
+	uint64_t readsPerCheckpoint = UINT64_MAX;
+	bool keepCheckpoint = false;
+	std::string checkpointPathPrefix = "bloom-dbg-checkpoint";
+	unsigned minCov = 2;
+	std::string readLogPath, covTrackPath, graphPath;
+	unsigned numHashes = 4;
+	std::string bloomPath;
+	unsigned threads = 1;
+	unsigned k = 0, K = 0;
+	std::string refPath;
+	unsigned qrSeedLen = 0;
+	std::string spacedSeed;
+	unsigned trim = UINT_MAX;
+	int verbose = 0;
+	std::string outputPath, tracePath;
+	int device = 0; // B200 extension: --device=N
+	uint64_t batchReads = 4000000; // B200 extension: --batch-reads=N
+	bool initialized() const { return bloomSize > 0 && k > 0 && trim != UINT_MAX; }
+	void resetSpacedSeedParams()
+	{
+		spacedSeed.clear();
+		K = 0;
+		qrSeedLen = 0;
+	}
+};
+
+static const char VERSION_MESSAGE[] = PROGRAM " (abyss-b200) 0.1.0, command-line compatible with " PROGRAM " (ABySS) 2.3.10\n";
+
+static const char USAGE_MESSAGE[] =
+    "Usage: " PROGRAM " -b <bloom_size> -H <bloom_hashes> -k <kmer_size> \\\n"
+    "    [options] <FASTQ> [FASTQ]... > assembly.fasta\n"
+    "\n"
+    "Perform a de Bruijn graph assembly of the given FASTQ files on an NVIDIA B200.\n"
+    "\n"
+    "Basic Options:\n"
+    "\n"
+    "  -b  --bloom-size=N           overall memory budget for the assembly in bytes.\n"
+    "                               Unit suffixes 'k', 'M', or 'G' may be used. [required]\n"
+    "      --chastity               discard unchaste reads [default]\n"
+    "      --no-chastity            do not discard unchaste reads\n"
+    "      --help                   display this help and exit\n"
+    "  -H  --num-hashes=N           number of Bloom filter hash functions [4]\n"
+    "  -i  --input-bloom=FILE       load Bloom filter from FILE\n"
+    "  -j, --threads=N              accepted for compatibility (the GPU does the work) [1]\n"
+    "      --trim-masked            trim masked bases from the ends of reads [default]\n"
+    "      --no-trim-masked         do not trim masked bases from the ends of reads\n"
+    "  -k, --kmer=N                 the size of a k-mer [<=192]\n"
+    "      --kc=N                   ignore k-mers having a count < N [2]\n"
+    "  -o, --out=FILE               write the contigs to FILE [STDOUT]\n"
+    "  -q, --trim-quality=N         trim bases from the ends of reads whose quality is less than N\n"
+    "  -Q, --mask-quality=N         mask all low quality bases as `N'\n"
+    "      --standard-quality       zero quality is `!' (33) [default]\n"
+    "      --illumina-quality       zero quality is `@' (64)\n"
+    "  -t, --trim-length=N          max branch length to trim, in k-mers [k]\n"
+    "  -v, --verbose                display verbose output\n"
+    "      --version                output version information and exit\n"
+    "      --read-log=FILE          write outcome of processing each read to FILE\n"
+    "      --device=N               CUDA device to use [0]\n"
+    "      --batch-reads=N          reads per GPU batch [4000000]\n"
+    "\n"
+    "Spaced seeds (-K, --qr-seed, -s) are accepted by the hashing/insert stage only; -g, -C, -R, -T\n"
+    "and --checkpoint are not supported by the B200 implementation.\n";
+
+static AssemblyParams params;
+static ReadOpts ropt;
+
+enum { OPT_HELP = 1, OPT_VERSION, QR_SEED, MIN_KMER_COV, CHECKPOINT, KEEP_CHECKPOINT, CHECKPOINT_PREFIX, READ_LOG, OPT_DEVICE, OPT_BATCH };
+
+static int chastity = 1, trimMasked = 1, illuminaQ = 0;
+static const char shortopts[] = "b:C:g:H:i:j:k:K:o:q:Q:R:s:t:T:v";
+static const struct option longopts[] = {
+	{ "bloom-size", required_argument, NULL, 'b' },
+	{ "min-coverage", required_argument, NULL, 'c' },
+	{ "cov-track", required_argument, NULL, 'C' },
+	{ "chastity", no_argument, &chastity, 1 },
+	{ "no-chastity", no_argument, &chastity, 0 },
+	{ "graph", required_argument, NULL, 'g' },
+	{ "num-hashes", required_argument, NULL, 'H' },
+	{ "help", no_argument, NULL, OPT_HELP },
+	{ "input-bloom", required_argument, NULL, 'i' },
+	{ "threads", required_argument, NULL, 'j' },
+	{ "trim-masked", no_argument, &trimMasked, 1 },
+	{ "no-trim-masked", no_argument, &trimMasked, 0 },
+	{ "kmer", required_argument, NULL, 'k' },
+	{ "kc", required_argument, NULL, MIN_KMER_COV },
+	{ "single-kmer", required_argument, NULL, 'K' },
+	{ "out", required_argument, NULL, 'o' },
+	{ "trim-quality", required_argument, NULL, 'q' },
+	{ "mask-quality", required_argument, NULL, 'Q' },
+	{ "standard-quality", no_argument, &illuminaQ, 0 },
+	{ "illumina-quality", no_argument, &illuminaQ, 1 },
+	{ "qr-seed", required_argument, NULL, QR_SEED },
+	{ "ref", required_argument, NULL, 'R' },
+	{ "spaced-seed", required_argument, NULL, 's' },
+	{ "trim-length", required_argument, NULL, 't' },
+	{ "trace-file", required_argument, NULL, 'T' },
+	{ "verbose", no_argument, NULL, 'v' },
+	{ "version", no_argument, NULL, OPT_VERSION },
+	{ "checkpoint", required_argument, NULL, CHECKPOINT },
+	{ "keep-checkpoint", no_argument, NULL, KEEP_CHECKPOINT },
+	{ "checkpoint-prefix", required_argument, NULL, CHECKPOINT_PREFIX },
+	{ "read-log", required_argument, NULL, READ_LOG },
+	{ "device", required_argument, NULL, OPT_DEVICE },
+	{ "batch-reads", required_argument, NULL, OPT_BATCH },
+	{ NULL, 0, NULL, 0 }
+};
+
+static void check(int rc, const char* what)
+{
+	if (rc != ABB_OK) {
+		std::cerr << PROGRAM ": " << what << ": " << abb_last_error() << "\n";
+		exit(EXIT_FAILURE);
+	}
+}
+
+/** printCountingBloomStats (bloom-dbg.cc:177-188) */
+static void printCountingBloomStats(abb_filter* f, std::ostream& os)
+{
+	uint64_t nz = 0, th = 0;
+	check(abb_filter_popcount(f, &nz, &th), "popcount");
+	const double fpr = std::pow((double)th / (double)abb_filter_size(f), (double)abb_filter_hash_num(f));
+	os << "Counting Bloom filter stats:"
+	   << "\n\t#counters               = " << abb_filter_size(f)
+	   << "\n\t#size (B)               = " << abb_filter_size_in_bytes(f)
+	   << "\n\tthreshold               = " << abb_filter_threshold(f)
+	   << "\n\tpopcount                = " << th
+	   << "\n\tFPR                     = " << std::setprecision(3) << 100.f * fpr << "%"
+	   << "\n";
+}
+
+template <typename Fn>
+static void for_each_batch(const std::vector<std::string>& files, Fn fn)
+{
+	ReadBatch batch;
+	std::string id, seq;
+	for (const auto& path : files) {
+		if (params.verbose)
+			std::cerr << "Reading `" << path << "'...\n";
+		SeqReader in(path, ropt);
+		while (in.next(id, seq)) {
+			batch.add(id, seq);
+			if (batch.size() >= params.batchReads) {
+				fn(batch);
+				batch.clear();
+			}
+		}
+	}
+	if (batch.size())
+		fn(batch);
+}
+
+int main(int argc, char** argv)
+{
+	bool die = false;
+	for (int c; (c = getopt_long(argc, argv, shortopts, longopts, NULL)) != -1;) {
+		std::istringstream arg(optarg != NULL ? optarg : "");
+		switch (c) {
+		case '?': die = true; break;
+		case 'b':
+			if (!si_to_bytes(optarg, &params.bloomSize)) {
+				std::cerr << PROGRAM ": invalid option: `-b" << optarg << "'\n";
+				exit(EXIT_FAILURE);
+			}
+			arg.seekg(0, std::ios::end);
+			arg.clear(std::ios::eofbit);
+			break;
+		case 'C': arg >> params.covTrackPath; break;
+		case 'g': arg >> params.graphPath; break;
+		case 'H': arg >> params.numHashes; break;
+		case 'i': arg >> params.bloomPath; break;
+		case 'j': arg >> params.threads; break;
+		case 'k': arg >> params.k; break;
+		case 'K': params.resetSpacedSeedParams(); arg >> params.K; break;
+		case 'o': arg >> params.outputPath; break;
+		case 'q': arg >> ropt.qualityThreshold; break;
+		case 'R': arg >> params.refPath; break;
+		case 's': params.resetSpacedSeedParams(); arg >> params.spacedSeed; break;
+		case 't': arg >> params.trim; break;
+		case 'T': arg >> params.tracePath; break;
+		case 'Q': arg >> ropt.internalQThreshold; break;
+		case 'v': ++params.verbose; break;
+		case OPT_HELP: std::cout << USAGE_MESSAGE; exit(EXIT_SUCCESS);
+		case MIN_KMER_COV: arg >> params.minCov; break;
+		case OPT_VERSION: std::cout << VERSION_MESSAGE; exit(EXIT_SUCCESS);
+		case QR_SEED: params.resetSpacedSeedParams(); arg >> params.qrSeedLen; break;
+		case CHECKPOINT: arg >> params.readsPerCheckpoint; break;
+		case KEEP_CHECKPOINT: params.keepCheckpoint = true; break;
+		case CHECKPOINT_PREFIX: arg >> params.checkpointPathPrefix; break;
+		case READ_LOG: arg >> params.readLogPath; break;
+		case OPT_DEVICE: arg >> params.device; break;
+		case OPT_BATCH: arg >> params.batchReads; break;
+		}
+		if (optarg != NULL && (!arg.eof() || arg.fail())) {
+			std::cerr << PROGRAM ": invalid option: `-" << (char)c << optarg << "'\n";
+			exit(EXIT_FAILURE);
+		}
+	}
+	ropt.chastityFilter = chastity;
+	ropt.trimMasked = trimMasked;
+	ropt.qualityOffset = illuminaQ ? 64 : 0;
+
+	if (params.bloomPath.empty() && params.bloomSize == 0) {
+		std::cerr << PROGRAM ": missing mandatory option `-b'\n";
+		die = true;
+	}
+	if (params.bloomPath.empty() && params.k == 0) {
+		std::cerr << PROGRAM ": missing mandatory option `-k'\n";
+		die = true;
+	}
+	if (params.k > 0 && params.K > 0 && params.K > params.k / 2) {
+		std::cerr << PROGRAM ": value of `-K' must be <= k/2\n";
+		die = true;
+	}
+	if (params.numHashes > MAX_HASHES) {
+		std::cerr << PROGRAM ": number of hash functions (`-H`) must be <= " << MAX_HASHES << "\n";
+		die = true;
+	}
+	if (params.k > MAX_KMER) {
+		std::cerr << PROGRAM ": k-mer size (`-k`) must be <= " << MAX_KMER << "\n";
+		die = true;
+	}
+	if (params.k > 0 && params.qrSeedLen > 0 && (params.qrSeedLen < 11 || params.qrSeedLen > params.k / 2)) {
+		std::cerr << PROGRAM ": value of `--qr-seed' must be >= 11 and <= k/2\n";
+		die = true;
+	}
+	if (!params.covTrackPath.empty() && params.refPath.empty()) {
+		std::cerr << PROGRAM ": you must specify a reference with `-R' when using `-C'\n";
+		die = true;
+	}
+	if (params.k > 0 && params.trim == UINT_MAX)
+		params.trim = params.k;
+	if (argc - optind < 1) {
+		std::cerr << PROGRAM ": missing input file arguments\n";
+		die = true;
+	}
+	if (die) {
+		std::cerr << "Try `" << PROGRAM << " --help' for more information.\n";
+		exit(EXIT_FAILURE);
+	}
+	if (!params.graphPath.empty() || !params.covTrackPath.empty() || !params.tracePath.empty() ||
+	    params.readsPerCheckpoint != UINT64_MAX) {
+		std::cerr << PROGRAM ": -g, -C, -T and --checkpoint are not supported by the B200 implementation\n";
+		exit(EXIT_FAILURE);
+	}
+	if (params.K > 0 || params.qrSeedLen > 0 || !params.spacedSeed.empty()) {
+		std::cerr << PROGRAM ": spaced seeds are not supported by the unitig extension stage yet\n";
+		exit(EXIT_FAILURE);
+	}
+
+	/* the `:' separator: files before it load the filter, files after it are assembled (BloomIO.h:104-113) */
+	std::vector<std::string> loadFiles, asmFiles;
+	{
+		bool sep = false;
+		std::vector<std::string> all(argv + optind, argv + argc);
+		for (auto& a : all) {
+			if (a == ":") {
+				sep = true;
+				continue;
+			}
+			(sep ? asmFiles : loadFiles).push_back(a);
+		}
+		if (!sep)
+			asmFiles = loadFiles;
+	}
+
+	std::ofstream outputFile;
+	if (!params.outputPath.empty()) {
+		outputFile.open(params.outputPath.c_str());
+		if (!outputFile) {
+			std::cerr << "error: `" << params.outputPath << "': " << strerror(errno) << "\n";
+			exit(EXIT_FAILURE);
+		}
+	}
+	std::ostream& out = params.outputPath.empty() ? std::cout : outputFile;
+
+	abb_filter* bloom = nullptr;
+	if (!params.bloomPath.empty()) {
+		/* prebuiltBloomAssembly (bloom-dbg.cc:301-345) */
+		if (params.verbose)
+			std::cerr << "Loading prebuilt Bloom filter from `" << params.bloomPath << "'\n";
+		BloomHeader h;
+		std::vector<uint8_t> raw;
+		read_counting_bloom(params.bloomPath, h, raw);
+		params.k = h.kmerSize;
+		params.numHashes = h.hashNum;
+		params.bloomSize = h.sizeInBytes;
+		if (params.trim == UINT_MAX)
+			params.trim = params.k;
+		check(abb_filter_create(&bloom, ABB_COUNTING, h.size, h.hashNum, h.kmerSize, params.minCov, "", params.device), "filter");
+		check(abb_filter_upload(bloom, 0, raw.data(), raw.size()), "upload");
+		printCountingBloomStats(bloom, std::cerr);
+	} else {
+		/* countingBloomAssembly (bloom-dbg.cc:347-386) */
+		if (params.verbose)
+			std::cerr << "Assembling with k-mer size " << params.k << "\n";
+		const double sz = (double)params.bloomSize / 1.125;
+		uint64_t counters = (uint64_t)std::llround(sz);
+		if (counters % 64)
+			counters += 64 - counters % 64;
+		check(abb_filter_create(&bloom, ABB_COUNTING, counters, params.numHashes, params.k, params.minCov, "", params.device), "filter");
+		uint64_t readCount = 0;
+		for_each_batch(loadFiles, [&](ReadBatch& b) {
+			check(abb_insert_reads(bloom, b.bases.data(), b.offsets.data(), b.size(), nullptr), "insert");
+			readCount += b.size();
+			if (params.verbose)
+				std::cerr << "Loaded " << readCount << " reads into Bloom filter\n";
+		});
+		if (params.verbose) {
+			uint64_t nz = 0;
+			check(abb_filter_popcount(bloom, &nz, nullptr), "popcount");
+			std::cerr << "Bloom filter FPR: " << std::setprecision(3)
+			          << 100 * std::pow((double)nz / (double)abb_filter_size(bloom), (double)params.numHashes) << "%\n";
+			printCountingBloomStats(bloom, std::cerr);
+		}
+	}
+
+	/* BloomDBG::assemble (bloom-dbg.h:900-1089) */
+	if (params.verbose)
+		std::cerr << "Trimming branches " << params.trim << " k-mers or shorter\n";
+	abb_assembly_params ap = { params.trim, (unsigned)params.verbose, params.readLogPath.empty() ? 0u : 1u, 0u };
+	abb_assembler* as = nullptr;
+	check(abb_assembler_create(&as, bloom, &ap), "assembler");
+	std::ofstream readLog;
+	static const char* names[] = { "SHORTER_THAN_K", "NON_ACGT", "BLUNT_END", "NOT_SOLID", "ALL_KMERS_VISITED", "GENERATED_CONTIGS", "NA" };
+	if (!params.readLogPath.empty()) {
+		readLog.open(params.readLogPath.c_str());
+		readLog << "read_id\tresult\n";
+	}
+	uint64_t contigID = 0, readBase = 0;
+	for_each_batch(asmFiles, [&](ReadBatch& b) {
+		const abb_contig* contigs = nullptr;
+		uint64_t n = 0;
+		const char* seqs = nullptr;
+		check(abb_assembler_process_reads(as, b.bases.data(), b.offsets.data(), b.size(), &contigs, &n, &seqs), "assemble");
+		for (uint64_t i = 0; i < n; ++i) {
+			const abb_contig& c = contigs[i];
+			/* printContig (bloom-dbg.h:455-487) */
+			out << '>' << contigID++ << ' ' << c.length << ' ' << c.coverage << " read:" << b.ids[c.seed_read - readBase] << '\n';
+			out.write(seqs + c.seq_offset, c.length);
+			out << '\n';
+		}
+		if (readLog.is_open()) {
+			const uint8_t* codes = nullptr;
+			uint64_t nc = 0;
+			check(abb_assembler_read_results(as, &codes, &nc), "read results");
+			for (uint64_t i = 0; i < nc; ++i)
+				readLog << b.ids[i] << '\t' << names[codes[i] > 6 ? 6 : codes[i]] << '\n';
+		}
+		readBase += b.size();
+		if (params.verbose) {
+			abb_assembly_counters cn;
+			abb_assembler_counters(as, &cn);
+			std::cerr << "Processed " << cn.reads_processed << " reads, solid reads: " << cn.solid_reads
+			          << ", visited reads: " << cn.visited_reads << "\nAssembled " << cn.bases_assembled << " bp in "
+			          << cn.contig_id << " contigs\n";
+		}
+	});
+	if (params.verbose)
+		std::cerr << "Assembly complete\n";
+	abb_assembler_destroy(as);
+	abb_filter_destroy(bloom);
+	if (!params.outputPath.empty())
+		outputFile.close();
+	return EXIT_SUCCESS;
+}

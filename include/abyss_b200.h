@@ -143,6 +143,10 @@ int abb_assembler_destroy(abb_assembler* a);
 int abb_assembler_process_reads(abb_assembler* a, const char* bases, const uint64_t* offsets,
                                 uint64_t n_reads, const abb_contig** contigs, uint64_t* n_contigs,
                                 const char** seqs);
+/* same with device-resident read buffers (no host<->device copy of the reads inside the call) */
+int abb_assembler_process_reads_dev(abb_assembler* a, const char* d_bases, const uint64_t* d_offsets,
+                                    uint64_t n_reads, const abb_contig** contigs, uint64_t* n_contigs,
+                                    const char** seqs);
 int abb_assembler_counters(const abb_assembler* a, abb_assembly_counters* out);
 /* optional per-read outcome log of the last batch (ReadResult, bloom-dbg.h:256-293);
  * codes: 0 SHORTER_THAN_K, 1 NON_ACGT, 2 BLUNT_END, 3 NOT_SOLID, 4 ALL_KMERS_VISITED,
@@ -150,6 +154,17 @@ int abb_assembler_counters(const abb_assembler* a, abb_assembly_counters* out);
 int abb_assembler_read_results(const abb_assembler* a, const uint8_t** codes, uint64_t* n);
 /* access to the assembled-k-mer bit filter (for checkpoints / tests) */
 abb_filter* abb_assembler_assembled_filter(abb_assembler* a);
+
+typedef struct abb_assembly_stats {
+	uint64_t rounds;            /* speculation rounds (K3b -> K4 -> K5) */
+	uint64_t speculated_reads;  /* reads extended by K4 */
+	uint64_t wasted_reads;      /* speculated reads found already assembled at replay */
+	uint64_t candidates;        /* solid, non-blunt reads */
+	uint64_t contigs_tried;     /* unitigs produced by K4 (before the redundancy test) */
+	uint64_t launches;          /* kernels launched by the assembler */
+	float ms_classify, ms_visited, ms_extend, ms_replay; /* CUDA-event time per phase */
+} abb_assembly_stats;
+int abb_assembler_stats(const abb_assembler* a, abb_assembly_stats* out);
 
 /* ---- profiling hooks used by bench.py ---------------------------------------------------- */
 typedef struct abb_insert_stats {
@@ -159,8 +174,14 @@ typedef struct abb_insert_stats {
 	uint64_t deferred;        /* events that lost a reservation and went through the ordered pass */
 	uint64_t launches;        /* kernels launched by this library since the last reset */
 	float ms_hash, ms_insert; /* CUDA-event time on the library stream since the last reset */
+	float ms_commit;          /* with profiling on: summed CUDA-event time of the k_commit launches */
+	uint64_t commit_launches; /* number of k_commit launches timed */
 } abb_insert_stats;
 int abb_filter_insert_stats(abb_filter* f, abb_insert_stats* out, int reset);
+/* time each launch of the Bloom-insert commit kernel with CUDA events (bench.py roofline) */
+int abb_filter_set_profiling(abb_filter* f, int on);
+/* the cudaStream_t all work of this filter (and of an assembler created on it) is issued to */
+void* abb_filter_stream(abb_filter* f);
 /* tuning: ordered-window size in k-mer slots (power of two, <= 2^20); 0 = default */
 int abb_filter_set_window(abb_filter* f, uint64_t window_slots);
 

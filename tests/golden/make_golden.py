@@ -132,6 +132,13 @@ def main():
         c["bloom_header"] = blob[:blob.index(tag) + len(tag)].decode()
         c["counters_sha256"] = hashlib.sha256(raw).hexdigest()
         c["counters_nonzero"] = int(np.count_nonzero(np.frombuffer(raw, dtype=np.uint8)))
+        # `abyss-bloom build -t rolling-hash -l 2`: whole file (header + last level) sha256
+        rh = os.path.join(tmp, c["name"] + ".rh.bloom")
+        subprocess.run([BLOOM, "build", "-k", str(c["k"]), "-t", "rolling-hash", "-l", "2", f"-H{c['H']}", f"-b{counters // 4}", "-j1", rh, fq],
+                       check=True, capture_output=True)
+        c["rolling_hash_l2_b"] = counters // 4
+        c["rolling_hash_l2_file_sha256"] = hashlib.sha256(open(rh, "rb").read()).hexdigest()
+        c["counting_file_sha256"] = hashlib.sha256(blob).hexdigest()
         print(c["name"], c["n_reads"], c["n_contigs"], counters, c["counters_nonzero"])
     json.dump(cases, open(os.path.join(HERE, "e2e_cases.json"), "w"), indent=1)
 

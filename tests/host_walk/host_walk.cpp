@@ -53,6 +53,12 @@ struct HostCtx {
 		}
 		return m;
 	}
+	struct Probe {
+		unsigned mask;
+	};
+	template <int KW>
+	Probe neighbors_issue(const Vtx<KW>& v) { return Probe{ neighbors(v) }; }
+	unsigned neighbors_finish(const Probe& p) { return p.mask; }
 	uint64_t rd64(const uint64_t* p) { return *p; }
 	void wr64(uint64_t* p, uint64_t v) { *p = v; }
 	uint8_t rd8(const uint8_t* p) { return *p; }

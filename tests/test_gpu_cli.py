@@ -1,0 +1,70 @@
+"""GPU: the C++ command-line programs (abyss-bloom-dbg, abyss-bloom build) over libabyssb200 produce
+the same bytes as the unmodified reference binaries (committed goldens)."""
+import hashlib
+import json
+import os
+import subprocess
+
+import pytest
+
+from abyss_b200.synth import ReadSet
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "abyss_b200", "lib")
+
+
+@pytest.fixture(scope="module")
+def cases(tmp_path_factory, abb):
+    d = tmp_path_factory.mktemp("cli")
+    out = {}
+    for c in json.load(open(os.path.join(ROOT, "tests", "golden", "e2e_cases.json"))):
+        rs = ReadSet.from_coverage(c["seed"], c["genome"], c["cov"], c["L"], c["err"])
+        fq = str(d / (c["name"] + ".fq"))
+        rs.write_fastq(fq)
+        out[c["name"]] = (c, fq, d)
+    return out
+
+
+@pytest.mark.parametrize("name", ["e2e_g20k_k32", "e2e_g30k_k64", "e2e_g10k_k25_small"])
+def test_abyss_bloom_dbg_cli(cases, name):
+    c, fq, d = cases[name]
+    fa = str(d / (name + ".fa"))
+    log = str(d / (name + ".log"))
+    r = subprocess.run([os.path.join(BIN, "abyss-bloom-dbg"), f"-k{c['k']}", f"--kc={c['kc']}", f"-b{c['b']}", f"-H{c['H']}", "-j1",
+                        "--batch-reads=1500", f"--read-log={log}", "-o", fa, fq], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    golden = os.path.join(ROOT, "tests", "golden")
+    assert open(fa).read() == open(os.path.join(golden, name + ".fa")).read()
+    assert open(log).read() == open(os.path.join(golden, name + ".readlog.tsv")).read()
+
+
+def test_abyss_bloom_build_and_prebuilt(cases):
+    c, fq, d = cases["e2e_g20k_k32"]
+    bf = str(d / "counting.bloom")
+    r = subprocess.run([os.path.join(BIN, "abyss-bloom"), "build", "-k", str(c["k"]), "-t", "counting", f"-b{c['counters']}",
+                        f"-H{c['H']}", bf, fq], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert hashlib.sha256(open(bf, "rb").read()).hexdigest() == c["counting_file_sha256"]
+    # -i FILE: prebuiltBloomAssembly gives the same unitigs as the de novo run
+    fa = str(d / "prebuilt.fa")
+    r = subprocess.run([os.path.join(BIN, "abyss-bloom-dbg"), f"--kc={c['kc']}", "-i", bf, "-o", fa, fq], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert open(fa).read() == open(os.path.join(ROOT, "tests", "golden", "e2e_g20k_k32.fa")).read()
+    # rolling-hash cascading filter, 2 levels: file identical to the reference's
+    rh = str(d / "rh.bloom")
+    r = subprocess.run([os.path.join(BIN, "abyss-bloom"), "build", "-k", str(c["k"]), "-t", "rolling-hash", "-l", "2", f"-H{c['H']}",
+                        f"-b{c['rolling_hash_l2_b']}", rh, fq], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert hashlib.sha256(open(rh, "rb").read()).hexdigest() == c["rolling_hash_l2_file_sha256"]
+
+
+def test_cli_errors(cases):
+    c, fq, d = cases["e2e_g20k_k32"]
+    exe = os.path.join(BIN, "abyss-bloom-dbg")
+    r = subprocess.run([exe, "-k32", fq], capture_output=True, text=True)
+    assert r.returncode != 0 and "missing mandatory option `-b'" in r.stderr
+    r = subprocess.run([exe, "-b1M", fq], capture_output=True, text=True)
+    assert r.returncode != 0 and "missing mandatory option `-k'" in r.stderr
+    r = subprocess.run([exe, "-b1M", "-k32"], capture_output=True, text=True)
+    assert r.returncode != 0 and "missing input file arguments" in r.stderr
