@@ -24,6 +24,7 @@
 #include "abb_common.h"
 #include "abb_walk.cuh"
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -33,6 +34,11 @@ namespace abb {
 // ------------------------------------------------------------------------------------------
 // device context: the Ctx concept of abb_walk.cuh for one warp
 // ------------------------------------------------------------------------------------------
+__host__ __device__ inline uint64_t tile_slot(uint64_t key, unsigned cls, unsigned mask)
+{
+	return (((key ^ (0x9E3779B97F4A7C15ULL * (cls + 1))) * 0xD6E8FEB86659FD93ULL) >> 24) & mask;
+}
+
 struct WarpCtx {
 	unsigned k, trim;
 	RollTab rt;
@@ -46,6 +52,25 @@ struct WarpCtx {
 	unsigned long long arena_size;
 	unsigned long long* arena_top;
 	unsigned fail_;
+	// tiles (null table = disabled)
+	const TileRec* tile_recs;
+	const unsigned* tile_tab; // open addressing: tile index + 1, 0 = empty
+	unsigned tile_mask;
+
+	__device__ bool tiles_enabled() const { return tile_tab != nullptr; }
+	__device__ const TileRec* tile_lookup(uint64_t key, unsigned cls) const
+	{
+		for (uint64_t s = tile_slot(key, cls, tile_mask);; s = (s + 1) & tile_mask) {
+			const unsigned v = __ldcg(tile_tab + s);
+			if (v == 0)
+				return nullptr;
+			const TileRec* t = tile_recs + (v - 1);
+			if (t->key == key && t->cls == cls)
+				return t;
+		}
+	}
+	__device__ uint32_t tile_index(const TileRec* t) const { return (uint32_t)(t - tile_recs); }
+	__device__ void wr32(uint32_t* p, uint32_t v) const { *(volatile uint32_t*)p = v; }
 
 	/** bits 0-3: out-neighbours (append A,C,G,T) present in the solid filter; bits 4-7: in-neighbours
 	 *  (prepend).  Lane = 4 * neighbour + hash slot: 8 neighbours x 4 hash functions per round trip
@@ -145,7 +170,7 @@ struct WarpCtx {
 		}
 		__syncwarp();
 	}
-	__device__ void mark_covered(const PathSet& ps, const uint64_t* rh, uint8_t* cov, unsigned nk, const ContigOut& o) const
+	__device__ void mark_covered(const PathSet& ps, const uint64_t* rh, uint8_t* cov, unsigned nk, const ContigOut& o)
 	{
 		for (unsigned j = lane; j < nk; j += 32) {
 			if (cov[j])
@@ -156,6 +181,64 @@ struct WarpCtx {
 			if ((o.popped_front && key == o.front_h) || (o.popped_back && key == o.back_h))
 				continue;
 			cov[j] = 1;
+		}
+		__syncwarp();
+		if (o.tiles_left.n + o.tiles_right.n == 0)
+			return;
+		// the spliced tiles' vertices are not in the PathSet: stream their hashes against a small
+		// table of the read's k-mer hashes
+		unsigned cap = 64;
+		while (cap < 2 * nk)
+			cap <<= 1;
+		uint64_t* keys = (uint64_t*)alloc((unsigned long long)cap * 8, true);
+		uint8_t* hit = alloc(cap, true);
+		if (!keys || !hit)
+			return;
+		for (unsigned j = lane; j < nk; j += 32) {
+			const uint64_t key = rh[j] ? rh[j] : 1; // 0 marks an empty slot; hash 0 is remapped (2^-64)
+			for (uint64_t t = pathset_slot(key, cap);; t = (t + 1) & (cap - 1)) {
+				const unsigned long long old = atomicCAS((unsigned long long*)(keys + t), 0ULL, (unsigned long long)key);
+				if (old == 0ULL || old == key)
+					break;
+			}
+		}
+		__syncwarp();
+		for (int side = 0; side < 2; ++side) {
+			const U32Vec& tv = side ? o.tiles_right : o.tiles_left;
+			for (unsigned ti = 0; ti < tv.n; ++ti) {
+				const TileRec* T = tile_recs + tv.p[ti];
+				for (unsigned i = lane; i < T->n; i += 32) {
+					uint64_t key = T->hashes[i];
+					if ((o.popped_front && key == o.front_h) || (o.popped_back && key == o.back_h))
+						continue;
+					key = key ? key : 1;
+					for (uint64_t t = pathset_slot(key, cap);; t = (t + 1) & (cap - 1)) {
+						const uint64_t v = keys[t];
+						if (v == key) {
+							hit[t] = 1;
+							break;
+						}
+						if (v == 0)
+							break;
+					}
+				}
+			}
+		}
+		__syncwarp();
+		for (unsigned j = lane; j < nk; j += 32) {
+			if (cov[j])
+				continue;
+			const uint64_t key = rh[j] ? rh[j] : 1;
+			for (uint64_t t = pathset_slot(key, cap);; t = (t + 1) & (cap - 1)) {
+				const uint64_t v = keys[t];
+				if (v == key) {
+					if (hit[t])
+						cov[j] = 1;
+					break;
+				}
+				if (v == 0)
+					break;
+			}
 		}
 		__syncwarp();
 	}
@@ -169,7 +252,8 @@ struct ContigRec {
 	unsigned len;
 	unsigned seed_pos;
 	unsigned psize;
-	unsigned char left, right, pad0, pad1;
+	unsigned char left, right, flags, pad1; // flags: 1 pushed_front, 2 pushed_back, 4 popped_front, 8 popped_back
+	unsigned long long front_h, back_h;     // canonical hashes of trimmed-off end vertices (flags 4 / 8)
 };
 
 struct DevEmit {
@@ -191,7 +275,10 @@ struct DevEmit {
 				r.psize = o.psize;
 				r.left = (unsigned char)o.left;
 				r.right = (unsigned char)o.right;
-				r.pad0 = r.pad1 = 0;
+				r.flags = (unsigned char)((o.pushed_front ? 1 : 0) | (o.pushed_back ? 2 : 0) | (o.popped_front ? 4 : 0) | (o.popped_back ? 8 : 0));
+				r.pad1 = 0;
+				r.front_h = o.front_h;
+				r.back_h = o.back_h;
 				recs[idx] = r;
 			}
 		}
@@ -203,6 +290,13 @@ struct WalkCfg {
 	unsigned k, trim, threshold;
 	RollTab rt;
 	const uint8_t* counters;
+};
+
+/** device view of the tile store (tab == nullptr: tiles disabled) */
+struct TileView {
+	const TileRec* recs;
+	const unsigned* tab;
+	unsigned mask;
 };
 
 __device__ __forceinline__ WarpCtx make_ctx(const WalkCfg& w, const HashCfg* cfg, Frame* frames, uint64_t* look, unsigned gwarp,
@@ -222,6 +316,9 @@ __device__ __forceinline__ WarpCtx make_ctx(const WalkCfg& w, const HashCfg* cfg
 	c.arena_size = arena_size;
 	c.arena_top = arena_top;
 	c.fail_ = 0;
+	c.tile_recs = nullptr;
+	c.tile_tab = nullptr;
+	c.tile_mask = 0;
 	return c;
 }
 
@@ -327,12 +424,15 @@ __global__ void __launch_bounds__(kWalkWarps * 32)
 k_extend(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offs, const unsigned* __restrict__ spec, unsigned n_spec,
          WalkCfg w, const __grid_constant__ HashCfg cfg, Frame* frames, uint64_t* look, uint8_t* arena,
          unsigned long long arena_size, unsigned long long* arena_top, ContigRec* recs, unsigned* nrecs, unsigned rec_cap,
-         unsigned* __restrict__ status)
+         unsigned* __restrict__ status, TileView tv)
 {
 	const unsigned gwarp = blockIdx.x * kWalkWarps + (threadIdx.x >> 5);
 	if (gwarp >= n_spec)
 		return;
 	WarpCtx c = make_ctx(w, &cfg, frames, look, gwarp, arena, arena_size, arena_top);
+	c.tile_recs = tv.recs;
+	c.tile_tab = tv.tab;
+	c.tile_mask = tv.mask;
 	const unsigned r = spec[gwarp];
 	const uint64_t beg = offs[r];
 	const unsigned L = (unsigned)(offs[r + 1] - beg);
@@ -340,6 +440,188 @@ k_extend(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offs, c
 	const bool ok = walk_read<KW>(c, bases + beg, L, emit);
 	if (c.lane == 0)
 		status[gwarp] = ok ? 0u : (c.fail_ ? c.fail_ : 1u);
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Tiles (abb_walk.cuh): marker enumeration, production, and the repeat check that guards them
+// ------------------------------------------------------------------------------------------
+/** every valid, solid k-mer slot whose canonical hash is a marker and that is not yet in the marker
+ *  set joins the list of new markers as (read, window) */
+__global__ void __launch_bounds__(256)
+k_find_markers(const uint64_t* __restrict__ h0, const uint8_t* __restrict__ valid, const uint64_t* __restrict__ slot_offs,
+               uint64_t n_reads, uint64_t n_slots, WalkCfg w, const __grid_constant__ HashCfg cfg, unsigned long long* mset,
+               unsigned mset_mask, unsigned long long* __restrict__ out /* packed (read << 24 | pos) */, unsigned* n_out,
+               unsigned out_cap)
+{
+	for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n_slots; s += (uint64_t)gridDim.x * blockDim.x) {
+		const uint64_t h = h0[s];
+		if (!is_marker(h) || !valid[s])
+			continue;
+		bool solid = true;
+		for (unsigned i = 0; i < cfg.H; ++i)
+			solid &= __ldcg(w.counters + nth_pos(h, cfg, i)) >= w.threshold;
+		if (!solid)
+			continue;
+		const unsigned long long key = h ? h : 1;
+		bool fresh = false;
+		for (uint64_t t = pathset_slot(key, mset_mask + 1);; t = (t + 1) & mset_mask) {
+			const unsigned long long old = atomicCAS(mset + t, 0ULL, key);
+			if (old == 0ULL) {
+				fresh = true;
+				break;
+			}
+			if (old == key)
+				break;
+		}
+		if (!fresh)
+			continue;
+		// which read does slot s belong to? upper_bound over slot_offs
+		uint64_t lo = 0, hi = n_reads;
+		while (lo < hi) {
+			const uint64_t mid = (lo + hi) / 2;
+			if (slot_offs[mid + 1] <= s)
+				lo = mid + 1;
+			else
+				hi = mid;
+		}
+		const unsigned idx = atomicAdd(n_out, 1u);
+		if (idx < out_cap)
+			out[idx] = (unsigned long long)lo << 24 | (unsigned long long)(s - slot_offs[lo]);
+	}
+}
+
+struct TileStore { // device-side handles used while producing tiles
+	TileRec* recs;
+	unsigned* tab;
+	unsigned mask;
+	unsigned cap;          // capacity of recs
+	unsigned* n_recs;
+	uint8_t* pool;
+	unsigned long long pool_size;
+	unsigned long long* pool_top;
+};
+
+/** persistent warps: work item = (new marker, w) with w = 2 * use_revcomp + direction */
+template <int KW>
+__global__ void __launch_bounds__(kWalkWarps * 32)
+k_make_tiles(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offs, const unsigned long long* __restrict__ markers,
+             unsigned n_markers, unsigned* work, WalkCfg w, const __grid_constant__ HashCfg cfg, Frame* frames, uint64_t* look,
+             uint8_t* stage_bases, uint64_t* stage_hashes, TileStore ts)
+{
+	const unsigned gwarp = blockIdx.x * kWalkWarps + (threadIdx.x >> 5);
+	WarpCtx c = make_ctx(w, &cfg, frames, look, gwarp, nullptr, 0, nullptr);
+	uint8_t* sb = stage_bases + (size_t)gwarp * kTileCap;
+	uint64_t* sh = stage_hashes + (size_t)gwarp * kTileCap;
+	const unsigned total = n_markers * 4;
+	for (;;) {
+		unsigned item = 0;
+		if (c.lane == 0)
+			item = atomicAdd(work, 1u);
+		item = __shfl_sync(0xffffffffu, item, 0);
+		if (item >= total)
+			break;
+		const unsigned long long mk = markers[item >> 2];
+		const uint64_t r = mk >> 24;
+		const unsigned pos = (unsigned)(mk & 0xffffff);
+		Vtx<KW> v = vtx_from_codes<KW>(bases + offs[r] + pos, w.k, true);
+		if (item & 2)
+			v = vtx_revcomp(v, w.k);
+		TileRec t;
+		c.fail_ = 0;
+		make_tile(c, v, (item & 1) ? REV : FWD, &t, sb, sh);
+		if (c.fail_)
+			continue; // scratch overflow inside successor(): no tile, walks pass this marker vertex by vertex
+		// store: hashes then bases, 16-byte aligned
+		const unsigned long long bytes = ((unsigned long long)t.n * 9 + 15) & ~15ULL;
+		unsigned long long off = 0;
+		unsigned idx = 0;
+		if (c.lane == 0) {
+			off = atomicAdd(ts.pool_top, bytes);
+			idx = atomicAdd(ts.n_recs, 1u);
+		}
+		off = __shfl_sync(0xffffffffu, off, 0);
+		idx = __shfl_sync(0xffffffffu, idx, 0);
+		if (off + bytes > ts.pool_size || idx >= ts.cap)
+			continue; // store full: same graceful degradation
+		uint64_t* dh = reinterpret_cast<uint64_t*>(ts.pool + off);
+		uint8_t* db = ts.pool + off + 8ULL * t.n;
+		for (unsigned i = c.lane; i < t.n; i += 32) {
+			dh[i] = sh[i];
+			db[i] = sb[i];
+		}
+		t.hashes = dh;
+		t.bases = db;
+		__syncwarp();
+		if (c.lane == 0) {
+			ts.recs[idx] = t;
+			__threadfence();
+			for (uint64_t s = tile_slot(t.key, t.cls, ts.mask);; s = (s + 1) & ts.mask) {
+				const unsigned old = atomicCAS(ts.tab + s, 0u, idx + 1);
+				if (old == 0u)
+					break;
+				const TileRec* o = ts.recs + (old - 1);
+				if (o->key == t.key && o->cls == t.cls)
+					break; // palindromic marker: the same (key, class) twice, keep the first
+			}
+		}
+	}
+}
+
+/** a canonical hash occurring twice in one (untrimmed) path means the tile splice skipped an
+ *  ER_CYCLE: flag the contig.  key = hash mixed with the contig index; a clash between different
+ *  (hash, contig) pairs only causes a harmless extra fallback. */
+__global__ void __launch_bounds__(256)
+k_repeat_check(const ContigRec* __restrict__ recs, unsigned n_contigs, const uint64_t* __restrict__ cslot,
+               const uint64_t* __restrict__ ch0, unsigned long long* tab, uint64_t tab_mask, uint8_t* __restrict__ flag)
+{
+	const uint64_t total = cslot[n_contigs];
+	for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < total + 2ULL * n_contigs;
+	     s += (uint64_t)gridDim.x * blockDim.x) {
+		unsigned c;
+		uint64_t h;
+		if (s < total) {
+			// contig of slot s
+			unsigned lo = 0, hi = n_contigs;
+			while (lo < hi) {
+				const unsigned mid = (lo + hi) / 2;
+				if (cslot[mid + 1] <= s)
+					lo = mid + 1;
+				else
+					hi = mid;
+			}
+			c = lo;
+			const uint64_t j = s - cslot[c], nk = cslot[c + 1] - cslot[c];
+			const unsigned fl = recs[c].flags;
+			if (((fl & 1) && j == 0) || ((fl & 2) && j == nk - 1))
+				continue; // preprocessCircularContig's intentional duplicate
+			h = ch0[s];
+		} else {
+			// the trimmed-off end vertices
+			const uint64_t e = s - total;
+			c = (unsigned)(e >> 1);
+			const unsigned fl = recs[c].flags;
+			if (e & 1) {
+				if (!(fl & 8))
+					continue;
+				h = recs[c].back_h;
+			} else {
+				if (!(fl & 4))
+					continue;
+				h = recs[c].front_h;
+			}
+		}
+		unsigned long long key = (h ^ (0x9E3779B97F4A7C15ULL * (c + 1))) | 1ULL;
+		for (uint64_t t = (key * 0xD6E8FEB86659FD93ULL >> 20) & tab_mask;; t = (t + 1) & tab_mask) {
+			const unsigned long long old = atomicCAS(tab + t, 0ULL, key);
+			if (old == 0ULL)
+				break;
+			if (old == key) {
+				flag[c] = 1;
+				break;
+			}
+		}
+	}
 }
 
 /** dense ASCII copies of the ordered unitigs (pathToSeq output as characters) */
@@ -624,6 +906,24 @@ struct abb_assembler {
 	unsigned* d_ends_n = nullptr;
 	uint64_t ends_upper = 0; // upper bound on entries
 
+	// tile store (abb_walk.cuh "Tiles"); persistent across batches
+	bool tiles_on = true;
+	TileRec* d_tiles = nullptr;
+	unsigned tile_cap = 0;
+	unsigned* d_tile_tab = nullptr;
+	unsigned tile_tab_mask = 0;
+	unsigned* d_tile_n = nullptr;       // [0] tiles stored, [1] work counter, [2] new markers
+	uint8_t* d_tile_pool = nullptr;
+	unsigned long long tile_pool_size = 0;
+	unsigned long long* d_tile_pool_top = nullptr;
+	unsigned long long* d_marker_set = nullptr;
+	unsigned marker_set_mask = 0;
+	DevBuf<unsigned long long> new_markers, rep_tab;
+	DevBuf<uint8_t> stage_bases, rep_flag;
+	DevBuf<uint64_t> stage_hashes;
+	uint64_t st_markers = 0, st_tiles = 0, st_fallbacks = 0;
+	float ms_tiles = 0;
+
 	// speculation control
 	unsigned spec_target = 1024;
 	// host outputs of the last batch
@@ -734,6 +1034,207 @@ int h2d(DevBuf<T>& d, const std::vector<T>& h, cudaStream_t s)
 	return ABB_OK;
 }
 
+TileView tile_view(const abb_assembler* a, bool on)
+{
+	TileView v = { nullptr, nullptr, 0 };
+	if (on && a->tiles_on && a->d_tile_tab) {
+		v.recs = a->d_tiles;
+		v.tab = a->d_tile_tab;
+		v.mask = a->tile_tab_mask;
+	}
+	return v;
+}
+
+/** allocate the tile store on first use, sized from the number of solid k-mers in the filter */
+int ensure_tile_store(abb_assembler* a)
+{
+	if (a->d_tile_tab || !a->tiles_on)
+		return ABB_OK;
+	uint64_t nz = 0, th = 0;
+	ABB_CHECK(abb_filter_popcount(a->solid, &nz, &th));
+	const uint64_t solid = th / std::max(1u, a->solid->H) + 1024; // ~ distinct k-mers with count >= kc
+	const uint64_t markers = solid / (kMarkerMask + 1) * 2 + 4096;
+	size_t free_b = 0, total_b = 0;
+	cudaMemGetInfo(&free_b, &total_b);
+	a->tile_cap = (unsigned)std::min<uint64_t>(markers * 4, 1u << 30);
+	unsigned long long pool = std::min<unsigned long long>(solid * 4 * 9 * 3 / 2 + (1 << 20), (unsigned long long)(free_b * 0.25));
+	uint64_t tab = 1;
+	while (tab < (uint64_t)a->tile_cap * 2)
+		tab <<= 1;
+	uint64_t mset = 1;
+	while (mset < markers * 4)
+		mset <<= 1;
+	ABB_CUDA(cudaMalloc((void**)&a->d_tiles, (size_t)a->tile_cap * sizeof(TileRec)));
+	ABB_CUDA(cudaMalloc((void**)&a->d_tile_tab, tab * sizeof(unsigned)));
+	ABB_CUDA(cudaMemsetAsync(a->d_tile_tab, 0, tab * sizeof(unsigned), a->stream));
+	a->tile_tab_mask = (unsigned)(tab - 1);
+	ABB_CUDA(cudaMalloc((void**)&a->d_marker_set, mset * sizeof(unsigned long long)));
+	ABB_CUDA(cudaMemsetAsync(a->d_marker_set, 0, mset * sizeof(unsigned long long), a->stream));
+	a->marker_set_mask = (unsigned)(mset - 1);
+	ABB_CUDA(cudaMalloc((void**)&a->d_tile_pool, pool));
+	a->tile_pool_size = pool;
+	ABB_CUDA(cudaMalloc((void**)&a->d_tile_n, 4 * sizeof(unsigned)));
+	ABB_CUDA(cudaMemsetAsync(a->d_tile_n, 0, 4 * sizeof(unsigned), a->stream));
+	ABB_CUDA(cudaMalloc((void**)&a->d_tile_pool_top, sizeof(unsigned long long)));
+	ABB_CUDA(cudaMemsetAsync(a->d_tile_pool_top, 0, sizeof(unsigned long long), a->stream));
+	return ABB_OK;
+}
+
+/** markers among this batch's k-mers that have no tiles yet get their four tiles */
+int produce_tiles(abb_assembler* a, uint64_t n_reads, uint64_t n_slots)
+{
+	if (!a->tiles_on || n_slots == 0)
+		return ABB_OK;
+	PhaseTimer tt(a, &a->ms_tiles);
+	ABB_CHECK(ensure_tile_store(a));
+	abb_filter* f = a->solid;
+	cudaStream_t st = a->stream;
+	const WalkCfg w = walk_cfg(a);
+	const unsigned out_cap = (unsigned)std::min<uint64_t>(n_slots / (kMarkerMask + 1) * 2 + 4096, a->marker_set_mask / 2 + 1);
+	ABB_CHECK(a->new_markers.reserve(out_cap));
+	ABB_CUDA(cudaMemsetAsync(a->d_tile_n + 1, 0, 2 * sizeof(unsigned), st));
+	k_find_markers<<<148 * 16, 256, 0, st>>>(a->h0.p, a->valid.p, a->slot_offs.p, n_reads, n_slots, w, f->cfg, a->d_marker_set,
+	                                         a->marker_set_mask, a->new_markers.p, a->d_tile_n + 2, out_cap);
+	ABB_CUDA(cudaGetLastError());
+	unsigned nm = 0;
+	ABB_CUDA(cudaMemcpyAsync(&nm, a->d_tile_n + 2, sizeof nm, cudaMemcpyDeviceToHost, st));
+	ABB_CUDA(cudaStreamSynchronize(st));
+	nm = std::min(nm, out_cap);
+	a->st_launches += 1;
+	if (nm == 0) {
+		tt.stop();
+		return ABB_OK;
+	}
+	int sms = 148;
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, f->device);
+	const unsigned grid = (unsigned)std::min<uint64_t>(blocks_for((uint64_t)nm * 4, kWalkWarps), (uint64_t)sms * 4);
+	const unsigned warps = grid * kWalkWarps;
+	ABB_CHECK(ensure_scratch(a, warps));
+	ABB_CHECK(a->stage_bases.reserve((size_t)warps * kTileCap));
+	ABB_CHECK(a->stage_hashes.reserve((size_t)warps * kTileCap));
+	TileStore ts = { a->d_tiles, a->d_tile_tab, a->tile_tab_mask, a->tile_cap, a->d_tile_n, a->d_tile_pool, a->tile_pool_size,
+		             a->d_tile_pool_top };
+	ABB_DISPATCH_KW(a->kw, (k_make_tiles<KW><<<grid, kWalkWarps * 32, 0, st>>>(a->cur_bases, a->cur_offs, a->new_markers.p, nm,
+	                                                                          a->d_tile_n + 1, w, f->cfg, a->frames.p, a->look.p,
+	                                                                          a->stage_bases.p, a->stage_hashes.p, ts)));
+	ABB_CUDA(cudaGetLastError());
+	a->st_launches += 1;
+	unsigned nt = 0;
+	ABB_CUDA(cudaMemcpyAsync(&nt, a->d_tile_n, sizeof nt, cudaMemcpyDeviceToHost, st));
+	ABB_CUDA(cudaStreamSynchronize(st));
+	a->st_markers += nm;
+	a->st_tiles = std::min(nt, a->tile_cap);
+	tt.stop();
+	return ABB_OK;
+}
+
+/** K4 over the reads listed in a->spec.p[0..n): returns the records (unsorted) and the per-read status.
+ *  keep_arena: do not rewind the arena (results of an earlier launch of this round still live there). */
+int run_extend(abb_assembler* a, unsigned n_spec, bool use_tiles, bool keep_arena, std::vector<ContigRec>& recs,
+               std::vector<unsigned>& status)
+{
+	abb_filter* f = a->solid;
+	cudaStream_t st = a->stream;
+	ABB_CHECK(ensure_scratch(a, n_spec));
+	ABB_CHECK(a->status.reserve(n_spec));
+	unsigned rec_cap = std::max<unsigned>(n_spec * 8, 4096);
+	status.assign(n_spec, 0);
+	unsigned long long arena_mark = 0;
+	if (keep_arena) {
+		ABB_CUDA(cudaMemcpyAsync(&arena_mark, a->d_arena_top, sizeof arena_mark, cudaMemcpyDeviceToHost, st));
+		ABB_CUDA(cudaStreamSynchronize(st));
+	}
+	for (;;) {
+		ABB_CHECK(a->recs.reserve(rec_cap));
+		ABB_CHECK(ensure_arena(a, a->arena_size ? a->arena_size : kArenaDefault));
+		ABB_CUDA(cudaMemcpyAsync(a->d_arena_top, &arena_mark, sizeof arena_mark, cudaMemcpyHostToDevice, st));
+		ABB_CUDA(cudaMemsetAsync(a->d_nrecs, 0, sizeof(unsigned), st));
+		const WalkCfg w = walk_cfg(a);
+		const TileView tv = tile_view(a, use_tiles);
+		ABB_DISPATCH_KW(a->kw, (k_extend<KW><<<blocks_for(n_spec, kWalkWarps), kWalkWarps * 32, 0, st>>>(
+		                           a->cur_bases, a->cur_offs, a->spec.p, n_spec, w, f->cfg, a->frames.p, a->look.p, a->d_arena, a->arena_size,
+		                           a->d_arena_top, a->recs.p, a->d_nrecs, rec_cap, a->status.p, tv)));
+		ABB_CUDA(cudaGetLastError());
+		++a->st_launches;
+		unsigned nrecs = 0;
+		ABB_CUDA(cudaMemcpyAsync(&nrecs, a->d_nrecs, sizeof nrecs, cudaMemcpyDeviceToHost, st));
+		ABB_CUDA(cudaMemcpyAsync(status.data(), a->status.p, n_spec * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+		ABB_CUDA(cudaStreamSynchronize(st));
+		if (nrecs > rec_cap) { // record buffer too small: rerun with room for everything
+			rec_cap = nrecs + nrecs / 4 + 16;
+			continue;
+		}
+		bool arena_fail = false;
+		for (unsigned i = 0; i < n_spec; ++i)
+			arena_fail |= (status[i] & (1u << 3)) != 0;
+		if (arena_fail && !keep_arena) {
+			// out of unitig scratch: grow the arena (free memory permitting) and rerun
+			size_t free_b = 0, total_b = 0;
+			cudaMemGetInfo(&free_b, &total_b);
+			const unsigned long long room = a->arena_size + (unsigned long long)(free_b * 0.8);
+			const unsigned long long bigger = std::min<unsigned long long>(std::min(kArenaMax, room), a->arena_size * 4);
+			if (bigger > a->arena_size + (1ULL << 28)) {
+				ABB_CHECK(ensure_arena(a, bigger));
+				continue;
+			}
+		}
+		recs.resize(nrecs);
+		if (nrecs)
+			ABB_CUDA(cudaMemcpyAsync(recs.data(), a->recs.p, nrecs * sizeof(ContigRec), cudaMemcpyDeviceToHost, st));
+		ABB_CUDA(cudaStreamSynchronize(st));
+		return ABB_OK;
+	}
+}
+
+/** sort records by (read, ordinal) and build the per-read / per-contig index arrays */
+struct RoundLayout {
+	std::vector<unsigned> spec_cbeg, clen;
+	std::vector<uint64_t> coffs, cslot;
+};
+void layout_records(std::vector<ContigRec>& recs, unsigned n_ok, unsigned k, RoundLayout& L)
+{
+	recs.erase(std::remove_if(recs.begin(), recs.end(), [&](const ContigRec& r) { return r.spec >= n_ok; }), recs.end());
+	std::sort(recs.begin(), recs.end(), [](const ContigRec& x, const ContigRec& y) {
+		return x.spec != y.spec ? x.spec < y.spec : x.ordinal < y.ordinal;
+	});
+	const unsigned nc = (unsigned)recs.size();
+	L.spec_cbeg.assign(n_ok + 1, 0);
+	L.clen.resize(nc);
+	L.coffs.assign(nc + 1, 0);
+	L.cslot.assign(nc + 1, 0);
+	for (unsigned c = 0; c < nc; ++c) {
+		++L.spec_cbeg[recs[c].spec + 1];
+		L.clen[c] = recs[c].len;
+		L.coffs[c + 1] = L.coffs[c] + recs[c].len;
+		L.cslot[c + 1] = L.cslot[c] + (recs[c].len - k + 1);
+	}
+	for (unsigned s = 0; s < n_ok; ++s)
+		L.spec_cbeg[s + 1] += L.spec_cbeg[s];
+}
+
+/** upload the layout, gather the unitigs as ASCII and hash them */
+int stage_contigs(abb_assembler* a, const std::vector<ContigRec>& recs, const RoundLayout& L)
+{
+	abb_filter* f = a->solid;
+	cudaStream_t st = a->stream;
+	const unsigned nc = (unsigned)recs.size();
+	ABB_CHECK(h2d(a->recs_sorted, recs, st));
+	ABB_CHECK(h2d(a->spec_cbeg, L.spec_cbeg, st));
+	ABB_CHECK(h2d(a->clen, L.clen, st));
+	ABB_CHECK(h2d(a->coffs, L.coffs, st));
+	ABB_CHECK(h2d(a->cslot, L.cslot, st));
+	ABB_CHECK(a->cseq.reserve(L.coffs[nc] + 16));
+	ABB_CHECK(a->ch0.reserve(L.cslot[nc] + 1));
+	ABB_CHECK(a->cvalid.reserve(L.cslot[nc] + 1));
+	if (nc) {
+		k_gather<<<std::min<unsigned>(nc, 148 * 8), 256, 0, st>>>(a->recs_sorted.p, nc, a->coffs.p, a->cseq.p);
+		ABB_CUDA(cudaGetLastError());
+		ABB_CHECK(launch_hash(nullptr, f->k, nullptr, a->cseq.p, a->coffs.p, a->cslot.p, 0, nc, 0, a->ch0.p, a->cvalid.p, st, nullptr));
+		a->st_launches += 2;
+	}
+	return ABB_OK;
+}
+
 /** one speculation round over candidates starting at *cursor; appends accepted contigs */
 int speculate_round(abb_assembler* a, const std::vector<unsigned>& cand, size_t* cursor, uint64_t n_reads)
 {
@@ -773,70 +1274,100 @@ int speculate_round(abb_assembler* a, const std::vector<unsigned>& cand, size_t*
 	++a->st_iterations;
 	a->st_speculated += spec.size();
 
-	// ---- K4: extend all speculated reads
+	// ---- K4: extend all speculated reads (tiles on), then the exact vertex-by-vertex fallback for
+	// reads whose tiled walk cycled or produced a path with a repeated vertex
 	const unsigned n_spec = (unsigned)spec.size();
-	ABB_CHECK(h2d(a->spec, spec, st));
-	ABB_CHECK(ensure_scratch(a, n_spec));
-	ABB_CHECK(a->status.reserve(n_spec));
-	unsigned rec_cap = std::max<unsigned>(n_spec * 8, 4096);
 	std::vector<ContigRec> recs;
-	std::vector<unsigned> status(n_spec);
-	unsigned n_ok = n_spec; // speculated reads [0, n_ok) completed
-	PhaseTimer te(a, &a->ms_extend);
-	for (;;) {
-		ABB_CHECK(a->recs.reserve(rec_cap));
-		ABB_CHECK(ensure_arena(a, a->arena_size ? a->arena_size : kArenaDefault));
-		ABB_CUDA(cudaMemsetAsync(a->d_arena_top, 0, sizeof(unsigned long long), st));
-		ABB_CUDA(cudaMemsetAsync(a->d_nrecs, 0, sizeof(unsigned), st));
-		const WalkCfg w = walk_cfg(a);
-		ABB_DISPATCH_KW(a->kw, (k_extend<KW><<<blocks_for(n_spec, kWalkWarps), kWalkWarps * 32, 0, st>>>(
-		                           a->cur_bases, a->cur_offs, a->spec.p, n_spec, w, f->cfg, a->frames.p, a->look.p, a->d_arena, a->arena_size,
-		                           a->d_arena_top, a->recs.p, a->d_nrecs, rec_cap, a->status.p)));
-		ABB_CUDA(cudaGetLastError());
-		++a->st_launches;
-		unsigned nrecs = 0;
-		ABB_CUDA(cudaMemcpyAsync(&nrecs, a->d_nrecs, sizeof nrecs, cudaMemcpyDeviceToHost, st));
-		ABB_CUDA(cudaMemcpyAsync(status.data(), a->status.p, n_spec * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-		ABB_CUDA(cudaStreamSynchronize(st));
-		if (nrecs > rec_cap) { // record buffer too small: rerun with room for everything
-			rec_cap = nrecs + nrecs / 4 + 16;
-			continue;
+	std::vector<unsigned> status;
+	RoundLayout L;
+	unsigned n_ok = n_spec;
+	{
+		PhaseTimer te(a, &a->ms_extend);
+		ABB_CHECK(h2d(a->spec, spec, st));
+		ABB_CHECK(run_extend(a, n_spec, true, false, recs, status));
+		std::vector<unsigned> redo; // indices into spec
+		for (unsigned i = 0; i < n_spec; ++i) {
+			if (status[i] & (1u << 4)) { // tile chain cycled
+				redo.push_back(i);
+				status[i] = 0;
+			}
 		}
-		n_ok = n_spec;
 		for (unsigned i = 0; i < n_spec; ++i)
 			if (status[i] != 0) {
 				n_ok = i;
 				break;
 			}
-		if (n_ok < n_spec) {
-			if (status[n_ok] & ((1u << 1) | (1u << 2))) {
-				if (n_ok == 0) {
-					set_error("graph traversal exceeded the per-warp scratch bounds (lookAhead %u / trueBranch %u frames)", kLookCap, kFrameCap);
-					return ABB_ENOMEM;
-				}
-			} else {
-				// out of unitig scratch: grow the arena (free memory permitting) and rerun the round
-				size_t free_b = 0, total_b = 0;
-				cudaMemGetInfo(&free_b, &total_b);
-				const unsigned long long room = a->arena_size + (unsigned long long)(free_b * 0.8);
-				const unsigned long long bigger = std::min<unsigned long long>(std::min(kArenaMax, room), a->arena_size * 4);
-				if (bigger > a->arena_size + (1ULL << 28)) {
-					ABB_CHECK(ensure_arena(a, bigger));
-					continue;
-				}
-				if (n_ok == 0) {
-					set_error("unitig scratch arena exhausted at %llu bytes", a->arena_size);
-					return ABB_ENOMEM;
-				}
+		if (n_ok == 0) {
+			if (status[0] & ((1u << 1) | (1u << 2)))
+				set_error("graph traversal exceeded the per-warp scratch bounds (lookAhead %u / trueBranch %u frames)", kLookCap, kFrameCap);
+			else
+				set_error("unitig scratch arena exhausted at %llu bytes", a->arena_size);
+			return ABB_ENOMEM;
+		}
+		// repeat check on everything that was produced with tiles
+		if (a->tiles_on && a->d_tile_tab) {
+			std::vector<ContigRec> keep;
+			for (auto& r : recs)
+				if (r.spec < n_ok && std::find(redo.begin(), redo.end(), r.spec) == redo.end())
+					keep.push_back(r);
+			recs.swap(keep);
+			layout_records(recs, n_ok, f->k, L);
+			ABB_CHECK(stage_contigs(a, recs, L));
+			const unsigned nc = (unsigned)recs.size();
+			if (nc) {
+				uint64_t tab = 1024;
+				while (tab < (L.cslot[nc] + 2ull * nc) * 2)
+					tab <<= 1;
+				ABB_CHECK(a->rep_tab.reserve(tab));
+				ABB_CHECK(a->rep_flag.reserve(nc));
+				ABB_CUDA(cudaMemsetAsync(a->rep_tab.p, 0, tab * sizeof(unsigned long long), st));
+				ABB_CUDA(cudaMemsetAsync(a->rep_flag.p, 0, nc, st));
+				k_repeat_check<<<148 * 8, 256, 0, st>>>(a->recs_sorted.p, nc, a->cslot.p, a->ch0.p, a->rep_tab.p, tab - 1, a->rep_flag.p);
+				ABB_CUDA(cudaGetLastError());
+				++a->st_launches;
+				std::vector<uint8_t> flag(nc);
+				ABB_CUDA(cudaMemcpyAsync(flag.data(), a->rep_flag.p, nc, cudaMemcpyDeviceToHost, st));
+				ABB_CUDA(cudaStreamSynchronize(st));
+				for (unsigned c = 0; c < nc; ++c)
+					if (flag[c] && (redo.empty() || redo.back() != recs[c].spec) &&
+					    std::find(redo.begin(), redo.end(), recs[c].spec) == redo.end())
+						redo.push_back(recs[c].spec);
 			}
 		}
-		recs.resize(nrecs);
-		if (nrecs)
-			ABB_CUDA(cudaMemcpyAsync(recs.data(), a->recs.p, nrecs * sizeof(ContigRec), cudaMemcpyDeviceToHost, st));
-		ABB_CUDA(cudaStreamSynchronize(st));
-		break;
+		redo.erase(std::remove_if(redo.begin(), redo.end(), [&](unsigned i) { return i >= n_ok; }), redo.end());
+		if (!redo.empty()) {
+			std::sort(redo.begin(), redo.end());
+			a->st_fallbacks += redo.size();
+			std::vector<unsigned> sub(redo.size());
+			for (size_t i = 0; i < redo.size(); ++i)
+				sub[i] = spec[redo[i]];
+			ABB_CHECK(h2d(a->spec, sub, st));
+			std::vector<ContigRec> recs2;
+			std::vector<unsigned> status2;
+			ABB_CHECK(run_extend(a, (unsigned)sub.size(), false, true, recs2, status2));
+			for (size_t i = 0; i < sub.size(); ++i)
+				if (status2[i] != 0) { // the serial walk itself ran out of scratch: end the round before this read
+					n_ok = std::min(n_ok, redo[i]);
+				}
+			std::vector<ContigRec> merged;
+			for (auto& r : recs)
+				if (!std::binary_search(redo.begin(), redo.end(), r.spec))
+					merged.push_back(r);
+			for (auto& r : recs2) {
+				r.spec = redo[r.spec];
+				merged.push_back(r);
+			}
+			recs.swap(merged);
+			ABB_CHECK(h2d(a->spec, spec, st)); // restore the full list for the replay
+			if (n_ok == 0) {
+				set_error("unitig scratch arena exhausted at %llu bytes", a->arena_size);
+				return ABB_ENOMEM;
+			}
+		}
+		layout_records(recs, n_ok, f->k, L);
+		ABB_CHECK(stage_contigs(a, recs, L));
+		te.stop();
 	}
-	te.stop();
 	if (n_ok < n_spec) {
 		// reads from the first failure on go back to the queue; speculate less next time.
 		// Candidates after the failed read that this round already labelled "visited" are re-examined
@@ -853,46 +1384,19 @@ int speculate_round(abb_assembler* a, const std::vector<unsigned>& cand, size_t*
 		spec.resize(n_ok);
 	}
 
-	// ---- order the records: by speculated read, then by ordinal; drop those of abandoned reads
-	recs.erase(std::remove_if(recs.begin(), recs.end(), [&](const ContigRec& r) { return r.spec >= n_ok; }), recs.end());
-	std::sort(recs.begin(), recs.end(), [](const ContigRec& x, const ContigRec& y) {
-		return x.spec != y.spec ? x.spec < y.spec : x.ordinal < y.ordinal;
-	});
 	const unsigned nc = (unsigned)recs.size();
-	std::vector<unsigned> spec_cbeg(n_ok + 1, 0), clen(nc);
-	std::vector<uint64_t> coffs(nc + 1, 0), cslot(nc + 1, 0);
-	for (unsigned c = 0; c < nc; ++c) {
-		++spec_cbeg[recs[c].spec + 1];
-		clen[c] = recs[c].len;
-		coffs[c + 1] = coffs[c] + recs[c].len;
-		cslot[c + 1] = cslot[c] + (recs[c].len - f->k + 1);
-	}
-	for (unsigned s = 0; s < n_ok; ++s)
-		spec_cbeg[s + 1] += spec_cbeg[s];
-
+	const std::vector<unsigned>& spec_cbeg = L.spec_cbeg;
+	const std::vector<unsigned>& clen = L.clen;
+	const std::vector<uint64_t>& coffs = L.coffs;
 	std::vector<uint8_t> rcode(n_ok), caccept(nc);
 	std::vector<unsigned> ccov(nc);
 	std::vector<char> seqs(coffs[nc]);
 	a->st_contigs_tried += nc;
 	{
 		PhaseTimer tr(a, &a->ms_replay);
-		ABB_CHECK(h2d(a->recs_sorted, recs, st));
-		ABB_CHECK(h2d(a->spec_cbeg, spec_cbeg, st));
-		ABB_CHECK(h2d(a->clen, clen, st));
-		ABB_CHECK(h2d(a->coffs, coffs, st));
-		ABB_CHECK(h2d(a->cslot, cslot, st));
-		ABB_CHECK(a->cseq.reserve(coffs[nc] + 16));
-		ABB_CHECK(a->ch0.reserve(cslot[nc] + 1));
-		ABB_CHECK(a->cvalid.reserve(cslot[nc] + 1));
 		ABB_CHECK(a->rcode.reserve(n_ok));
 		ABB_CHECK(a->caccept.reserve(nc + 1));
 		ABB_CHECK(a->ccov.reserve(nc + 1));
-		if (nc) {
-			k_gather<<<std::min<unsigned>(nc, 148 * 8), 256, 0, st>>>(a->recs_sorted.p, nc, a->coffs.p, a->cseq.p);
-			ABB_CUDA(cudaGetLastError());
-			ABB_CHECK(launch_hash(nullptr, f->k, nullptr, a->cseq.p, a->coffs.p, a->cslot.p, 0, nc, 0, a->ch0.p, a->cvalid.p, st, nullptr));
-			a->st_launches += 2;
-		}
 		ABB_CHECK(ensure_endset(a, 2ull * nc));
 		a->ends_upper += 2ull * nc;
 		ReplayIO io;
@@ -1008,6 +1512,7 @@ int abb_assembler_create(abb_assembler** out, abb_filter* solid, const abb_assem
 	if (a->params.trim == 0xffffffffu)
 		a->params.trim = solid->k; // bloom-dbg.cc:518-520
 	a->kw = (int)((2 * solid->k + 63) / 64);
+	a->tiles_on = getenv("ABB_NO_TILES") == nullptr; // debugging switch: vertex-by-vertex walks only
 	// BloomFilter assembledKmerSet(solid.size(), solid.getHashNum(), solid.getKmerSize()) (bloom-dbg.h:910-911)
 	int rc = abb_filter_create(&a->assembled, ABB_BIT, solid->size, solid->H, solid->k, 0, "", solid->device);
 	if (rc != ABB_OK) {
@@ -1045,6 +1550,13 @@ int abb_assembler_destroy(abb_assembler* a)
 	a->offs.release(); a->slot_offs.release(); a->h0.release(); a->coffs.release(); a->cslot.release(); a->ch0.release();
 	a->cand.release(); a->spec.release(); a->spec_cbeg.release(); a->clen.release(); a->ccov.release(); a->status.release();
 	a->recs.release(); a->recs_sorted.release(); a->frames.release(); a->look.release();
+	cudaFree(a->d_tiles);
+	cudaFree(a->d_tile_tab);
+	cudaFree(a->d_tile_n);
+	cudaFree(a->d_tile_pool);
+	cudaFree(a->d_tile_pool_top);
+	cudaFree(a->d_marker_set);
+	a->new_markers.release(); a->rep_tab.release(); a->stage_bases.release(); a->rep_flag.release(); a->stage_hashes.release();
 	cudaFree(a->d_arena);
 	cudaFree(a->d_arena_top);
 	cudaFree(a->d_nrecs);
@@ -1093,6 +1605,8 @@ static int process_batch(abb_assembler* a, const uint8_t* d_bases, const uint64_
 	a->counters.solid_reads += cand.size();
 	a->st_candidates += cand.size();
 	ABB_CHECK(h2d(a->cand, cand, st));
+	if (!cand.empty())
+		ABB_CHECK(produce_tiles(a, n_reads, total));
 
 	size_t cursor = 0;
 	while (cursor < cand.size())
@@ -1162,6 +1676,10 @@ int abb_assembler_stats(const abb_assembler* a, abb_assembly_stats* out)
 	out->ms_visited = a->ms_visited;
 	out->ms_extend = a->ms_extend;
 	out->ms_replay = a->ms_replay;
+	out->ms_tiles = a->ms_tiles;
+	out->markers = a->st_markers;
+	out->tiles = a->st_tiles;
+	out->serial_fallbacks = a->st_fallbacks;
 	return ABB_OK;
 }
 

@@ -222,6 +222,7 @@ ABB_HD unsigned ctz4(unsigned m) { return (m & 1) ? 0 : (m & 2) ? 1 : (m & 4) ? 
  *   void fail(unsigned why), bool failed()   record an overflow; the walk of this read is abandoned and retried by the host
  *   void copy8(dst, src, n), copy8_rev(dst, src, n)   cooperative byte copies (rev: dst[i] = src[n-1-i])
  *   void rehash(old, oldcap, new, newcap)              cooperative PathSet growth
+ *   bool tiles_enabled(); const TileRec* tile_lookup(key, cls); uint32_t tile_index(const TileRec*); void wr32(uint32_t*, uint32_t)
  *   void mark_covered(ps, rh, cov, nk, contig)         cooperative: flag read k-mers that lie on the contig path
  *   Frame* frames; uint64_t* look;   per-warp scratch
  */
@@ -532,6 +533,182 @@ ABB_HD bool bytevec_push(Ctx& c, ByteVec& v, uint8_t x)
 }
 
 // ------------------------------------------------------------------------------------------
+// Tiles: marker-to-marker path segments computed once, in parallel, and spliced by the walks.
+//
+// A unitig walk is a chain of dependent steps (Mbp-long unitigs = seconds of latency).  The step
+// taken at a head h depends only on h and on the canonical hash of the previous head p:
+//     look-behind  LB(h, d) = successor(h, opposite d)   must be (LENGTH_LIMIT, t) with t == p
+//     next         NX(h, d) = successor(h, d)            must be (LENGTH_LIMIT, v); v becomes the head
+// (extendPathBySingleVertex, ExtendPath.h:403-459; the start vertex of an extension skips LB).
+// Vertices whose canonical hash has its low bits clear are MARKERS.  For every marker m, held
+// orientation o and direction d, tile(m, o, d) is exactly the walk extendPath would do from the
+// start vertex m -- no LB at m, LB at every later head -- cut when it pushes another marker (or
+// stops for a graph reason, or after kTileCap pushes), together with LB(m, d) itself.  A walk that
+// arrives at m from p applies the stored LB(m) to p, appends the tile, and continues at the tile's
+// end marker with the tile's own last predecessor: by construction the result is what stepping
+// vertex by vertex would have produced.  The visited set is not consulted while splicing; instead
+// every finished path is checked for a repeated vertex afterwards and, if one is found (cycles,
+// hairpins: rare), that read is walked again without tiles.
+// ------------------------------------------------------------------------------------------
+constexpr uint64_t kMarkerMask = 255;   // 1 vertex in 256 is a marker
+constexpr unsigned kTileCap = 4096;     // longest tile, in pushed vertices
+enum TileStop : uint8_t { TS_MARKER = 0, TS_CODE = 1, TS_CAP = 2 };
+
+ABB_HD bool is_marker(uint64_t canon) { return (canon & kMarkerMask) == 0; }
+
+struct TileRec {
+	uint64_t key;        // canonical hash of the marker
+	uint64_t lb_t;       // canonical hash of LB's unique predecessor (valid if lb_code == ER_LENGTH_LIMIT)
+	uint64_t prev_last;  // canonical hash of the vertex before the last pushed one (the marker itself if n == 1)
+	uint64_t end_key;    // canonical hash of the last pushed vertex
+	uint8_t* bases;      // n pushed bases, in push order
+	uint64_t* hashes;    // n canonical hashes of the pushed vertices
+	uint32_t n;
+	uint8_t cls;         // (held orientation is the canonical-hash one) << 1 | direction
+	uint8_t lb_code;     // ExtCode of LB(marker)
+	uint8_t stop_kind;   // TileStop
+	uint8_t stop_code;   // ExtCode when stop_kind == TS_CODE
+	uint8_t end_orient;  // orientation bit of the last pushed vertex
+	uint8_t pad[7];
+};
+
+template <int KW>
+ABB_HD unsigned vtx_orient(const Vtx<KW>& v) { return v.h.fh <= v.h.rh ? 1u : 0u; }
+template <int KW>
+ABB_HD unsigned vtx_class(const Vtx<KW>& v, Dir d) { return (vtx_orient(v) << 1) | (unsigned)d; }
+
+/** growable vector of tile indices (arena memory) */
+struct U32Vec {
+	uint32_t* p;
+	unsigned cap, n;
+};
+template <class Ctx>
+ABB_HD bool u32vec_push(Ctx& c, U32Vec& v, uint32_t x)
+{
+	if (v.n == v.cap) {
+		const unsigned ncap = v.cap ? v.cap * 2 : 256;
+		uint32_t* np = (uint32_t*)c.alloc((uint64_t)ncap * 4, false);
+		if (!np)
+			return false;
+		c.copy8((uint8_t*)np, (const uint8_t*)v.p, v.n * 4);
+		v.p = np;
+		v.cap = ncap;
+	}
+	c.wr32(v.p + v.n, x);
+	++v.n;
+	return true;
+}
+/** append n bytes */
+template <class Ctx>
+ABB_HD bool bytevec_append(Ctx& c, ByteVec& v, const uint8_t* src, unsigned n)
+{
+	if (v.n + n > v.cap) {
+		unsigned ncap = v.cap ? v.cap : 1024;
+		while (ncap < v.n + n)
+			ncap *= 2;
+		uint8_t* np = c.alloc(ncap, false);
+		if (!np)
+			return false;
+		c.copy8(np, v.p, v.n);
+		v.p = np;
+		v.cap = ncap;
+	}
+	c.copy8(v.p + v.n, src, n);
+	v.n += n;
+	return true;
+}
+
+/** the end vertex of an extension that started at `start` and pushed the bases in `v` (direction d) */
+template <int KW, class Ctx>
+ABB_HD Vtx<KW> rebuild_head(Ctx& c, const Vtx<KW>& start, const ByteVec& v, unsigned from, Dir d)
+{
+	const unsigned k = c.k;
+	Vtx<KW> h = start;
+	const unsigned pushed = v.n - from;
+	if (pushed >= k) {
+		// the last k pushed bases spell the vertex (REV pushes prepend: newest base first)
+		uint8_t tmp[kMaxK];
+		for (unsigned i = 0; i < k; ++i)
+			tmp[i] = d == FWD ? c.rd8(v.p + v.n - k + i) : c.rd8(v.p + v.n - 1 - i);
+		return vtx_from_codes<KW>(tmp, k, false);
+	}
+	for (unsigned i = from; i < v.n; ++i)
+		vtx_step(h, k, c.rt, d, c.rd8(v.p + i));
+	return h;
+}
+
+/**
+ * tile(m, orientation of m as held, dir): see the block comment above.  bases/hashes are staging
+ * buffers of kTileCap entries owned by the calling warp.
+ */
+template <int KW, class Ctx>
+ABB_HD void make_tile(Ctx& c, const Vtx<KW>& m, Dir dir, TileRec* t, uint8_t* bases, uint64_t* hashes)
+{
+	Vtx<KW> head = m;
+	unsigned nb = c.neighbors(head);
+	unsigned b = 0;
+	{ // LB(m, dir), consulted by whoever arrives at m
+		const ExtCode lb = successor(c, head, nb, opposite(dir), &b);
+		t->lb_code = (uint8_t)lb;
+		t->lb_t = 0;
+		if (lb == ER_LENGTH_LIMIT) {
+			const HashPair th = dir == FWD ? roll_left(head.h, c.rt, kmer_last(head.km), b)
+			                               : roll_right(head.h, c.rt, kmer_first(head.km, c.k), b);
+			t->lb_t = th.canonical();
+		}
+	}
+	t->key = m.canon();
+	t->cls = (uint8_t)vtx_class(m, dir);
+	unsigned n = 0;
+	uint64_t prev_h = 0;
+	bool look_behind = false;
+	t->stop_kind = TS_CAP;
+	t->stop_code = 0;
+	for (;;) {
+		if (look_behind) {
+			const ExtCode r = successor(c, head, nb, opposite(dir), &b);
+			if (r == ER_AMBI_OUT || r == ER_DEAD_END) {
+				t->stop_kind = TS_CODE;
+				t->stop_code = (uint8_t)ER_AMBI_IN;
+				break;
+			}
+			const HashPair th = dir == FWD ? roll_left(head.h, c.rt, kmer_last(head.km), b)
+			                               : roll_right(head.h, c.rt, kmer_first(head.km, c.k), b);
+			if (th.canonical() != prev_h) {
+				t->stop_kind = TS_CODE;
+				t->stop_code = (uint8_t)ER_AMBI_IN;
+				break;
+			}
+		}
+		const ExtCode r = successor(c, head, nb, dir, &b);
+		if (r != ER_LENGTH_LIMIT) {
+			t->stop_kind = TS_CODE;
+			t->stop_code = (uint8_t)r;
+			break;
+		}
+		prev_h = head.canon();
+		vtx_step(head, c.k, c.rt, dir, b);
+		c.wr8(bases + n, (uint8_t)b);
+		c.wr64(hashes + n, head.canon());
+		++n;
+		look_behind = true;
+		if (is_marker(head.canon())) {
+			t->stop_kind = TS_MARKER;
+			break;
+		}
+		if (n >= kTileCap || c.failed()) {
+			t->stop_kind = TS_CAP;
+			break;
+		}
+		nb = c.neighbors(head);
+	}
+	t->n = n;
+	t->prev_last = prev_h;
+	t->end_key = head.canon();
+	t->end_orient = (uint8_t)vtx_orient(head);
+}
+
+// ------------------------------------------------------------------------------------------
 // extendPath in one direction (Graph/ExtendPath.h:403-459,621-681) with ExtendPathParams
 // {trimLen = trim, fpTrim = 5, maxLen = NO_LIMIT, lookBehind = true, lookBehindStartVertex = false}
 // (bloom-dbg.h:845-850).
@@ -540,10 +717,14 @@ ABB_HD bool bytevec_push(Ctx& c, ByteVec& v, uint8_t x)
 //   bases     receives the new base of every vertex pushed (in push order)
 // ------------------------------------------------------------------------------------------
 template <int KW, class Ctx>
-ABB_HD ExtCode extend_dir(Ctx& c, Vtx<KW>& head, Dir dir, unsigned* psize, ByteVec& bases, PathSet& ps, bool* ok)
+ABB_HD ExtCode extend_dir(Ctx& c, Vtx<KW>& head, Dir dir, unsigned* psize, ByteVec& bases, PathSet& ps, bool* ok, U32Vec& tiles)
 {
 	bool look_behind = false; // lookBehindStartVertex
 	uint64_t prev_h = 0;
+	const Vtx<KW> start = head;
+	// Brent cycle detection over the chain of spliced tiles (a circular unitig chains for ever)
+	uint32_t brent_tortoise = 0xffffffffu;
+	unsigned brent_power = 1, brent_lam = 0;
 	unsigned nb = c.neighbors(head);
 	for (;;) {
 		unsigned b = 0;
@@ -582,6 +763,58 @@ ABB_HD ExtCode extend_dir(Ctx& c, Vtx<KW>& head, Dir dir, unsigned* psize, ByteV
 		look_behind = true; // params.lookBehind
 		if (c.failed())
 			return ER_DEAD_END;
+		if (c.tiles_enabled() && is_marker(head.canon())) {
+			// splice marker-to-marker tiles for as long as they chain (see the Tiles comment above)
+			uint64_t hk = head.canon();
+			unsigned cls = vtx_class(head, dir);
+			bool moved = false;
+			for (;;) {
+				const TileRec* T = c.tile_lookup(hk, cls);
+				if (!T)
+					break;
+				// extendPathBySingleVertex's look-behind at this marker, from the stored LB
+				if (T->lb_code != ER_LENGTH_LIMIT || T->lb_t != prev_h) {
+					if (moved)
+						head = rebuild_head(c, start, bases, 0, dir);
+					return ER_AMBI_IN;
+				}
+				const unsigned n = T->n;
+				if (n) {
+					const uint32_t ti = c.tile_index(T);
+					if (ti == brent_tortoise) { // the same tile again: a cycle the splice cannot see; walk this read without tiles
+						c.fail(4);
+						*ok = false;
+						return ER_DEAD_END;
+					}
+					if (++brent_lam == brent_power) {
+						brent_tortoise = ti;
+						brent_power *= 2;
+						brent_lam = 0;
+					}
+					if (!bytevec_append(c, bases, T->bases, n) || !u32vec_push(c, tiles, ti)) {
+						*ok = false;
+						return ER_DEAD_END;
+					}
+					*psize += n;
+					prev_h = T->prev_last;
+					hk = T->end_key;
+					cls = ((unsigned)T->end_orient << 1) | (unsigned)dir;
+					moved = true;
+				}
+				if (T->stop_kind == TS_CODE) {
+					if (moved)
+						head = rebuild_head(c, start, bases, 0, dir);
+					return (ExtCode)T->stop_code;
+				}
+				if (T->stop_kind == TS_CAP)
+					break;
+			}
+			if (moved) {
+				head = rebuild_head(c, start, bases, 0, dir);
+				nb = c.neighbors(head);
+				continue;
+			}
+		}
 		nb = c.neighbors_finish(pr);
 	}
 }
@@ -607,6 +840,8 @@ struct ContigOut {
 	bool tip;        // isTip: not output, but its k-mers still count as assembled for this read
 	bool popped_front, popped_back; // a real path vertex (not a pushed duplicate) was trimmed off that end
 	uint64_t front_h, back_h;       // canonical hashes of the trimmed-off vertices
+	bool pushed_front, pushed_back; // preprocessCircularContig's duplicate vertex survives at that end of seq
+	U32Vec tiles_left, tiles_right; // tiles spliced into the path (their vertices are not in the PathSet)
 };
 
 /**
@@ -620,12 +855,15 @@ ABB_HD bool extend_seed(Ctx& c, const Vtx<KW>& seed, PathSet& ps, ContigOut* o)
 	bool ok = true;
 	pathset_insert(c, ps, seed.canon(), &ok);
 	ByteVec left = { nullptr, 0, 0 }, right = { nullptr, 0, 0 };
+	o->tiles_left = U32Vec{ nullptr, 0, 0 };
+	o->tiles_right = U32Vec{ nullptr, 0, 0 };
+	o->pushed_front = o->pushed_back = false;
 	unsigned psize = 1;
 	Vtx<KW> front = seed, back = seed;
-	o->left = extend_dir(c, front, REV, &psize, left, ps, &ok);
+	o->left = extend_dir(c, front, REV, &psize, left, ps, &ok, o->tiles_left);
 	if (!ok || c.failed())
 		return false;
-	o->right = extend_dir(c, back, FWD, &psize, right, ps, &ok);
+	o->right = extend_dir(c, back, FWD, &psize, right, ps, &ok, o->tiles_right);
 	if (!ok || c.failed())
 		return false;
 	o->psize = psize;
@@ -701,14 +939,16 @@ ABB_HD bool extend_seed(Ctx& c, const Vtx<KW>& seed, PathSet& ps, ContigOut* o)
 			o->popped_front = true;
 			o->front_h = front.canon();
 		}
-	}
+	} else
+		o->pushed_front = pushed_front;
 	if (amb2) {
 		--end;
 		if (!pushed_back) {
 			o->popped_back = true;
 			o->back_h = back.canon();
 		}
-	}
+	} else
+		o->pushed_back = pushed_back;
 	o->seq = s + begin;
 	o->len = end - begin;
 	return true;

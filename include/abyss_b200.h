@@ -163,6 +163,9 @@ typedef struct abb_assembly_stats {
 	uint64_t contigs_tried;     /* unitigs produced by K4 (before the redundancy test) */
 	uint64_t launches;          /* kernels launched by the assembler */
 	float ms_classify, ms_visited, ms_extend, ms_replay; /* CUDA-event time per phase */
+	float ms_tiles;             /* marker enumeration + tile production */
+	uint64_t markers, tiles;    /* marker vertices found / marker-to-marker tiles stored */
+	uint64_t serial_fallbacks;  /* reads re-walked vertex by vertex after the repeat check */
 } abb_assembly_stats;
 int abb_assembler_stats(const abb_assembler* a, abb_assembly_stats* out);
 

@@ -18,6 +18,7 @@ extern "C" {
 #include <iostream>
 #include <memory>
 #include <string>
+#include <unordered_map>
 #include <unordered_set>
 #include <vector>
 
@@ -59,6 +60,27 @@ struct HostCtx {
 	template <int KW>
 	Probe neighbors_issue(const Vtx<KW>& v) { return Probe{ neighbors(v) }; }
 	unsigned neighbors_finish(const Probe& p) { return p.mask; }
+	// tiles
+	std::vector<TileRec> tile_recs;
+	std::vector<std::unique_ptr<uint8_t[]>> tile_mem;
+	std::unordered_map<uint64_t, uint32_t> tile_map; // (key mixed with class) -> index, verified on lookup
+	bool use_tiles = false;
+	unsigned long long tile_splices = 0;
+	static uint64_t tkey(uint64_t key, unsigned cls) { return key * 4 + cls; } // exact for the emulation: 64-bit wrap is fine with verification
+	bool tiles_enabled() const { return use_tiles; }
+	const TileRec* tile_lookup(uint64_t key, unsigned cls)
+	{
+		auto range = tile_multi.equal_range(tkey(key, cls));
+		for (auto it = range.first; it != range.second; ++it)
+			if (tile_recs[it->second].key == key && tile_recs[it->second].cls == cls) {
+				++tile_splices;
+				return &tile_recs[it->second];
+			}
+		return nullptr;
+	}
+	std::unordered_multimap<uint64_t, uint32_t> tile_multi;
+	uint32_t tile_index(const TileRec* t) const { return (uint32_t)(t - tile_recs.data()); }
+	void wr32(uint32_t* p, uint32_t v) { *p = v; }
 	uint64_t rd64(const uint64_t* p) { return *p; }
 	void wr64(uint64_t* p, uint64_t v) { *p = v; }
 	uint8_t rd8(const uint8_t* p) { return *p; }
@@ -78,7 +100,15 @@ struct HostCtx {
 			memset(allocs.back().get(), 0, bytes);
 		return allocs.back().get();
 	}
-	void fail(unsigned why) { fail_ = true; fprintf(stderr, "host_walk: scratch overflow %u\n", why); }
+	bool tile_cycle = false;
+	void fail(unsigned why)
+	{
+		fail_ = true;
+		if (why == 4)
+			tile_cycle = true;
+		else
+			fprintf(stderr, "host_walk: scratch overflow %u\n", why);
+	}
 	bool failed() const { return fail_; }
 	void copy8(uint8_t* d, const uint8_t* s, unsigned n) { if (n) memcpy(d, s, n); }
 	void copy8_rev(uint8_t* d, const uint8_t* s, unsigned n) { for (unsigned i = 0; i < n; ++i) d[i] = s[n - 1 - i]; }
@@ -94,8 +124,16 @@ struct HostCtx {
 	}
 	void mark_covered(const PathSet& ps, const uint64_t* rh, uint8_t* cov, unsigned nk, const ContigOut& o)
 	{
+		std::unordered_set<uint64_t> tilev;
+		for (int side = 0; side < 2; ++side) {
+			const U32Vec& tv = side ? o.tiles_right : o.tiles_left;
+			for (unsigned ti = 0; ti < tv.n; ++ti) {
+				const TileRec& T = tile_recs[tv.p[ti]];
+				tilev.insert(T.hashes, T.hashes + T.n);
+			}
+		}
 		for (unsigned j = 0; j < nk; ++j) {
-			if (cov[j] || !pathset_contains(*this, ps, rh[j]))
+			if (cov[j] || !(pathset_contains(*this, ps, rh[j]) || tilev.count(rh[j])))
 				continue;
 			if (o.popped_front && rh[j] == o.front_h)
 				continue;
@@ -140,13 +178,54 @@ struct Assembly {
 		}
 		return mn;
 	}
-	// outputContig (bloom-dbg.h:538-620)
+	struct Collected {
+		std::string seq;
+		bool pushed_front, pushed_back, popped_front, popped_back;
+		uint64_t front_h, back_h;
+	};
+	std::vector<Collected> collected;
 	void operator()(HostCtx&, unsigned, const ContigOut& o)
 	{
-		const unsigned k = c->k;
-		std::string seq(o.len, 'N');
+		Collected x;
+		x.seq.assign(o.len, 'N');
 		for (unsigned i = 0; i < o.len; ++i)
-			seq[i] = "ACGT"[o.seq[i]];
+			x.seq[i] = "ACGT"[o.seq[i]];
+		x.pushed_front = o.pushed_front; x.pushed_back = o.pushed_back;
+		x.popped_front = o.popped_front; x.popped_back = o.popped_back;
+		x.front_h = o.front_h; x.back_h = o.back_h;
+		collected.push_back(x);
+	}
+	std::vector<uint64_t> hashes_of(const std::string& seq) const
+	{
+		const unsigned k = c->k;
+		std::vector<uint64_t> tmp((seq.size() - k + 1) * c->H), hs(seq.size() - k + 1);
+		size_t n = abo_hash_seq(seq.data(), seq.size(), k, c->H, NULL, tmp.data(), NULL);
+		if (n != hs.size()) { fprintf(stderr, "host_walk: contig hashing mismatch\n"); exit(3); }
+		for (size_t i = 0; i < n; ++i)
+			hs[i] = tmp[i * c->H];
+		return hs;
+	}
+	/** a vertex occurs twice in the (untrimmed) path: the tile splice skipped an ER_CYCLE */
+	bool has_repeat(const Collected& x) const
+	{
+		std::vector<uint64_t> hs = hashes_of(x.seq);
+		std::unordered_set<uint64_t> seen;
+		size_t b = x.pushed_front ? 1 : 0, e = hs.size() - (x.pushed_back ? 1 : 0);
+		for (size_t i = b; i < e; ++i)
+			if (!seen.insert(hs[i]).second)
+				return true;
+		if (x.popped_front && !seen.insert(x.front_h).second)
+			return true;
+		if (x.popped_back && !seen.insert(x.back_h).second)
+			return true;
+		return false;
+	}
+	// outputContig (bloom-dbg.h:538-620)
+	void output(const Collected& x)
+	{
+		const unsigned k = c->k;
+		const std::string& seq = x.seq;
+		struct { unsigned len; } o = { (unsigned)seq.size() };
 		std::vector<uint64_t> hs(o.len - k + 1);
 		std::vector<uint64_t> tmp(hs.size() * c->H);
 		size_t n = abo_hash_seq(seq.data(), seq.size(), k, c->H, NULL, tmp.data(), NULL);
@@ -216,6 +295,41 @@ static int run(unsigned k, unsigned kc, unsigned H, uint64_t m, unsigned trim, c
 	c.frames = frames.data();
 	c.look = look.data();
 
+	if (getenv("HOST_WALK_TILES")) {
+		// markers = solid k-mers of the reads whose canonical hash has its low bits clear; 4 tiles each
+		std::vector<uint8_t> sb(kTileCap);
+		std::vector<uint64_t> sh(kTileCap);
+		std::unordered_set<uint64_t> seen;
+		for (auto& s : seqs) {
+			if (s.size() < k)
+				continue;
+			for (size_t j = 0; j + k <= s.size(); ++j) {
+				if (s.find_first_not_of("ACGT", j) < j + k)
+					continue;
+				Vtx<KW> v = vtx_from_codes<KW>((const uint8_t*)s.data() + j, k, true);
+				if (!is_marker(v.canon()) || !c.contains(v.canon()) || !seen.insert(v.canon()).second)
+					continue;
+				const Vtx<KW> rc = vtx_revcomp(v, k);
+				for (int w = 0; w < 4; ++w) {
+					TileRec t;
+					memset(&t, 0, sizeof t);
+					make_tile(c, (w & 2) ? rc : v, (w & 1) ? REV : FWD, &t, sb.data(), sh.data());
+					c.tile_mem.emplace_back(new uint8_t[t.n * 9 + 16]);
+					uint8_t* mem = c.tile_mem.back().get();
+					t.hashes = (uint64_t*)mem;
+					t.bases = mem + 8 * (size_t)t.n;
+					memcpy(t.hashes, sh.data(), 8 * (size_t)t.n);
+					memcpy(t.bases, sb.data(), t.n);
+					c.tile_recs.push_back(t);
+				}
+			}
+		}
+		for (uint32_t i = 0; i < c.tile_recs.size(); ++i)
+			c.tile_multi.emplace(HostCtx::tkey(c.tile_recs[i].key, c.tile_recs[i].cls), i);
+		c.use_tiles = true;
+		fprintf(stderr, "host_walk: %zu tiles from %zu markers\n", c.tile_recs.size(), seen.size());
+	}
+
 	Assembly as;
 	as.c = &c;
 	as.mbits = m;
@@ -224,6 +338,7 @@ static int run(unsigned k, unsigned kc, unsigned H, uint64_t m, unsigned trim, c
 	if (log)
 		fprintf(log, "read_id\tresult\n");
 	static const char* names[] = { "SHORTER_THAN_K", "NON_ACGT", "BLUNT_END", "NOT_SOLID", "ALL_KMERS_VISITED", "GENERATED_CONTIGS" };
+	size_t fallbacks = 0;
 	for (size_t r = 0; r < seqs.size(); ++r) {
 		const std::string& s = seqs[r];
 		int code;
@@ -264,10 +379,31 @@ static int run(unsigned k, unsigned kc, unsigned H, uint64_t m, unsigned trim, c
 					else {
 						code = RC_GENERATED_CONTIGS;
 						as.readID = &ids[r];
+						as.collected.clear();
+						bool repeat = false;
 						if (!walk_read<KW>(c, (const uint8_t*)s.data(), (unsigned)s.size(), as)) {
-							fprintf(stderr, "host_walk: walk failed on read %zu\n", r);
-							return 4;
+							if (!c.use_tiles || !c.tile_cycle) {
+								fprintf(stderr, "host_walk: walk failed on read %zu\n", r);
+								return 4;
+							}
+							repeat = true; // tile chain cycled: exact fallback below
+							c.fail_ = false;
+							c.tile_cycle = false;
 						}
+						if (c.use_tiles && !repeat)
+							for (auto& x : as.collected)
+								repeat |= as.has_repeat(x);
+						if (repeat) { // exact fallback: walk this read again vertex by vertex
+							++fallbacks;
+							c.use_tiles = false;
+							as.collected.clear();
+							c.allocs.clear();
+							if (!walk_read<KW>(c, (const uint8_t*)s.data(), (unsigned)s.size(), as))
+								return 4;
+							c.use_tiles = true;
+						}
+						for (auto& x : as.collected)
+							as.output(x);
 						c.allocs.clear();
 					}
 				}
@@ -278,7 +414,8 @@ static int run(unsigned k, unsigned kc, unsigned H, uint64_t m, unsigned trim, c
 	}
 	if (log)
 		fclose(log);
-	fprintf(stderr, "host_walk: %zu reads, %zu contigs, %llu neighbour probes\n", seqs.size(), as.contigID, c.probes);
+	fprintf(stderr, "host_walk: %zu reads, %zu contigs, %llu neighbour probes, %llu tile splices, %zu serial fallbacks\n", seqs.size(),
+	        as.contigID, c.probes, c.tile_splices, fallbacks);
 	return 0;
 }
 

@@ -51,3 +51,34 @@ def test_mixed_reads_edge_cases(abb, golden_dir):
     assert READ_CODES[codes[11]] == "NON_ACGT"
     assert READ_CODES[codes[12]] == "SHORTER_THAN_K"
     assert codes.max() <= 5
+
+
+def _read_fasta_gz(path):
+    import gzip
+    ids, seqs = [], []
+    with gzip.open(path, "rt") as f:
+        for line in f:
+            (ids if line[0] == ">" else seqs).append(line[1:].strip() if line[0] == ">" else line.strip())
+    return ids, seqs
+
+
+@pytest.mark.parametrize("case", json.load(open(os.path.join(os.path.dirname(__file__), "golden", "cyc_cases.json"))),
+                         ids=lambda c: c["name"])
+def test_cycles_hairpins_tandems(abb, golden_dir, case):
+    # circular plasmids, palindromic hairpins and tandem repeats: ER_CYCLE paths, the tile splice's
+    # repeat check and the vertex-by-vertex fallback must all reproduce the reference
+    from abyss_b200.capi import bloom_dbg
+    ids, seqs = _read_fasta_gz(os.path.join(golden_dir, case["reads"]))
+    fasta, _ = bloom_dbg(ids, seqs, case["k"], case["kc"], case["H"], bloom_size=case["b"], trim=case["trim"])
+    assert fasta == open(os.path.join(golden_dir, case["name"] + ".fa")).read()
+
+
+def test_tiles_on_off_same_output(abb, golden_dir, monkeypatch):
+    from abyss_b200.capi import fixed_length_reads, bloom_dbg
+    c, rs = load_case(golden_dir, "e2e_g20k_k32")
+    ids = [rs.read_id(i) for i in range(rs.n)]
+    reads = fixed_length_reads(rs.ascii(0, rs.n))
+    on, _ = bloom_dbg(ids, reads, c["k"], c["kc"], c["H"], counters=c["counters"])
+    monkeypatch.setenv("ABB_NO_TILES", "1")
+    off, _ = bloom_dbg(ids, reads, c["k"], c["kc"], c["H"], counters=c["counters"])
+    assert on == off == open(os.path.join(golden_dir, "e2e_g20k_k32.fa")).read()
