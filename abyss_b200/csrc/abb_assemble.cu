@@ -922,10 +922,10 @@ struct abb_assembler {
 	DevBuf<uint8_t> stage_bases, rep_flag;
 	DevBuf<uint64_t> stage_hashes;
 	uint64_t st_markers = 0, st_tiles = 0, st_fallbacks = 0;
-	float ms_tiles = 0;
+	float ms_tiles = 0, ms_walk = 0, ms_stage = 0, ms_repeat = 0;
 
 	// speculation control
-	unsigned spec_target = 1024;
+	unsigned spec_target = 256;
 	// host outputs of the last batch
 	std::vector<abb_contig> out_contigs;
 	std::vector<char> out_seqs;
@@ -933,7 +933,7 @@ struct abb_assembler {
 	// statistics
 	uint64_t st_iterations = 0, st_speculated = 0, st_wasted = 0, st_launches = 0, st_candidates = 0, st_contigs_tried = 0;
 	float ms_classify = 0, ms_visited = 0, ms_extend = 0, ms_replay = 0;
-	cudaEvent_t ev[2] = { nullptr, nullptr };
+	cudaEvent_t ev[2] = { nullptr, nullptr }, ev2[2] = { nullptr, nullptr };
 };
 
 namespace {
@@ -953,8 +953,9 @@ struct PhaseTimer { // CUDA-event time of a phase on the assembler stream
 };
 
 constexpr unsigned kMaxSpec = 2048;  // about one resident wave of walking warps on 148 SMs
-constexpr unsigned kMinSpec = 512;   // speculation is cheap (parallel), latency is not: never go narrow
+constexpr unsigned kMinSpec = 64;
 constexpr unsigned long long kArenaDefault = 4ULL << 30;
+static unsigned long long g_arena_hint = 0; // the arena size the previous assembler of this process ended up needing
 constexpr unsigned long long kArenaMax = 96ULL << 30;
 
 int ensure_scratch(abb_assembler* a, unsigned warps)
@@ -1146,20 +1147,27 @@ int run_extend(abb_assembler* a, unsigned n_spec, bool use_tiles, bool keep_aren
 	}
 	for (;;) {
 		ABB_CHECK(a->recs.reserve(rec_cap));
-		ABB_CHECK(ensure_arena(a, a->arena_size ? a->arena_size : kArenaDefault));
+		ABB_CHECK(ensure_arena(a, a->arena_size ? a->arena_size : std::max(kArenaDefault, g_arena_hint)));
 		ABB_CUDA(cudaMemcpyAsync(a->d_arena_top, &arena_mark, sizeof arena_mark, cudaMemcpyHostToDevice, st));
 		ABB_CUDA(cudaMemsetAsync(a->d_nrecs, 0, sizeof(unsigned), st));
 		const WalkCfg w = walk_cfg(a);
 		const TileView tv = tile_view(a, use_tiles);
+		cudaEventRecord(a->ev2[0], st);
 		ABB_DISPATCH_KW(a->kw, (k_extend<KW><<<blocks_for(n_spec, kWalkWarps), kWalkWarps * 32, 0, st>>>(
 		                           a->cur_bases, a->cur_offs, a->spec.p, n_spec, w, f->cfg, a->frames.p, a->look.p, a->d_arena, a->arena_size,
 		                           a->d_arena_top, a->recs.p, a->d_nrecs, rec_cap, a->status.p, tv)));
 		ABB_CUDA(cudaGetLastError());
+		cudaEventRecord(a->ev2[1], st);
 		++a->st_launches;
 		unsigned nrecs = 0;
 		ABB_CUDA(cudaMemcpyAsync(&nrecs, a->d_nrecs, sizeof nrecs, cudaMemcpyDeviceToHost, st));
 		ABB_CUDA(cudaMemcpyAsync(status.data(), a->status.p, n_spec * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
 		ABB_CUDA(cudaStreamSynchronize(st));
+		{
+			float ms = 0;
+			cudaEventElapsedTime(&ms, a->ev2[0], a->ev2[1]);
+			a->ms_walk += ms;
+		}
 		if (nrecs > rec_cap) { // record buffer too small: rerun with room for everything
 			rec_cap = nrecs + nrecs / 4 + 16;
 			continue;
@@ -1175,6 +1183,7 @@ int run_extend(abb_assembler* a, unsigned n_spec, bool use_tiles, bool keep_aren
 			const unsigned long long bigger = std::min<unsigned long long>(std::min(kArenaMax, room), a->arena_size * 4);
 			if (bigger > a->arena_size + (1ULL << 28)) {
 				ABB_CHECK(ensure_arena(a, bigger));
+				g_arena_hint = std::max(g_arena_hint, bigger);
 				continue;
 			}
 		}
@@ -1227,9 +1236,15 @@ int stage_contigs(abb_assembler* a, const std::vector<ContigRec>& recs, const Ro
 	ABB_CHECK(a->ch0.reserve(L.cslot[nc] + 1));
 	ABB_CHECK(a->cvalid.reserve(L.cslot[nc] + 1));
 	if (nc) {
+		cudaEventRecord(a->ev2[0], st);
 		k_gather<<<std::min<unsigned>(nc, 148 * 8), 256, 0, st>>>(a->recs_sorted.p, nc, a->coffs.p, a->cseq.p);
 		ABB_CUDA(cudaGetLastError());
 		ABB_CHECK(launch_hash(nullptr, f->k, nullptr, a->cseq.p, a->coffs.p, a->cslot.p, 0, nc, 0, a->ch0.p, a->cvalid.p, st, nullptr));
+		cudaEventRecord(a->ev2[1], st);
+		cudaEventSynchronize(a->ev2[1]);
+		float ms = 0;
+		cudaEventElapsedTime(&ms, a->ev2[0], a->ev2[1]);
+		a->ms_stage += ms;
 		a->st_launches += 2;
 	}
 	return ABB_OK;
@@ -1320,14 +1335,21 @@ int speculate_round(abb_assembler* a, const std::vector<unsigned>& cand, size_t*
 					tab <<= 1;
 				ABB_CHECK(a->rep_tab.reserve(tab));
 				ABB_CHECK(a->rep_flag.reserve(nc));
+				cudaEventRecord(a->ev2[0], st);
 				ABB_CUDA(cudaMemsetAsync(a->rep_tab.p, 0, tab * sizeof(unsigned long long), st));
 				ABB_CUDA(cudaMemsetAsync(a->rep_flag.p, 0, nc, st));
 				k_repeat_check<<<148 * 8, 256, 0, st>>>(a->recs_sorted.p, nc, a->cslot.p, a->ch0.p, a->rep_tab.p, tab - 1, a->rep_flag.p);
 				ABB_CUDA(cudaGetLastError());
+				cudaEventRecord(a->ev2[1], st);
 				++a->st_launches;
 				std::vector<uint8_t> flag(nc);
 				ABB_CUDA(cudaMemcpyAsync(flag.data(), a->rep_flag.p, nc, cudaMemcpyDeviceToHost, st));
 				ABB_CUDA(cudaStreamSynchronize(st));
+				{
+					float ms = 0;
+					cudaEventElapsedTime(&ms, a->ev2[0], a->ev2[1]);
+					a->ms_repeat += ms;
+				}
 				for (unsigned c = 0; c < nc; ++c)
 					if (flag[c] && (redo.empty() || redo.back() != recs[c].spec) &&
 					    std::find(redo.begin(), redo.end(), recs[c].spec) == redo.end())
@@ -1475,9 +1497,9 @@ int speculate_round(abb_assembler* a, const std::vector<unsigned>& cand, size_t*
 	a->st_wasted += wasted;
 	// adapt the amount of speculation: grow while most speculated reads were really needed
 	if (n_ok == n_spec) {
-		if (wasted * 2 <= n_ok)
+		if (wasted * 4 <= n_ok)
 			a->spec_target = std::min(kMaxSpec, a->spec_target * 2);
-		else if (wasted * 10 > n_ok * 9)
+		else if (wasted * 2 > n_ok)
 			a->spec_target = std::max(kMinSpec, a->spec_target / 2);
 	}
 	(void)n_reads;
@@ -1528,6 +1550,8 @@ int abb_assembler_create(abb_assembler** out, abb_filter* solid, const abb_assem
 	a->stream = solid->stream; // one stream carries pass 1 and pass 2 of a filter
 	if ((e = cudaEventCreate(&a->ev[0])) != cudaSuccess) return fail(e, "cudaEventCreate");
 	if ((e = cudaEventCreate(&a->ev[1])) != cudaSuccess) return fail(e, "cudaEventCreate");
+	if ((e = cudaEventCreate(&a->ev2[0])) != cudaSuccess) return fail(e, "cudaEventCreate");
+	if ((e = cudaEventCreate(&a->ev2[1])) != cudaSuccess) return fail(e, "cudaEventCreate");
 	if ((e = cudaMalloc((void**)&a->d_arena_top, sizeof(unsigned long long))) != cudaSuccess) return fail(e, "cudaMalloc");
 	if ((e = cudaMalloc((void**)&a->d_nrecs, sizeof(unsigned))) != cudaSuccess) return fail(e, "cudaMalloc");
 	if ((e = cudaMalloc((void**)&a->d_ends_n, 2 * sizeof(unsigned))) != cudaSuccess) return fail(e, "cudaMalloc");
@@ -1564,6 +1588,8 @@ int abb_assembler_destroy(abb_assembler* a)
 	cudaFree(a->d_ends_n);
 	if (a->ev[0]) cudaEventDestroy(a->ev[0]);
 	if (a->ev[1]) cudaEventDestroy(a->ev[1]);
+	if (a->ev2[0]) cudaEventDestroy(a->ev2[0]);
+	if (a->ev2[1]) cudaEventDestroy(a->ev2[1]);
 	delete a;
 	return ABB_OK;
 }
@@ -1677,6 +1703,9 @@ int abb_assembler_stats(const abb_assembler* a, abb_assembly_stats* out)
 	out->ms_extend = a->ms_extend;
 	out->ms_replay = a->ms_replay;
 	out->ms_tiles = a->ms_tiles;
+	out->ms_walk = a->ms_walk;
+	out->ms_stage = a->ms_stage;
+	out->ms_repeat = a->ms_repeat;
 	out->markers = a->st_markers;
 	out->tiles = a->st_tiles;
 	out->serial_fallbacks = a->st_fallbacks;

@@ -300,11 +300,13 @@ def main():
         "config": workload_config(args), "clocks": clk.summary(), "e2e": e2e,
         "gpu_launches": int(ist.launches + ast.launches), "roofline": roofline, "cpu_baseline": cpu,
         "phases_ms": {"hash": ist.ms_hash, "insert": ist.ms_insert, "classify": ast.ms_classify, "visited": ast.ms_visited,
-                      "extend": ast.ms_extend, "replay": ast.ms_replay},
+                      "tiles": ast.ms_tiles, "extend": ast.ms_extend, "extend_walk": ast.ms_walk, "extend_stage": ast.ms_stage,
+                      "extend_repeat_check": ast.ms_repeat, "replay": ast.ms_replay},
         "insert_kmers_per_s": nk / ((ist.ms_hash + ist.ms_insert) * 1e-3),
-        "extend_kmers_per_s": nk / ((ast.ms_classify + ast.ms_visited + ast.ms_extend + ast.ms_replay) * 1e-3),
+        "extend_kmers_per_s": nk / ((ast.ms_classify + ast.ms_tiles + ast.ms_visited + ast.ms_extend + ast.ms_replay) * 1e-3),
         "unitigs": int(cnt.contig_id), "bases_assembled": int(cnt.bases_assembled),
-        "speculation": {"rounds": int(ast.rounds), "speculated": int(ast.speculated_reads), "wasted": int(ast.wasted_reads)},
+        "speculation": {"rounds": int(ast.rounds), "speculated": int(ast.speculated_reads), "wasted": int(ast.wasted_reads),
+                        "markers": int(ast.markers), "tiles": int(ast.tiles), "serial_fallbacks": int(ast.serial_fallbacks)},
         "deferred_inserts": int(ist.deferred),
     }
     print(json.dumps(line))

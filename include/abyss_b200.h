@@ -164,6 +164,7 @@ typedef struct abb_assembly_stats {
 	uint64_t launches;          /* kernels launched by the assembler */
 	float ms_classify, ms_visited, ms_extend, ms_replay; /* CUDA-event time per phase */
 	float ms_tiles;             /* marker enumeration + tile production */
+	float ms_walk, ms_stage, ms_repeat; /* inside ms_extend: K4 kernels, unitig gather+hash, repeat check */
 	uint64_t markers, tiles;    /* marker vertices found / marker-to-marker tiles stored */
 	uint64_t serial_fallbacks;  /* reads re-walked vertex by vertex after the repeat check */
 } abb_assembly_stats;
