@@ -77,6 +77,9 @@ SIGNATURES = {
     "abb_contains_hashes": (C.c_int, [_vp, _vp, C.c_uint64, _vp]),
     "abb_mincount_hashes": (C.c_int, [_vp, _vp, C.c_uint64, _vp]),
     "abb_hash_reads": (C.c_int, [C.c_uint, C.c_char_p, _vp, _vp, C.c_uint64, _vp, _vp, _u64p, C.c_int]),
+    "abb_hash_reads_dev": (C.c_int, [_vp, _vp, _vp, C.c_uint64, _vp, _vp, C.c_uint64, _u64p]),
+    "abb_insert_h0_dev": (C.c_int, [_vp, _vp, C.c_uint64]),
+    "abb_filter_device_ptr": (_vp, [_vp, C.c_int]),
     "abb_filter_download": (C.c_int, [_vp, C.c_int, _vp, C.c_uint64]),
     "abb_filter_upload": (C.c_int, [_vp, C.c_int, _vp, C.c_uint64]),
     "abb_filter_clear": (C.c_int, [_vp]),
@@ -224,6 +227,19 @@ class Filter:
         n = C.c_uint64(0)
         check(self._lib.abb_insert_reads_dev(self._h, _vp(d_bases_ptr), _vp(d_offs_ptr), n_reads, n_bases, C.byref(n)))
         return n.value
+
+    # -- multi-GPU building blocks
+    def hash_reads_dev(self, d_bases_ptr, d_offs_ptr, n_reads, d_h0_ptr=0, d_valid_ptr=0, capacity=0) -> int:
+        n = C.c_uint64(0)
+        check(self._lib.abb_hash_reads_dev(self._h, _vp(d_bases_ptr), _vp(d_offs_ptr), n_reads, _vp(d_h0_ptr), _vp(d_valid_ptr), capacity,
+                                           C.byref(n)))
+        return n.value
+
+    def insert_h0_dev(self, d_h0_ptr: int, n: int):
+        check(self._lib.abb_insert_h0_dev(self._h, _vp(d_h0_ptr), n))
+
+    def device_ptr(self, level: int = -1) -> int:
+        return self._lib.abb_filter_device_ptr(self._h, level) or 0
 
     # -- literal hash interface
     def _hashes(self, hashes):

@@ -534,6 +534,56 @@ int abb_insert_hashes(abb_filter* f, const uint64_t* hashes, uint64_t n)
 	return ABB_OK;
 }
 
+int abb_insert_h0_dev(abb_filter* f, const uint64_t* d_h0, uint64_t n)
+{
+	ABB_REQUIRE(f, "NULL filter");
+	if (n == 0)
+		return ABB_OK;
+	ABB_REQUIRE(d_h0, "NULL hashes");
+	ABB_CUDA(cudaSetDevice(f->device));
+	ABB_CHECK(ordered_insert<false>(f, d_h0, nullptr, n));
+	ABB_CUDA(cudaStreamSynchronize(f->stream));
+	f->st.kmers += n;
+	f->st.slots += n;
+	return ABB_OK;
+}
+
+int abb_hash_reads_dev(abb_filter* f, const char* d_bases, const uint64_t* d_offsets, uint64_t n_reads, uint64_t* d_h0,
+                       uint8_t* d_valid, uint64_t capacity, uint64_t* n_slots_out)
+{
+	ABB_REQUIRE(f, "NULL filter");
+	if (n_slots_out)
+		*n_slots_out = 0;
+	if (n_reads == 0)
+		return ABB_OK;
+	ABB_REQUIRE(d_bases && d_offsets, "NULL read buffers");
+	ABB_CUDA(cudaSetDevice(f->device));
+	uint64_t total = 0;
+	ABB_CHECK(compute_slot_offsets(f->k, d_offsets, n_reads, f->slot_offs, f->scan_tmp, f->stream, &total, &f->st.launches));
+	if (n_slots_out)
+		*n_slots_out = total;
+	if (total == 0 || !d_h0 || !d_valid)
+		return ABB_OK;
+	ABB_REQUIRE(capacity >= total, "output buffers hold %llu slots, %llu needed", (unsigned long long)capacity, (unsigned long long)total);
+	ABB_CHECK(launch_hash(f, f->k, f->d_care, (const uint8_t*)d_bases, d_offsets, f->slot_offs.p, 0, n_reads, 0, d_h0, d_valid, f->stream,
+	                      &f->st.launches));
+	ABB_CUDA(cudaStreamSynchronize(f->stream));
+	return ABB_OK;
+}
+
+void* abb_filter_device_ptr(abb_filter* f, int level)
+{
+	if (!f)
+		return nullptr;
+	if (level < 0)
+		level = (int)f->levels - 1;
+	if ((unsigned)level >= f->levels)
+		return nullptr;
+	cudaSetDevice(f->device);
+	cudaStreamSynchronize(f->stream);
+	return f->d_data + (uint64_t)level * f->bytes_per_level;
+}
+
 static int query_hashes(abb_filter* f, const uint64_t* hashes, uint64_t n, uint8_t* out, bool want_min)
 {
 	ABB_REQUIRE(f, "NULL filter");

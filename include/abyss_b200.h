@@ -100,6 +100,17 @@ int abb_hash_reads(unsigned k, const char* mask, const char* bases, const uint64
                    uint64_t n_reads, uint64_t* out_h0, uint8_t* out_valid, uint64_t* n_slots_out,
                    int device);
 
+/* ---- multi-GPU building blocks (hash-range sharding) ------------------
+ * abb_hash_reads_dev: K1 only, device in / device out (d_h0, d_valid hold `capacity` slots).
+ * abb_insert_h0_dev:  ordered insert of n canonical hashes (device resident, all valid), in array
+ *                     order -- what a rank does with the k-mers it owns after the all-to-all.
+ * abb_filter_device_ptr: the raw device array of a level, for the NCCL union (all-reduce max /
+ *                     or) issued by the caller; synchronises the filter's stream first. */
+int abb_hash_reads_dev(abb_filter* f, const char* d_bases, const uint64_t* d_offsets, uint64_t n_reads,
+                       uint64_t* d_h0, uint8_t* d_valid, uint64_t capacity, uint64_t* n_slots_out);
+int abb_insert_h0_dev(abb_filter* f, const uint64_t* d_h0, uint64_t n);
+void* abb_filter_device_ptr(abb_filter* f, int level);
+
 /* ---- raw array <-> host (operator<< / loadFilter: CountingBloomFilter.hpp:262-379,
  * BloomFilter.hpp:98-163,288-294; for ABB_CASCADING `level` selects the level, -1 = last,
  * which is the only one the reference serialises, HashAgnosticCascadingBloom.h:143-150) */
