@@ -58,7 +58,8 @@ static FilterView view_of(const abb_filter* f)
 	return v;
 }
 
-/** make sure the ordered-insert workspace exists for the current window size */
+/** make sure the ordered-insert workspace exists for the current window size: two tag tables so that
+ *  the reservation pass of window w+1 overlaps the commit/resolve of window w */
 static int ensure_workspace(abb_filter* f)
 {
 	const uint64_t want = next_pow2(2 * f->window * f->H);
@@ -70,11 +71,20 @@ static int ensure_workspace(abb_filter* f)
 		cudaFree(f->d_deferred);
 	f->d_tags = nullptr;
 	f->d_deferred = nullptr;
-	ABB_CUDA(cudaMalloc((void**)&f->d_tags, want * sizeof(unsigned long long)));
-	ABB_CUDA(cudaMemsetAsync(f->d_tags, 0, want * sizeof(unsigned long long), f->stream));
+	ABB_CUDA(cudaMalloc((void**)&f->d_tags, 2 * want * sizeof(unsigned long long)));
+	ABB_CUDA(cudaMemsetAsync(f->d_tags, 0, 2 * want * sizeof(unsigned long long), f->stream));
 	ABB_CUDA(cudaMalloc((void**)&f->d_deferred, f->window * sizeof(unsigned)));
 	f->tag_slots = want;
 	f->epoch = 0;
+	f->epoch2[0] = f->epoch2[1] = 0;
+	if (!f->stream2) {
+		ABB_CUDA(cudaStreamCreateWithFlags(&f->stream2, cudaStreamNonBlocking));
+		for (int i = 0; i < 2; ++i) {
+			ABB_CUDA(cudaEventCreateWithFlags(&f->ev_res[i], cudaEventDisableTiming));
+			ABB_CUDA(cudaEventCreateWithFlags(&f->ev_done[i], cudaEventDisableTiming));
+		}
+		ABB_CUDA(cudaEventCreateWithFlags(&f->ev_in, cudaEventDisableTiming));
+	}
 	return ABB_OK;
 }
 
@@ -106,40 +116,62 @@ static int ordered_insert(abb_filter* f, const uint64_t* d_hashes, const uint8_t
 		return ABB_OK;
 	}
 	ABB_CHECK(ensure_workspace(f));
-	const TagTable tab = { f->d_tags, f->tag_slots - 1 };
 	const FilterView fv = view_of(f);
-	for (uint64_t w0 = 0; w0 < n_slots; w0 += f->window) {
+	cudaStream_t s_main = f->stream, s_res = f->stream2;
+	// the reservation stream may start once the hashes are there
+	ABB_CUDA(cudaEventRecord(f->ev_in, s_main));
+	ABB_CUDA(cudaStreamWaitEvent(s_res, f->ev_in, 0));
+	const uint64_t n_windows = (n_slots + f->window - 1) / f->window;
+	bool done_recorded[2] = { false, false };
+	unsigned epoch_of[2] = { 0, 0 };
+	auto issue_reserve = [&](uint64_t w) -> int {
+		const int p = (int)(w & 1);
+		const uint64_t w0 = w * f->window;
 		const unsigned n = (unsigned)std::min<uint64_t>(f->window, n_slots - w0);
-		if (f->epoch >= kMaxEpoch) {
-			ABB_CUDA(cudaMemsetAsync(f->d_tags, 0, f->tag_slots * sizeof(unsigned long long), f->stream));
-			f->epoch = 0;
+		const TagTable tab = { f->d_tags + (uint64_t)p * f->tag_slots, f->tag_slots - 1 };
+		if (done_recorded[p]) // table p is free again once window w-2 has been resolved
+			ABB_CUDA(cudaStreamWaitEvent(s_res, f->ev_done[p], 0));
+		if (f->epoch2[p] >= kMaxEpoch) {
+			ABB_CUDA(cudaMemsetAsync(tab.e, 0, f->tag_slots * sizeof(unsigned long long), s_res));
+			f->epoch2[p] = 0;
 		}
-		const unsigned epoch = ++f->epoch;
+		epoch_of[p] = ++f->epoch2[p];
+		ABB_DISPATCH_H(f->H, (k_reserve<LITERAL, MAXH><<<blocks_for(n, 256), 256, 0, s_res>>>(d_hashes, d_valid, w0, n, f->cfg, tab, epoch_of[p])));
+		ABB_CUDA(cudaEventRecord(f->ev_res[p], s_res));
+		return ABB_OK;
+	};
+	ABB_CHECK(issue_reserve(0));
+	for (uint64_t w = 0; w < n_windows; ++w) {
+		const int p = (int)(w & 1);
+		const uint64_t w0 = w * f->window;
+		const unsigned n = (unsigned)std::min<uint64_t>(f->window, n_slots - w0);
+		const TagTable tab = { f->d_tags + (uint64_t)p * f->tag_slots, f->tag_slots - 1 };
+		const unsigned epoch = epoch_of[p];
+		if (w + 1 < n_windows)
+			ABB_CHECK(issue_reserve(w + 1)); // overlaps this window's commit + resolve
+		ABB_CUDA(cudaStreamWaitEvent(s_main, f->ev_res[p], 0));
 		const unsigned grid = blocks_for(n, 256);
 		ABB_DISPATCH_H(f->H, {
-			k_reserve<LITERAL, MAXH><<<grid, 256, 0, f->stream>>>(d_hashes, d_valid, w0, n, f->cfg, tab, epoch);
 			if (f->kind == ABB_COUNTING) {
 				if (f->profile && f->prof_used + 2 <= f->prof_ev.size())
-					cudaEventRecord(f->prof_ev[f->prof_used++], f->stream);
-				k_commit<0, LITERAL, MAXH><<<grid, 256, 0, f->stream>>>(d_hashes, d_valid, w0, n, f->cfg, tab, epoch, fv,
-				                                                       f->d_deferred, f->d_ndef);
+					cudaEventRecord(f->prof_ev[f->prof_used++], s_main);
+				k_commit<0, LITERAL, MAXH><<<grid, 256, 0, s_main>>>(d_hashes, d_valid, w0, n, f->cfg, tab, epoch, fv, f->d_deferred, f->d_ndef);
 				if (f->profile && (f->prof_used & 1))
-					cudaEventRecord(f->prof_ev[f->prof_used++], f->stream);
-				k_resolve<0, LITERAL, MAXH><<<1, 1024, 0, f->stream>>>(d_hashes, w0, f->cfg, tab, epoch, fv,
-				                                                      f->d_deferred, f->d_ndef, f->d_stats);
+					cudaEventRecord(f->prof_ev[f->prof_used++], s_main);
+				k_resolve<0, LITERAL, MAXH><<<1, 1024, 0, s_main>>>(d_hashes, w0, f->cfg, tab, epoch, fv, f->d_deferred, f->d_ndef, f->d_stats);
 			} else {
-				k_commit<1, LITERAL, MAXH><<<grid, 256, 0, f->stream>>>(d_hashes, d_valid, w0, n, f->cfg, tab, epoch, fv,
-				                                                       f->d_deferred, f->d_ndef);
-				k_resolve<1, LITERAL, MAXH><<<1, 1024, 0, f->stream>>>(d_hashes, w0, f->cfg, tab, epoch, fv,
-				                                                      f->d_deferred, f->d_ndef, f->d_stats);
+				k_commit<1, LITERAL, MAXH><<<grid, 256, 0, s_main>>>(d_hashes, d_valid, w0, n, f->cfg, tab, epoch, fv, f->d_deferred, f->d_ndef);
+				k_resolve<1, LITERAL, MAXH><<<1, 1024, 0, s_main>>>(d_hashes, w0, f->cfg, tab, epoch, fv, f->d_deferred, f->d_ndef, f->d_stats);
 			}
 		});
+		ABB_CUDA(cudaEventRecord(f->ev_done[p], s_main));
+		done_recorded[p] = true;
 		f->st.launches += 3;
 		f->st.windows += 1;
 	}
 	ABB_CUDA(cudaGetLastError());
 	if (f->profile && f->prof_used) { // fold the per-launch k_commit times into the statistics
-		ABB_CUDA(cudaStreamSynchronize(f->stream));
+		ABB_CUDA(cudaStreamSynchronize(s_main));
 		for (size_t i = 0; i + 1 < f->prof_used; i += 2) {
 			float ms = 0;
 			cudaEventElapsedTime(&ms, f->prof_ev[i], f->prof_ev[i + 1]);
@@ -210,6 +242,21 @@ int launch_hash(abb_filter* f, unsigned k, const uint8_t* d_care, const uint8_t*
 		k_hash_reads<<<grid, kHashWarps * 32, 0, stream>>>(d_bases, d_offs + r0, d_slot_offs + r0, slot_base, n, k, d_h0, d_valid);
 	if (launches)
 		*launches += 1;
+	ABB_CUDA(cudaGetLastError());
+	return ABB_OK;
+}
+
+/** K1 over explicit (possibly overlapping) segments, see k_hash_segments */
+int launch_hash_segments(unsigned k, const uint8_t* d_bases, const uint64_t* d_seg_beg, const unsigned* d_seg_len,
+                         const uint64_t* d_seg_slot, uint64_t n_segs, uint64_t* d_h0, uint8_t* d_valid, cudaStream_t stream)
+{
+	if (n_segs == 0)
+		return ABB_OK;
+	int sms = 148, dev = 0;
+	cudaGetDevice(&dev);
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	const unsigned grid = (unsigned)std::min<uint64_t>((n_segs + kHashWarps - 1) / kHashWarps, (uint64_t)sms * 32);
+	k_hash_segments<<<grid, kHashWarps * 32, 0, stream>>>(d_bases, d_seg_beg, d_seg_len, d_seg_slot, n_segs, k, d_h0, d_valid);
 	ABB_CUDA(cudaGetLastError());
 	return ABB_OK;
 }
@@ -438,6 +485,15 @@ int abb_filter_destroy(abb_filter* f)
 	f->out8.release();
 	for (auto e : f->prof_ev)
 		cudaEventDestroy(e);
+	if (f->stream2) {
+		cudaStreamSynchronize(f->stream2);
+		for (int i = 0; i < 2; ++i) {
+			cudaEventDestroy(f->ev_res[i]);
+			cudaEventDestroy(f->ev_done[i]);
+		}
+		cudaEventDestroy(f->ev_in);
+		cudaStreamDestroy(f->stream2);
+	}
 	if (f->ev0)
 		cudaEventDestroy(f->ev0);
 	if (f->ev1)

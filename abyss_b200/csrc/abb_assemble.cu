@@ -205,10 +205,12 @@ struct WarpCtx {
 		__syncwarp();
 		for (int side = 0; side < 2; ++side) {
 			const U32Vec& tv = side ? o.tiles_right : o.tiles_left;
-			for (unsigned ti = 0; ti < tv.n; ++ti) {
+			for (unsigned ti = lane; ti < tv.n; ti += 32) { // one lane per tile: 32 independent streams
 				const TileRec* T = tile_recs + tv.p[ti];
-				for (unsigned i = lane; i < T->n; i += 32) {
-					uint64_t key = T->hashes[i];
+				const uint64_t* th = T->hashes;
+				const unsigned tn = T->n;
+				for (unsigned i = 0; i < tn; ++i) {
+					uint64_t key = th[i];
 					if ((o.popped_front && key == o.front_h) || (o.popped_back && key == o.back_h))
 						continue;
 					key = key ? key : 1;
@@ -626,12 +628,17 @@ k_repeat_check(const ContigRec* __restrict__ recs, unsigned n_contigs, const uin
 
 /** dense ASCII copies of the ordered unitigs (pathToSeq output as characters) */
 __global__ void __launch_bounds__(256)
-k_gather(const ContigRec* __restrict__ recs, unsigned n, const uint64_t* __restrict__ coffs, uint8_t* __restrict__ out)
+k_gather(const ContigRec* __restrict__ recs, const unsigned* __restrict__ seg_contig, const uint64_t* __restrict__ seg_beg,
+         const unsigned* __restrict__ seg_len, unsigned n_segs, const uint64_t* __restrict__ coffs, uint8_t* __restrict__ out)
 {
-	for (unsigned c = blockIdx.x; c < n; c += gridDim.x) {
-		const uint8_t* s = reinterpret_cast<const uint8_t*>(recs[c].seq);
-		uint8_t* d = out + coffs[c];
-		for (unsigned i = threadIdx.x; i < recs[c].len; i += blockDim.x)
+	// one block per segment of a unitig (long unitigs are cut so that the copy uses the whole GPU);
+	// seg_beg is the absolute offset in `out`, seg_len includes the k-1 overlap (harmlessly copied twice)
+	for (unsigned sgi = blockIdx.x; sgi < n_segs; sgi += gridDim.x) {
+		const unsigned c = seg_contig[sgi];
+		const uint64_t rel = seg_beg[sgi] - coffs[c];
+		const uint8_t* s = reinterpret_cast<const uint8_t*>(recs[c].seq) + rel;
+		uint8_t* d = out + seg_beg[sgi];
+		for (unsigned i = threadIdx.x; i < seg_len[sgi]; i += blockDim.x)
 			d[i] = "ACGT"[s[i] & 3];
 	}
 }
@@ -891,7 +898,8 @@ struct abb_assembler {
 	// batch state (device)
 	DevBuf<uint8_t> bases, valid, codes, vis, scan_tmp, cseq, cvalid, rcode, caccept;
 	DevBuf<uint64_t> offs, slot_offs, h0, coffs, cslot, ch0;
-	DevBuf<unsigned> cand, spec, spec_cbeg, clen, ccov, status;
+	DevBuf<unsigned> cand, spec, spec_cbeg, clen, ccov, status, seg_contig, seg_len;
+	DevBuf<uint64_t> seg_beg, seg_slot;
 	DevBuf<ContigRec> recs, recs_sorted;
 	DevBuf<Frame> frames;
 	DevBuf<uint64_t> look;
@@ -1236,10 +1244,30 @@ int stage_contigs(abb_assembler* a, const std::vector<ContigRec>& recs, const Ro
 	ABB_CHECK(a->ch0.reserve(L.cslot[nc] + 1));
 	ABB_CHECK(a->cvalid.reserve(L.cslot[nc] + 1));
 	if (nc) {
+		// cut the unitigs into segments of kSegWindows k-mers (+ k-1 bases of overlap)
+		constexpr unsigned kSegWindows = 8192;
+		std::vector<unsigned> seg_contig, seg_len;
+		std::vector<uint64_t> seg_beg, seg_slot;
+		for (unsigned c = 0; c < nc; ++c) {
+			const unsigned nk = recs[c].len - f->k + 1;
+			for (unsigned j = 0; j < nk; j += kSegWindows) {
+				const unsigned w = std::min(kSegWindows, nk - j);
+				seg_contig.push_back(c);
+				seg_beg.push_back(L.coffs[c] + j);
+				seg_len.push_back(w + f->k - 1);
+				seg_slot.push_back(L.cslot[c] + j);
+			}
+		}
+		const unsigned ns = (unsigned)seg_contig.size();
+		ABB_CHECK(h2d(a->seg_contig, seg_contig, st));
+		ABB_CHECK(h2d(a->seg_len, seg_len, st));
+		ABB_CHECK(h2d(a->seg_beg, seg_beg, st));
+		ABB_CHECK(h2d(a->seg_slot, seg_slot, st));
 		cudaEventRecord(a->ev2[0], st);
-		k_gather<<<std::min<unsigned>(nc, 148 * 8), 256, 0, st>>>(a->recs_sorted.p, nc, a->coffs.p, a->cseq.p);
+		k_gather<<<std::min<unsigned>(ns, 148 * 16), 256, 0, st>>>(a->recs_sorted.p, a->seg_contig.p, a->seg_beg.p, a->seg_len.p, ns, a->coffs.p,
+		                                                          a->cseq.p);
 		ABB_CUDA(cudaGetLastError());
-		ABB_CHECK(launch_hash(nullptr, f->k, nullptr, a->cseq.p, a->coffs.p, a->cslot.p, 0, nc, 0, a->ch0.p, a->cvalid.p, st, nullptr));
+		ABB_CHECK(launch_hash_segments(f->k, a->cseq.p, a->seg_beg.p, a->seg_len.p, a->seg_slot.p, ns, a->ch0.p, a->cvalid.p, st));
 		cudaEventRecord(a->ev2[1], st);
 		cudaEventSynchronize(a->ev2[1]);
 		float ms = 0;
@@ -1580,6 +1608,7 @@ int abb_assembler_destroy(abb_assembler* a)
 	cudaFree(a->d_tile_pool);
 	cudaFree(a->d_tile_pool_top);
 	cudaFree(a->d_marker_set);
+	a->seg_contig.release(); a->seg_len.release(); a->seg_beg.release(); a->seg_slot.release();
 	a->new_markers.release(); a->rep_tab.release(); a->stage_bases.release(); a->rep_flag.release(); a->stage_hashes.release();
 	cudaFree(a->d_arena);
 	cudaFree(a->d_arena_top);

@@ -81,6 +81,8 @@ namespace abb {
 int launch_hash(abb_filter* f, unsigned k, const uint8_t* d_care, const uint8_t* d_bases, const uint64_t* d_offs,
                 const uint64_t* d_slot_offs, uint64_t r0, uint64_t r1, uint64_t slot_base, uint64_t* d_h0, uint8_t* d_valid,
                 cudaStream_t stream, uint64_t* launches);
+int launch_hash_segments(unsigned k, const uint8_t* d_bases, const uint64_t* d_seg_beg, const unsigned* d_seg_len,
+                         const uint64_t* d_seg_slot, uint64_t n_segs, uint64_t* d_h0, uint8_t* d_valid, cudaStream_t stream);
 }
 
 /** The filter handle (opaque in the C ABI). */
@@ -102,6 +104,9 @@ struct abb_filter {
 	unsigned long long* d_tags = nullptr;
 	uint64_t tag_slots = 0;
 	unsigned epoch = 0;
+	unsigned epoch2[2] = { 0, 0 };          // per tag table
+	cudaStream_t stream2 = nullptr;         // reservation pass of the next window
+	cudaEvent_t ev_res[2] = { nullptr, nullptr }, ev_done[2] = { nullptr, nullptr }, ev_in = nullptr;
 	unsigned* d_deferred = nullptr;
 	unsigned* d_ndef = nullptr;
 	unsigned long long* d_stats = nullptr; // [0] deferred [1] max rounds [2] serial [3..4] popcount scratch

@@ -175,6 +175,60 @@ ABB_D uint64_t shfl64(uint64_t v, int src)
  * P_i = XOR_{t<=i} R^{-t}(seed(c_t)), Q_i = XOR_{t<=i} R^{t}(seed(comp c_t)):
  *   fwd(j) = R^{j+k-1}(P_{j+k-1} ^ P_{j-1}),  rc(j) = R^{-j}(Q_{j+k-1} ^ Q_{j-1}).
  */
+/** one warp hashes the L bases at `beg`; window j goes to slot slot0 + j */
+ABB_D void hash_one_read(const uint8_t* __restrict__ bases, uint64_t beg, unsigned L, uint64_t slot0, unsigned k, uint64_t* P,
+                         uint64_t* Q, unsigned* B, int lane, uint64_t* __restrict__ h0_out, uint8_t* __restrict__ valid_out)
+{
+	uint64_t carryP = 0, carryQ = 0;
+	unsigned carryB = 0;
+	for (unsigned base = 0; base < L; base += 32) {
+		const unsigned i = base + lane;
+		unsigned code = 4;
+		if (i < L)
+			code = base_code(bases[beg + i]);
+		uint64_t p = 0, q = 0;
+		if (code < 4) {
+			p = sror_n(seed_of(code), i);
+			q = srol_n(seed_of(3 - code), i);
+		}
+		// inclusive prefix XOR across the warp
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			uint64_t up = shfl_up64(p, d), uq = shfl_up64(q, d);
+			if (lane >= d) {
+				p ^= up;
+				q ^= uq;
+			}
+		}
+		p ^= carryP;
+		q ^= carryQ;
+		const unsigned badmask = __ballot_sync(0xffffffffu, code >= 4 && i < L);
+		const unsigned b = carryB + __popc(badmask & (0xffffffffu >> (31 - lane)));
+		P[i & (kRing - 1)] = p;
+		Q[i & (kRing - 1)] = q;
+		B[i & (kRing - 1)] = b;
+		carryP = shfl64(p, 31);
+		carryQ = shfl64(q, 31);
+		carryB += __popc(badmask);
+		__syncwarp();
+		if (i < L && i + 1 >= k) {
+			const unsigned j = i + 1 - k; // window [j, i]
+			uint64_t pj = 0, qj = 0;
+			unsigned bj = 0;
+			if (j > 0) {
+				pj = P[(j - 1) & (kRing - 1)];
+				qj = Q[(j - 1) & (kRing - 1)];
+				bj = B[(j - 1) & (kRing - 1)];
+			}
+			const uint64_t fh = srol_n(p ^ pj, i);
+			const uint64_t rh = sror_n(q ^ qj, j);
+			h0_out[slot0 + j] = rh < fh ? rh : fh;
+			valid_out[slot0 + j] = (b == bj) ? 1 : 0;
+		}
+		__syncwarp();
+	}
+}
+
 static __global__ void __launch_bounds__(kHashWarps * 32)
 k_hash_reads(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offs,
              const uint64_t* __restrict__ slot_offs, uint64_t slot_base, uint64_t n_reads, unsigned k,
@@ -184,65 +238,31 @@ k_hash_reads(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ off
 	__shared__ uint64_t sQ[kHashWarps][kRing];
 	__shared__ unsigned sB[kHashWarps][kRing];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	uint64_t* P = sP[warp];
-	uint64_t* Q = sQ[warp];
-	unsigned* B = sB[warp];
-
-	for (uint64_t r = (uint64_t)blockIdx.x * kHashWarps + warp; r < n_reads;
-	     r += (uint64_t)gridDim.x * kHashWarps) {
+	for (uint64_t r = (uint64_t)blockIdx.x * kHashWarps + warp; r < n_reads; r += (uint64_t)gridDim.x * kHashWarps) {
 		const uint64_t beg = offs[r];
 		const unsigned L = (unsigned)(offs[r + 1] - beg);
 		if (L < k)
 			continue;
-		const uint64_t slot0 = slot_offs[r] - slot_base;
-		uint64_t carryP = 0, carryQ = 0;
-		unsigned carryB = 0;
-		for (unsigned base = 0; base < L; base += 32) {
-			const unsigned i = base + lane;
-			unsigned code = 4;
-			if (i < L)
-				code = base_code(bases[beg + i]);
-			uint64_t p = 0, q = 0;
-			if (code < 4) {
-				p = sror_n(seed_of(code), i);
-				q = srol_n(seed_of(3 - code), i);
-			}
-			// inclusive prefix XOR across the warp
-#pragma unroll
-			for (int d = 1; d < 32; d <<= 1) {
-				uint64_t up = shfl_up64(p, d), uq = shfl_up64(q, d);
-				if (lane >= d) {
-					p ^= up;
-					q ^= uq;
-				}
-			}
-			p ^= carryP;
-			q ^= carryQ;
-			const unsigned badmask = __ballot_sync(0xffffffffu, code >= 4 && i < L);
-			const unsigned b = carryB + __popc(badmask & (0xffffffffu >> (31 - lane)));
-			P[i & (kRing - 1)] = p;
-			Q[i & (kRing - 1)] = q;
-			B[i & (kRing - 1)] = b;
-			carryP = shfl64(p, 31);
-			carryQ = shfl64(q, 31);
-			carryB += __popc(badmask);
-			__syncwarp();
-			if (i < L && i + 1 >= k) {
-				const unsigned j = i + 1 - k; // window [j, i]
-				uint64_t pj = 0, qj = 0;
-				unsigned bj = 0;
-				if (j > 0) {
-					pj = P[(j - 1) & (kRing - 1)];
-					qj = Q[(j - 1) & (kRing - 1)];
-					bj = B[(j - 1) & (kRing - 1)];
-				}
-				const uint64_t fh = srol_n(p ^ pj, i);
-				const uint64_t rh = sror_n(q ^ qj, j);
-				h0_out[slot0 + j] = rh < fh ? rh : fh;
-				valid_out[slot0 + j] = (b == bj) ? 1 : 0;
-			}
-			__syncwarp();
-		}
+		hash_one_read(bases, beg, L, slot_offs[r] - slot_base, k, sP[warp], sQ[warp], sB[warp], lane, h0_out, valid_out);
+	}
+}
+
+/** the same over explicit segments (long sequences are cut into overlapping pieces so that every
+ *  warp has work): segment s = bases [seg_beg[s], +seg_len[s]), its first window is slot seg_slot[s] */
+static __global__ void __launch_bounds__(kHashWarps * 32)
+k_hash_segments(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ seg_beg, const unsigned* __restrict__ seg_len,
+                const uint64_t* __restrict__ seg_slot, uint64_t n_segs, unsigned k, uint64_t* __restrict__ h0_out,
+                uint8_t* __restrict__ valid_out)
+{
+	__shared__ uint64_t sP[kHashWarps][kRing];
+	__shared__ uint64_t sQ[kHashWarps][kRing];
+	__shared__ unsigned sB[kHashWarps][kRing];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	for (uint64_t r = (uint64_t)blockIdx.x * kHashWarps + warp; r < n_segs; r += (uint64_t)gridDim.x * kHashWarps) {
+		const unsigned L = seg_len[r];
+		if (L < k)
+			continue;
+		hash_one_read(bases, seg_beg[r], L, seg_slot[r], k, sP[warp], sQ[warp], sB[warp], lane, h0_out, valid_out);
 	}
 }
 
