@@ -146,16 +146,60 @@ struct WarpCtx {
 	}
 	__device__ void fail(unsigned why) { fail_ |= 1u << why; }
 	__device__ bool failed() const { return fail_ != 0; }
-	__device__ void copy8(uint8_t* d, const uint8_t* s, unsigned n) const
+	// cooperative byte copies.  Loads are issued in batches before the dependent stores: a naive
+	// d[i] = s[i] loop pays one DRAM round trip per iteration (no restrict => no load hoisting), which made
+	// splicing and vector growth the dominant cost of a tiled walk.
+	__device__ void copy8(uint8_t* __restrict__ d, const uint8_t* __restrict__ s, unsigned n) const
 	{
-		for (unsigned i = lane; i < n; i += 32)
-			d[i] = s[i];
+		unsigned done = 0;
+		if (n >= 1024 && (((uintptr_t)d | (uintptr_t)s) & 15) == 0) { // big aligned copies (vector growth): 16 B per lane, 4 in flight
+			const uint4* s4 = reinterpret_cast<const uint4*>(s);
+			uint4* d4 = reinterpret_cast<uint4*>(d);
+			const unsigned n16 = n / 16;
+			unsigned i = lane;
+			for (; i + 96 < n16; i += 128) {
+				const uint4 a = s4[i], b = s4[i + 32], c2 = s4[i + 64], e = s4[i + 96];
+				d4[i] = a;
+				d4[i + 32] = b;
+				d4[i + 64] = c2;
+				d4[i + 96] = e;
+			}
+			for (; i < n16; i += 32)
+				d4[i] = s4[i];
+			done = n16 * 16;
+		}
+		for (unsigned base = done; base < n; base += 256) { // 8 bytes per lane in flight
+			uint8_t v[8];
+#pragma unroll
+			for (int j = 0; j < 8; ++j) {
+				const unsigned i = base + lane + 32 * j;
+				v[j] = i < n ? s[i] : 0;
+			}
+#pragma unroll
+			for (int j = 0; j < 8; ++j) {
+				const unsigned i = base + lane + 32 * j;
+				if (i < n)
+					d[i] = v[j];
+			}
+		}
 		__syncwarp();
 	}
-	__device__ void copy8_rev(uint8_t* d, const uint8_t* s, unsigned n) const
+	__device__ void copy8_rev(uint8_t* __restrict__ d, const uint8_t* __restrict__ s, unsigned n) const
 	{
-		for (unsigned i = lane; i < n; i += 32)
-			d[i] = s[n - 1 - i];
+		for (unsigned base = 0; base < n; base += 256) {
+			uint8_t v[8];
+#pragma unroll
+			for (int j = 0; j < 8; ++j) {
+				const unsigned i = base + lane + 32 * j;
+				v[j] = i < n ? s[n - 1 - i] : 0;
+			}
+#pragma unroll
+			for (int j = 0; j < 8; ++j) {
+				const unsigned i = base + lane + 32 * j;
+				if (i < n)
+					d[i] = v[j];
+			}
+		}
 		__syncwarp();
 	}
 	__device__ void rehash(const uint64_t* o, unsigned ocap, uint64_t* nt, unsigned ncap) const
@@ -207,21 +251,30 @@ struct WarpCtx {
 			const U32Vec& tv = side ? o.tiles_right : o.tiles_left;
 			for (unsigned ti = lane; ti < tv.n; ti += 32) { // one lane per tile: 32 independent streams
 				const TileRec* T = tile_recs + tv.p[ti];
-				const uint64_t* th = T->hashes;
+				const uint64_t* __restrict__ th = T->hashes;
 				const unsigned tn = T->n;
-				for (unsigned i = 0; i < tn; ++i) {
-					uint64_t key = th[i];
-					if ((o.popped_front && key == o.front_h) || (o.popped_back && key == o.back_h))
-						continue;
-					key = key ? key : 1;
-					for (uint64_t t = pathset_slot(key, cap);; t = (t + 1) & (cap - 1)) {
-						const uint64_t v = keys[t];
-						if (v == key) {
-							hit[t] = 1;
+				for (unsigned i0 = 0; i0 < tn; i0 += 8) {
+					uint64_t kv[8];
+#pragma unroll
+					for (int j = 0; j < 8; ++j) // 8 independent loads before any probe
+						kv[j] = i0 + j < tn ? th[i0 + j] : 0;
+#pragma unroll
+					for (int j = 0; j < 8; ++j) {
+						uint64_t key = kv[j];
+						if (i0 + j >= tn)
 							break;
+						if ((o.popped_front && key == o.front_h) || (o.popped_back && key == o.back_h))
+							continue;
+						key = key ? key : 1;
+						for (uint64_t t = pathset_slot(key, cap);; t = (t + 1) & (cap - 1)) {
+							const uint64_t v = keys[t];
+							if (v == key) {
+								hit[t] = 1;
+								break;
+							}
+							if (v == 0)
+								break;
 						}
-						if (v == 0)
-							break;
 					}
 				}
 			}
@@ -571,11 +624,13 @@ k_make_tiles(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ off
 }
 
 /** a canonical hash occurring twice in one (untrimmed) path means the tile splice skipped an
- *  ER_CYCLE: flag the contig.  key = hash mixed with the contig index; a clash between different
- *  (hash, contig) pairs only causes a harmless extra fallback. */
+ *  ER_CYCLE: flag the contig.  Every contig has its own open-addressing region
+ *  [tab_off[c], tab_off[c+1]) keyed by the full 64-bit canonical hash, so a hit is a genuine repeat
+ *  (a false alarm would cost a vertex-by-vertex walk of a possibly Mbp-long unitig). */
 __global__ void __launch_bounds__(256)
 k_repeat_check(const ContigRec* __restrict__ recs, unsigned n_contigs, const uint64_t* __restrict__ cslot,
-               const uint64_t* __restrict__ ch0, unsigned long long* tab, uint64_t tab_mask, uint8_t* __restrict__ flag)
+               const uint64_t* __restrict__ ch0, unsigned long long* tab, const uint64_t* __restrict__ tab_off,
+               uint8_t* __restrict__ flag)
 {
 	const uint64_t total = cslot[n_contigs];
 	for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < total + 2ULL * n_contigs;
@@ -613,15 +668,19 @@ k_repeat_check(const ContigRec* __restrict__ recs, unsigned n_contigs, const uin
 				h = recs[c].front_h;
 			}
 		}
-		unsigned long long key = (h ^ (0x9E3779B97F4A7C15ULL * (c + 1))) | 1ULL;
-		for (uint64_t t = (key * 0xD6E8FEB86659FD93ULL >> 20) & tab_mask;; t = (t + 1) & tab_mask) {
-			const unsigned long long old = atomicCAS(tab + t, 0ULL, key);
+		const unsigned long long key = h ? h : 1ULL; // 0 marks an empty slot
+		const uint64_t base = tab_off[c], size = tab_off[c + 1] - base;
+		uint64_t t = __umul64hi(key * 0xD6E8FEB86659FD93ULL, size);
+		for (;;) {
+			const unsigned long long old = atomicCAS(tab + base + t, 0ULL, key);
 			if (old == 0ULL)
 				break;
 			if (old == key) {
 				flag[c] = 1;
 				break;
 			}
+			if (++t == size)
+				t = 0;
 		}
 	}
 }
@@ -899,7 +958,7 @@ struct abb_assembler {
 	DevBuf<uint8_t> bases, valid, codes, vis, scan_tmp, cseq, cvalid, rcode, caccept;
 	DevBuf<uint64_t> offs, slot_offs, h0, coffs, cslot, ch0;
 	DevBuf<unsigned> cand, spec, spec_cbeg, clen, ccov, status, seg_contig, seg_len;
-	DevBuf<uint64_t> seg_beg, seg_slot;
+	DevBuf<uint64_t> seg_beg, seg_slot, rep_off;
 	DevBuf<ContigRec> recs, recs_sorted;
 	DevBuf<Frame> frames;
 	DevBuf<uint64_t> look;
@@ -933,7 +992,8 @@ struct abb_assembler {
 	float ms_tiles = 0, ms_walk = 0, ms_stage = 0, ms_repeat = 0;
 
 	// speculation control
-	unsigned spec_target = 256;
+	unsigned spec_target = 512;
+	unsigned spec_fixed = 0;
 	// host outputs of the last batch
 	std::vector<abb_contig> out_contigs;
 	std::vector<char> out_seqs;
@@ -960,8 +1020,8 @@ struct PhaseTimer { // CUDA-event time of a phase on the assembler stream
 	}
 };
 
-constexpr unsigned kMaxSpec = 2048;  // about one resident wave of walking warps on 148 SMs
-constexpr unsigned kMinSpec = 64;
+constexpr unsigned kMaxSpec = 1024;
+constexpr unsigned kMinSpec = 256;   // with tiles a round costs about the same latency for 64 or 1024 walkers, and wasted walks are cheap
 constexpr unsigned long long kArenaDefault = 4ULL << 30;
 static unsigned long long g_arena_hint = 0; // the arena size the previous assembler of this process ended up needing
 constexpr unsigned long long kArenaMax = 96ULL << 30;
@@ -1358,15 +1418,17 @@ int speculate_round(abb_assembler* a, const std::vector<unsigned>& cand, size_t*
 			ABB_CHECK(stage_contigs(a, recs, L));
 			const unsigned nc = (unsigned)recs.size();
 			if (nc) {
-				uint64_t tab = 1024;
-				while (tab < (L.cslot[nc] + 2ull * nc) * 2)
-					tab <<= 1;
+				std::vector<uint64_t> tab_off(nc + 1, 0);
+				for (unsigned c = 0; c < nc; ++c)
+					tab_off[c + 1] = tab_off[c] + 2 * (L.cslot[c + 1] - L.cslot[c]) + 8;
+				const uint64_t tab = tab_off[nc];
+				ABB_CHECK(h2d(a->rep_off, tab_off, st));
 				ABB_CHECK(a->rep_tab.reserve(tab));
 				ABB_CHECK(a->rep_flag.reserve(nc));
 				cudaEventRecord(a->ev2[0], st);
 				ABB_CUDA(cudaMemsetAsync(a->rep_tab.p, 0, tab * sizeof(unsigned long long), st));
 				ABB_CUDA(cudaMemsetAsync(a->rep_flag.p, 0, nc, st));
-				k_repeat_check<<<148 * 8, 256, 0, st>>>(a->recs_sorted.p, nc, a->cslot.p, a->ch0.p, a->rep_tab.p, tab - 1, a->rep_flag.p);
+				k_repeat_check<<<148 * 8, 256, 0, st>>>(a->recs_sorted.p, nc, a->cslot.p, a->ch0.p, a->rep_tab.p, a->rep_off.p, a->rep_flag.p);
 				ABB_CUDA(cudaGetLastError());
 				cudaEventRecord(a->ev2[1], st);
 				++a->st_launches;
@@ -1492,8 +1554,12 @@ int speculate_round(abb_assembler* a, const std::vector<unsigned>& cand, size_t*
 		if (nc) {
 			ABB_CUDA(cudaMemcpyAsync(caccept.data(), a->caccept.p, nc, cudaMemcpyDeviceToHost, st));
 			ABB_CUDA(cudaMemcpyAsync(ccov.data(), a->ccov.p, nc * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-			ABB_CUDA(cudaMemcpyAsync(seqs.data(), a->cseq.p, coffs[nc], cudaMemcpyDeviceToHost, st));
 		}
+		ABB_CUDA(cudaStreamSynchronize(st));
+		// only the unitigs that were printed travel back to the host
+		for (unsigned c = 0; c < nc; ++c)
+			if (caccept[c])
+				ABB_CUDA(cudaMemcpyAsync(seqs.data() + coffs[c], a->cseq.p + coffs[c], clen[c], cudaMemcpyDeviceToHost, st));
 		ABB_CUDA(cudaStreamSynchronize(st));
 		tr.stop();
 	}
@@ -1524,10 +1590,10 @@ int speculate_round(abb_assembler* a, const std::vector<unsigned>& cand, size_t*
 	}
 	a->st_wasted += wasted;
 	// adapt the amount of speculation: grow while most speculated reads were really needed
-	if (n_ok == n_spec) {
-		if (wasted * 4 <= n_ok)
+	if (n_ok == n_spec && !a->spec_fixed) {
+		if (wasted * 2 <= n_ok)
 			a->spec_target = std::min(kMaxSpec, a->spec_target * 2);
-		else if (wasted * 2 > n_ok)
+		else if (wasted * 20 > n_ok * 19)
 			a->spec_target = std::max(kMinSpec, a->spec_target / 2);
 	}
 	(void)n_reads;
@@ -1563,6 +1629,8 @@ int abb_assembler_create(abb_assembler** out, abb_filter* solid, const abb_assem
 		a->params.trim = solid->k; // bloom-dbg.cc:518-520
 	a->kw = (int)((2 * solid->k + 63) / 64);
 	a->tiles_on = getenv("ABB_NO_TILES") == nullptr; // debugging switch: vertex-by-vertex walks only
+	if (const char* sp = getenv("ABB_SPEC")) // tuning switch: fixed speculation width
+		a->spec_fixed = a->spec_target = (unsigned)std::max(1, atoi(sp));
 	// BloomFilter assembledKmerSet(solid.size(), solid.getHashNum(), solid.getKmerSize()) (bloom-dbg.h:910-911)
 	int rc = abb_filter_create(&a->assembled, ABB_BIT, solid->size, solid->H, solid->k, 0, "", solid->device);
 	if (rc != ABB_OK) {
@@ -1608,6 +1676,7 @@ int abb_assembler_destroy(abb_assembler* a)
 	cudaFree(a->d_tile_pool);
 	cudaFree(a->d_tile_pool_top);
 	cudaFree(a->d_marker_set);
+	a->rep_off.release();
 	a->seg_contig.release(); a->seg_len.release(); a->seg_beg.release(); a->seg_slot.release();
 	a->new_markers.release(); a->rep_tab.release(); a->stage_bases.release(); a->rep_flag.release(); a->stage_hashes.release();
 	cudaFree(a->d_arena);

@@ -161,6 +161,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reads", type=int, default=N_READS, help="number of reads of the workload (default: the BASELINE config)")
     ap.add_argument("--ref-reads", type=int, default=2_000_000, help="bounded CPU sample (reads)")
+    ap.add_argument("--window", type=int, default=0, help="ordered-insert window in k-mer slots (0 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -206,6 +207,8 @@ def main():
 
     filt = capi.Filter.counting(counters, H, K, KC, device=local_rank)
     filt.set_profiling(True)
+    if args.window:
+        filt.set_window(args.window)
     ext = torch.cuda.ExternalStream(filt.stream(), device=dev)
 
     # N > 1: pass 1 is sharded by k-mer hash range (all-to-all of hashes, ordered insert of the owned
