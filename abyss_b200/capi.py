@@ -89,6 +89,7 @@ SIGNATURES = {
     "abb_assembler_process_reads": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.POINTER(C.POINTER(Contig)), _u64p, C.POINTER(C.c_char_p)]),
     "abb_assembler_process_reads_dev": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.POINTER(C.POINTER(Contig)), _u64p, C.POINTER(C.c_char_p)]),
     "abb_assembler_stats": (C.c_int, [_vp, C.POINTER(AssemblyStats)]),
+    "abb_assembler_reset": (C.c_int, [_vp]),
     "abb_assembler_counters": (C.c_int, [_vp, C.POINTER(AssemblyCounters)]),
     "abb_assembler_read_results": (C.c_int, [_vp, C.POINTER(_u8p), _u64p]),
     "abb_assembler_assembled_filter": (_vp, [_vp]),
@@ -304,6 +305,7 @@ class Assembler:
         self._lib = load()
         self._solid = solid  # keep alive
         self._h = _vp()
+        self.raw_results = False
         p = AssemblyParams(0xFFFFFFFF if trim is None else trim, verbose, int(read_log), 0)
         check(self._lib.abb_assembler_create(C.byref(self._h), solid.handle, C.byref(p)))
 
@@ -326,6 +328,9 @@ class Assembler:
     def process_reads_dev(self, d_bases_ptr: int, d_offs_ptr: int, n_reads: int):
         return self._run(self._lib.abb_assembler_process_reads_dev, _vp(d_bases_ptr), _vp(d_offs_ptr), n_reads)
 
+    def reset(self):
+        check(self._lib.abb_assembler_reset(self._h))
+
     def stats(self) -> AssemblyStats:
         st = AssemblyStats()
         check(self._lib.abb_assembler_stats(self._h, C.byref(st)))
@@ -336,6 +341,9 @@ class Assembler:
         n = C.c_uint64(0)
         seqs = C.c_char_p()
         check(fn(self._h, bases_p, offs_p, n_reads, C.byref(contigs), C.byref(n), C.byref(seqs)))
+        self.last_n_contigs = n.value
+        if self.raw_results:  # (seed_read, length, coverage) only; sequences stay in the library buffer
+            return [(contigs[i].seed_read, contigs[i].length, contigs[i].coverage) for i in range(n.value)]
         out = []
         if n.value:
             base = C.cast(seqs, C.c_void_p).value

@@ -1810,6 +1810,36 @@ int abb_assembler_stats(const abb_assembler* a, abb_assembly_stats* out)
 	return ABB_OK;
 }
 
+int abb_assembler_reset(abb_assembler* a)
+{
+	ABB_REQUIRE(a, "NULL assembler");
+	ABB_CUDA(cudaSetDevice(a->solid->device));
+	cudaStream_t st = a->stream;
+	ABB_CUDA(cudaStreamSynchronize(st));
+	ABB_CHECK(abb_filter_clear(a->assembled));
+	if (a->d_ends)
+		ABB_CUDA(cudaMemsetAsync(a->d_ends, 0, (size_t)a->ends_cap * sizeof(unsigned long long), st));
+	ABB_CUDA(cudaMemsetAsync(a->d_ends_n, 0, 2 * sizeof(unsigned), st));
+	a->ends_upper = 0;
+	if (a->d_tile_tab) { // the tiles describe the old contents of the solid filter: forget them, keep the memory
+		ABB_CUDA(cudaMemsetAsync(a->d_tile_tab, 0, ((size_t)a->tile_tab_mask + 1) * sizeof(unsigned), st));
+		ABB_CUDA(cudaMemsetAsync(a->d_marker_set, 0, ((size_t)a->marker_set_mask + 1) * sizeof(unsigned long long), st));
+		ABB_CUDA(cudaMemsetAsync(a->d_tile_n, 0, 4 * sizeof(unsigned), st));
+		ABB_CUDA(cudaMemsetAsync(a->d_tile_pool_top, 0, sizeof(unsigned long long), st));
+	}
+	ABB_CUDA(cudaStreamSynchronize(st));
+	a->counters = abb_assembly_counters{};
+	a->reads_seen = 0;
+	a->spec_target = a->spec_fixed ? a->spec_fixed : 512;
+	a->st_iterations = a->st_speculated = a->st_wasted = a->st_launches = a->st_candidates = a->st_contigs_tried = 0;
+	a->st_markers = a->st_tiles = a->st_fallbacks = 0;
+	a->ms_classify = a->ms_visited = a->ms_extend = a->ms_replay = a->ms_tiles = a->ms_walk = a->ms_stage = a->ms_repeat = 0;
+	a->out_contigs.clear();
+	a->out_seqs.clear();
+	a->out_codes.clear();
+	return ABB_OK;
+}
+
 int abb_assembler_counters(const abb_assembler* a, abb_assembly_counters* out)
 {
 	ABB_REQUIRE(a && out, "NULL argument");

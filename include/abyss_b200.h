@@ -158,6 +158,9 @@ int abb_assembler_process_reads(abb_assembler* a, const char* bases, const uint6
 int abb_assembler_process_reads_dev(abb_assembler* a, const char* d_bases, const uint64_t* d_offsets,
                                     uint64_t n_reads, const abb_contig** contigs, uint64_t* n_contigs,
                                     const char** seqs);
+/* Start a new assembly on the same handle (the solid filter has been refilled): clears the assembled
+ * filter, the contig-end table, the tile store, counters and statistics, keeps all device buffers. */
+int abb_assembler_reset(abb_assembler* a);
 int abb_assembler_counters(const abb_assembler* a, abb_assembly_counters* out);
 /* optional per-read outcome log of the last batch (ReadResult, bloom-dbg.h:256-293);
  * codes: 0 SHORTER_THAN_K, 1 NON_ACGT, 2 BLUNT_END, 3 NOT_SOLID, 4 ALL_KMERS_VISITED,

@@ -82,3 +82,21 @@ def test_tiles_on_off_same_output(abb, golden_dir, monkeypatch):
     monkeypatch.setenv("ABB_NO_TILES", "1")
     off, _ = bloom_dbg(ids, reads, c["k"], c["kc"], c["H"], counters=c["counters"])
     assert on == off == open(os.path.join(golden_dir, "e2e_g20k_k32.fa")).read()
+
+
+def test_assembler_reset_reuses_handle(abb, golden_dir):
+    # abb_assembler_reset: a second assembly on the same handles gives the same bytes
+    from abyss_b200.capi import fixed_length_reads, Filter, Assembler
+    c, rs = load_case(golden_dir, "e2e_g20k_k32")
+    reads = fixed_length_reads(rs.ascii(0, rs.n))
+    f = Filter.counting(c["counters"], c["H"], c["k"], c["kc"])
+    a = Assembler(f)
+    outs = []
+    for _ in range(2):
+        f.clear()
+        a.reset()
+        f.insert_reads(reads)
+        outs.append("".join(f">{i} {len(s)} {cv} read:{rs.read_id(r)}\n{s}\n" for i, (r, s, cv) in enumerate(a.process_reads(reads))))
+    a.close()
+    f.close()
+    assert outs[0] == outs[1] == open(os.path.join(golden_dir, "e2e_g20k_k32.fa")).read()
