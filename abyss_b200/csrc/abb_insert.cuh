@@ -95,6 +95,21 @@ ABB_D uint64_t tag_owner(const TagTable& t, unsigned epoch, uint64_t pos)
 	}
 }
 
+/** like tag_owner, also reporting where the entry lives so that the release needs no second probe */
+ABB_D uint64_t tag_owner_at(const TagTable& t, unsigned epoch, uint64_t pos, uint64_t* where)
+{
+	const uint64_t key = tag_pack(epoch, pos, 0) >> kSlotBits;
+	uint64_t s = tag_home(pos, t);
+	for (;;) {
+		unsigned long long cur = __ldcg(&t.e[s]);
+		if ((cur >> kSlotBits) == key) {
+			*where = s;
+			return cur & kSlotMask;
+		}
+		s = (s + 1) & t.mask;
+	}
+}
+
 /** the owner is done with pos: later slots may now win it (slot field := kSlotMask) */
 ABB_D void tag_release(const TagTable& t, unsigned epoch, uint64_t pos)
 {
@@ -381,7 +396,9 @@ k_reserve(const uint64_t* __restrict__ hashes, const uint8_t* __restrict__ valid
 			tag_reserve(tab, epoch, pos[i], t);
 }
 
-/** K2b: owners apply and release, everybody else is deferred */
+/** K2b: owners apply and release, everybody else is deferred.
+ *  The counter loads are issued before the ownership probes (they are wasted only for the <1 % of
+ *  slots that lose a reservation) so that the HBM round trip overlaps the L2 round trip. */
 template <int KIND, bool LITERAL, int MAXH>
 __global__ void __launch_bounds__(256)
 k_commit(const uint64_t* __restrict__ hashes, const uint8_t* __restrict__ valid, uint64_t w0,
@@ -396,17 +413,39 @@ k_commit(const uint64_t* __restrict__ hashes, const uint8_t* __restrict__ valid,
 		return;
 	uint64_t pos[MAXH];
 	slot_positions<LITERAL, MAXH>(hashes, s, cfg, pos);
-	bool owner = true;
-#pragma unroll
-	for (int i = 0; i < MAXH; ++i)
-		if (i < (int)cfg.H)
-			owner &= tag_owner(tab, epoch, pos[i]) == t;
-	if (owner) {
-		apply_owner<KIND, MAXH>(f, pos, cfg.H);
+	unsigned v[MAXH];
+	if (KIND == 0) {
 #pragma unroll
 		for (int i = 0; i < MAXH; ++i)
 			if (i < (int)cfg.H)
-				tag_release(tab, epoch, pos[i]);
+				v[i] = __ldcg(f.data + pos[i]);
+	}
+	bool owner = true;
+	uint64_t where[MAXH];
+#pragma unroll
+	for (int i = 0; i < MAXH; ++i)
+		if (i < (int)cfg.H)
+			owner &= tag_owner_at(tab, epoch, pos[i], &where[i]) == t;
+	if (owner) {
+		if (KIND == 0) {
+			// CountingBloomFilter::incrementMin by the single owner (CountingBloomFilter.hpp:138-162)
+			unsigned mn = 255;
+#pragma unroll
+			for (int i = 0; i < MAXH; ++i)
+				if (i < (int)cfg.H)
+					mn = min(mn, v[i]);
+			if (mn != 255) {
+#pragma unroll
+				for (int i = 0; i < MAXH; ++i)
+					if (i < (int)cfg.H && v[i] == mn)
+						__stcg(f.data + pos[i], (uint8_t)(mn + 1));
+			}
+		} else
+			apply_owner<KIND, MAXH>(f, pos, cfg.H);
+#pragma unroll
+		for (int i = 0; i < MAXH; ++i)
+			if (i < (int)cfg.H)
+				__stcg(&tab.e[where[i]], (unsigned long long)tag_pack(epoch, pos[i], kSlotMask));
 	} else
 		deferred[atomicAdd(n_deferred, 1u)] = t;
 }
