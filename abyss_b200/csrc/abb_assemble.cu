@@ -23,7 +23,10 @@
 // reference would have, while the expensive graph walks run thousands at a time.
 #include "abb_common.h"
 #include "abb_walk.cuh"
+#include <cub/device/device_select.cuh>
+#include <thrust/iterator/counting_iterator.h>
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -339,6 +342,11 @@ struct DevEmit {
 		}
 		++ordinal;
 	}
+};
+
+struct IsCandidate {
+	const uint8_t* codes;
+	__host__ __device__ bool operator()(unsigned r) const { return codes[r] == RC_CANDIDATE; }
 };
 
 struct WalkCfg {
@@ -989,7 +997,7 @@ struct abb_assembler {
 	DevBuf<uint8_t> stage_bases, rep_flag;
 	DevBuf<uint64_t> stage_hashes;
 	uint64_t st_markers = 0, st_tiles = 0, st_fallbacks = 0;
-	float ms_tiles = 0, ms_walk = 0, ms_stage = 0, ms_repeat = 0;
+	float ms_tiles = 0, ms_walk = 0, ms_stage = 0, ms_repeat = 0, ms_total = 0, ms_cand = 0;
 
 	// speculation control
 	unsigned spec_target = 512;
@@ -1502,7 +1510,8 @@ int speculate_round(abb_assembler* a, const std::vector<unsigned>& cand, size_t*
 	const std::vector<uint64_t>& coffs = L.coffs;
 	std::vector<uint8_t> rcode(n_ok), caccept(nc);
 	std::vector<unsigned> ccov(nc);
-	std::vector<char> seqs(coffs[nc]);
+	std::vector<uint64_t> hoff(nc + 1, 0); // where each accepted unitig lands in `seqs`
+	std::vector<char> seqs;
 	a->st_contigs_tried += nc;
 	{
 		PhaseTimer tr(a, &a->ms_replay);
@@ -1558,8 +1567,11 @@ int speculate_round(abb_assembler* a, const std::vector<unsigned>& cand, size_t*
 		ABB_CUDA(cudaStreamSynchronize(st));
 		// only the unitigs that were printed travel back to the host
 		for (unsigned c = 0; c < nc; ++c)
+			hoff[c + 1] = hoff[c] + (caccept[c] ? clen[c] : 0);
+		seqs.resize(hoff[nc]);
+		for (unsigned c = 0; c < nc; ++c)
 			if (caccept[c])
-				ABB_CUDA(cudaMemcpyAsync(seqs.data() + coffs[c], a->cseq.p + coffs[c], clen[c], cudaMemcpyDeviceToHost, st));
+				ABB_CUDA(cudaMemcpyAsync(seqs.data() + hoff[c], a->cseq.p + coffs[c], clen[c], cudaMemcpyDeviceToHost, st));
 		ABB_CUDA(cudaStreamSynchronize(st));
 		tr.stop();
 	}
@@ -1582,7 +1594,7 @@ int speculate_round(abb_assembler* a, const std::vector<unsigned>& cand, size_t*
 			oc.length = clen[c];
 			oc.coverage = ccov[c];
 			a->out_contigs.push_back(oc);
-			a->out_seqs.insert(a->out_seqs.end(), seqs.begin() + coffs[c], seqs.begin() + coffs[c] + clen[c]);
+			a->out_seqs.insert(a->out_seqs.end(), seqs.begin() + hoff[c], seqs.begin() + hoff[c] + clen[c]);
 			a->out_seqs.push_back('\0');
 			++a->counters.contig_id;
 			a->counters.bases_assembled += clen[c];
@@ -1695,6 +1707,12 @@ int abb_assembler_destroy(abb_assembler* a)
 static int process_batch(abb_assembler* a, const uint8_t* d_bases, const uint64_t* d_offs, uint64_t n_reads,
                          const abb_contig** contigs, uint64_t* n_contigs, const char** seqs)
 {
+	const auto t_begin = std::chrono::steady_clock::now();
+	struct Total {
+		abb_assembler* a;
+		std::chrono::steady_clock::time_point t0;
+		~Total() { a->ms_total += std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+	} total_guard{ a, t_begin };
 	abb_filter* f = a->solid;
 	cudaStream_t st = a->stream;
 	a->cur_bases = d_bases;
@@ -1722,13 +1740,28 @@ static int process_batch(abb_assembler* a, const uint8_t* d_bases, const uint64_
 	ABB_CUDA(cudaStreamSynchronize(st));
 	tc.stop();
 
+	const auto t_cand = std::chrono::steady_clock::now();
+	// candidate list = indices of the reads classified RC_CANDIDATE, compacted on the device
 	std::vector<unsigned> cand;
-	for (uint64_t r = 0; r < n_reads; ++r)
-		if (a->out_codes[r] == RC_CANDIDATE)
-			cand.push_back((unsigned)r);
+	{
+		ABB_CHECK(a->cand.reserve(n_reads + 1));
+		IsCandidate pred{ a->codes.p };
+		thrust::counting_iterator<unsigned> first(0);
+		size_t bytes = 0;
+		ABB_CUDA(cub::DeviceSelect::If(nullptr, bytes, first, a->cand.p, a->d_nrecs, (int)n_reads, pred, st));
+		ABB_CHECK(a->scan_tmp.reserve(bytes));
+		ABB_CUDA(cub::DeviceSelect::If(a->scan_tmp.p, bytes, first, a->cand.p, a->d_nrecs, (int)n_reads, pred, st));
+		unsigned nc = 0;
+		ABB_CUDA(cudaMemcpyAsync(&nc, a->d_nrecs, sizeof nc, cudaMemcpyDeviceToHost, st));
+		ABB_CUDA(cudaStreamSynchronize(st));
+		cand.resize(nc);
+		if (nc)
+			ABB_CUDA(cudaMemcpyAsync(cand.data(), a->cand.p, (size_t)nc * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+		ABB_CUDA(cudaStreamSynchronize(st));
+	}
+	a->ms_cand += std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_cand).count();
 	a->counters.solid_reads += cand.size();
 	a->st_candidates += cand.size();
-	ABB_CHECK(h2d(a->cand, cand, st));
 	if (!cand.empty())
 		ABB_CHECK(produce_tiles(a, n_reads, total));
 
@@ -1753,7 +1786,7 @@ static int begin_batch(abb_assembler* a, uint64_t n_reads, const abb_contig** co
 	if (contigs) *contigs = nullptr;
 	if (n_contigs) *n_contigs = 0;
 	if (seqs) *seqs = nullptr;
-	ABB_REQUIRE(n_reads < (1ULL << 32), "at most 2^32-1 reads per batch");
+	ABB_REQUIRE(n_reads < (1ULL << 31), "at most 2^31-1 reads per batch");
 	ABB_CUDA(cudaSetDevice(a->solid->device));
 	// the filters may have been written on their own streams
 	ABB_CUDA(cudaStreamSynchronize(a->solid->stream));
@@ -1802,6 +1835,8 @@ int abb_assembler_stats(const abb_assembler* a, abb_assembly_stats* out)
 	out->ms_replay = a->ms_replay;
 	out->ms_tiles = a->ms_tiles;
 	out->ms_walk = a->ms_walk;
+	out->ms_total = a->ms_total;
+	out->ms_cand = a->ms_cand;
 	out->ms_stage = a->ms_stage;
 	out->ms_repeat = a->ms_repeat;
 	out->markers = a->st_markers;
@@ -1833,7 +1868,7 @@ int abb_assembler_reset(abb_assembler* a)
 	a->spec_target = a->spec_fixed ? a->spec_fixed : 512;
 	a->st_iterations = a->st_speculated = a->st_wasted = a->st_launches = a->st_candidates = a->st_contigs_tried = 0;
 	a->st_markers = a->st_tiles = a->st_fallbacks = 0;
-	a->ms_classify = a->ms_visited = a->ms_extend = a->ms_replay = a->ms_tiles = a->ms_walk = a->ms_stage = a->ms_repeat = 0;
+	a->ms_classify = a->ms_visited = a->ms_extend = a->ms_replay = a->ms_tiles = a->ms_walk = a->ms_stage = a->ms_repeat = a->ms_total = a->ms_cand = 0;
 	a->out_contigs.clear();
 	a->out_seqs.clear();
 	a->out_codes.clear();

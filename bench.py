@@ -324,7 +324,8 @@ def main():
         "gpu_launches": int(ist.launches + ast.launches), "roofline": roofline, "cpu_baseline": cpu,
         "phases_ms": {"hash": ist.ms_hash, "insert": ist.ms_insert, "classify": ast.ms_classify, "visited": ast.ms_visited,
                       "tiles": ast.ms_tiles, "extend": ast.ms_extend, "extend_walk": ast.ms_walk, "extend_stage": ast.ms_stage,
-                      "extend_repeat_check": ast.ms_repeat, "replay": ast.ms_replay},
+                      "extend_repeat_check": ast.ms_repeat, "replay": ast.ms_replay, "pass2_wall": ast.ms_total,
+                      "candidate_list_host": ast.ms_cand},
         "pass1_ms": ist.ms_pass1, "insert_kmers_per_s": nk / (ist.ms_pass1 * 1e-3),
         "extend_kmers_per_s": nk / ((ast.ms_classify + ast.ms_tiles + ast.ms_visited + ast.ms_extend + ast.ms_replay) * 1e-3),
         "unitigs": int(cnt.contig_id), "bases_assembled": int(cnt.bases_assembled),

@@ -179,6 +179,7 @@ typedef struct abb_assembly_stats {
 	float ms_classify, ms_visited, ms_extend, ms_replay; /* CUDA-event time per phase */
 	float ms_tiles;             /* marker enumeration + tile production */
 	float ms_walk, ms_stage, ms_repeat; /* inside ms_extend: K4 kernels, unitig gather+hash, repeat check */
+	float ms_total, ms_cand;    /* host wall clock of the process_reads calls / of building the candidate list */
 	uint64_t markers, tiles;    /* marker vertices found / marker-to-marker tiles stored */
 	uint64_t serial_fallbacks;  /* reads re-walked vertex by vertex after the repeat check */
 } abb_assembly_stats;
