@@ -73,6 +73,12 @@ struct WarpCtx {
 		}
 	}
 	__device__ uint32_t tile_index(const TileRec* t) const { return (uint32_t)(t - tile_recs); }
+	__device__ const TileRec* tile_at(uint32_t idx) const { return tile_recs + idx; }
+	__device__ void prefetch(const void* p) const
+	{
+		if (p)
+			asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+	}
 	__device__ void wr32(uint32_t* p, uint32_t v) const { *(volatile uint32_t*)p = v; }
 
 	/** bits 0-3: out-neighbours (append A,C,G,T) present in the solid filter; bits 4-7: in-neighbours
@@ -109,6 +115,26 @@ struct WarpCtx {
 	__device__ unsigned neighbors(const Vtx<KW>& v) const
 	{
 		return neighbors_finish(neighbors_issue(v));
+	}
+	/** neighbours in one direction only: 16 of the 32 lanes probe (lookAhead never turns around) */
+	template <int KW>
+	__device__ unsigned neighbors_dir(const Vtx<KW>& v, Dir d) const
+	{
+		const unsigned n = lane >> 2, hs = lane & 3;
+		const bool mine = (n < 4) == (d == FWD);
+		bool ok = true;
+		if (mine) {
+			const HashPair h = n < 4 ? roll_right(v.h, rt, kmer_first(v.km, k), n) : roll_left(v.h, rt, kmer_last(v.km), n - 4);
+			const uint64_t h0 = h.canonical();
+			unsigned mn = 255;
+			for (unsigned i = hs; i < cfg->H; i += 4)
+				mn = min(mn, (unsigned)__ldcg(counters + nth_pos(h0, *cfg, i)));
+			ok = mn >= threshold;
+		}
+		Probe p;
+		p.ok = ok;
+		const unsigned m = neighbors_finish(p);
+		return d == FWD ? (m & 15) : (m >> 4);
 	}
 	// scratch accesses: every lane stores the same value to the same address and reads back its own
 	// store, so no intra-warp synchronisation is needed for uniform data
@@ -626,6 +652,30 @@ k_make_tiles(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ off
 				const TileRec* o = ts.recs + (old - 1);
 				if (o->key == t.key && o->cls == t.cls)
 					break; // palindromic marker: the same (key, class) twice, keep the first
+			}
+		}
+	}
+}
+
+/** resolve TileRec::next for every tile that ended on a marker (tiles of later batches link to earlier ones
+ *  and vice versa, so this runs over the whole store after each production) */
+__global__ void __launch_bounds__(256)
+k_link_tiles(TileRec* recs, unsigned n, const unsigned* __restrict__ tab, unsigned mask)
+{
+	for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		TileRec* t = recs + i;
+		if (t->next || t->stop_kind != TS_MARKER || t->n == 0)
+			continue;
+		const uint64_t key = t->end_key;
+		const unsigned cls = ((unsigned)t->end_orient << 1) | (t->cls & 1u);
+		for (uint64_t s = tile_slot(key, cls, mask);; s = (s + 1) & mask) {
+			const unsigned v = tab[s];
+			if (v == 0)
+				break;
+			const TileRec* o = recs + (v - 1);
+			if (o->key == key && o->cls == cls) {
+				t->next = v;
+				break;
 			}
 		}
 	}
@@ -1201,6 +1251,9 @@ int produce_tiles(abb_assembler* a, uint64_t n_reads, uint64_t n_slots)
 	ABB_CUDA(cudaStreamSynchronize(st));
 	a->st_markers += nm;
 	a->st_tiles = std::min(nt, a->tile_cap);
+	k_link_tiles<<<148 * 8, 256, 0, st>>>(a->d_tiles, (unsigned)a->st_tiles, a->d_tile_tab, a->tile_tab_mask);
+	ABB_CUDA(cudaGetLastError());
+	a->st_launches += 1;
 	tt.stop();
 	return ABB_OK;
 }

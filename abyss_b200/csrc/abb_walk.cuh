@@ -215,6 +215,7 @@ ABB_HD unsigned ctz4(unsigned m) { return (m & 1) ? 0 : (m & 2) ? 1 : (m & 4) ? 
  *   unsigned k, trim; RollTab rt;
  *   template<int KW> unsigned neighbors(const Vtx<KW>&)   bits 0-3: out-neighbours A,C,G,T exist; 4-7: in-neighbours
  *   Probe neighbors_issue(v) / unsigned neighbors_finish(Probe)   the same, split so that other loads can be in flight
+ *   unsigned neighbors_dir(v, dir)   4-bit mask of the neighbours in one direction only (half the probes; lookAhead)
  *   uint64_t rd64(const uint64_t*), void wr64(uint64_t*, uint64_t), uint8_t rd8(const uint8_t*), void wr8(uint8_t*, uint8_t)
  *   void sync()                      make lane-0 writes visible to the warp
  *   bool find64(const uint64_t* a, unsigned n, uint64_t key, unsigned stride_words)   cooperative linear search
@@ -222,7 +223,8 @@ ABB_HD unsigned ctz4(unsigned m) { return (m & 1) ? 0 : (m & 2) ? 1 : (m & 4) ? 
  *   void fail(unsigned why), bool failed()   record an overflow; the walk of this read is abandoned and retried by the host
  *   void copy8(dst, src, n), copy8_rev(dst, src, n)   cooperative byte copies (rev: dst[i] = src[n-1-i])
  *   void rehash(old, oldcap, new, newcap)              cooperative PathSet growth
- *   bool tiles_enabled(); const TileRec* tile_lookup(key, cls); uint32_t tile_index(const TileRec*); void wr32(uint32_t*, uint32_t)
+ *   bool tiles_enabled(); const TileRec* tile_lookup(key, cls); const TileRec* tile_at(idx); void prefetch(const void*);
+ *   uint32_t tile_index(const TileRec*); void wr32(uint32_t*, uint32_t)
  *   void mark_covered(ps, rh, cov, nk, contig)         cooperative: flag read k-mers that lie on the contig path
  *   Frame* frames; uint64_t* look;   per-warp scratch
  */
@@ -242,8 +244,7 @@ ABB_HD bool look_ahead(Ctx& c, const Vtx<KW>& start, Dir dir, unsigned limit)
 	unsigned masks[8], dropped[8];
 	unsigned sp = 0;
 	{
-		const unsigned m = c.neighbors(cur);
-		masks[0] = dir == FWD ? (m & 15) : (m >> 4);
+		masks[0] = c.neighbors_dir(cur, dir);
 		dropped[0] = 0;
 		sp = 1;
 	}
@@ -272,9 +273,8 @@ ABB_HD bool look_ahead(Ctx& c, const Vtx<KW>& start, Dir dir, unsigned limit)
 		c.sync();
 		if (sp >= limit) // depth of cur == sp
 			return true;
-		const unsigned nm = c.neighbors(cur);
 		dropped[sp] = out;
-		masks[sp] = dir == FWD ? (nm & 15) : (nm >> 4);
+		masks[sp] = c.neighbors_dir(cur, dir);
 		++sp;
 	}
 	return false;
@@ -564,12 +564,13 @@ struct TileRec {
 	uint8_t* bases;      // n pushed bases, in push order
 	uint64_t* hashes;    // n canonical hashes of the pushed vertices
 	uint32_t n;
+	uint32_t next;       // index + 1 of the tile that starts at this tile's end marker (same direction), 0 = look it up
 	uint8_t cls;         // (held orientation is the canonical-hash one) << 1 | direction
 	uint8_t lb_code;     // ExtCode of LB(marker)
 	uint8_t stop_kind;   // TileStop
 	uint8_t stop_code;   // ExtCode when stop_kind == TS_CODE
 	uint8_t end_orient;  // orientation bit of the last pushed vertex
-	uint8_t pad[7];
+	uint8_t pad[3];
 };
 
 template <int KW>
@@ -658,6 +659,7 @@ ABB_HD void make_tile(Ctx& c, const Vtx<KW>& m, Dir dir, TileRec* t, uint8_t* ba
 		}
 	}
 	t->key = m.canon();
+	t->next = 0;
 	t->cls = (uint8_t)vtx_class(m, dir);
 	unsigned n = 0;
 	uint64_t prev_h = 0;
@@ -768,10 +770,8 @@ ABB_HD ExtCode extend_dir(Ctx& c, Vtx<KW>& head, Dir dir, unsigned* psize, ByteV
 			uint64_t hk = head.canon();
 			unsigned cls = vtx_class(head, dir);
 			bool moved = false;
-			for (;;) {
-				const TileRec* T = c.tile_lookup(hk, cls);
-				if (!T)
-					break;
+			const TileRec* T = c.tile_lookup(hk, cls);
+			while (T) {
 				// extendPathBySingleVertex's look-behind at this marker, from the stored LB
 				if (T->lb_code != ER_LENGTH_LIMIT || T->lb_t != prev_h) {
 					if (moved)
@@ -779,6 +779,12 @@ ABB_HD ExtCode extend_dir(Ctx& c, Vtx<KW>& head, Dir dir, unsigned* psize, ByteV
 					return ER_AMBI_IN;
 				}
 				const unsigned n = T->n;
+				// where the chain goes next is known before the bases are copied: start fetching that record now
+				const TileRec* Tn = nullptr;
+				if (T->stop_kind == TS_MARKER && n) {
+					Tn = T->next ? c.tile_at(T->next - 1) : c.tile_lookup(T->end_key, ((unsigned)T->end_orient << 1) | (unsigned)dir);
+					c.prefetch(Tn);
+				}
 				if (n) {
 					const uint32_t ti = c.tile_index(T);
 					if (ti == brent_tortoise) { // the same tile again: a cycle the splice cannot see; walk this read without tiles
@@ -806,8 +812,9 @@ ABB_HD ExtCode extend_dir(Ctx& c, Vtx<KW>& head, Dir dir, unsigned* psize, ByteV
 						head = rebuild_head(c, start, bases, 0, dir);
 					return (ExtCode)T->stop_code;
 				}
-				if (T->stop_kind == TS_CAP)
+				if (T->stop_kind == TS_CAP || !n)
 					break;
+				T = Tn;
 			}
 			if (moved) {
 				head = rebuild_head(c, start, bases, 0, dir);

@@ -18,7 +18,8 @@ bases = torch.cat(chunks); del chunks
 offs = torch.arange(rs.n + 1, dtype=torch.int64, device="cuda") * L
 torch.cuda.synchronize()
 print(f"generated {rs.n} reads in {time.time()-t0:.1f}s")
-for window in [1 << 17, 1 << 18, 1 << 19, (1 << 20) - 64]:
+windows = [int(sys.argv[3])] if len(sys.argv) > 3 else [1 << 17, 1 << 18, 1 << 19, (1 << 20) - 64]
+for window in windows:
     f = capi.Filter.counting(counters, H, k, 3)
     f.set_window(window)
     f.insert_reads_dev(bases.data_ptr(), offs.data_ptr(), min(rs.n, 100000), 0)  # warm-up

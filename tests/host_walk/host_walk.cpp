@@ -54,6 +54,12 @@ struct HostCtx {
 		}
 		return m;
 	}
+	template <int KW>
+	unsigned neighbors_dir(const Vtx<KW>& v, Dir d)
+	{
+		const unsigned m = neighbors(v);
+		return d == FWD ? (m & 15) : (m >> 4);
+	}
 	struct Probe {
 		unsigned mask;
 	};
@@ -80,6 +86,8 @@ struct HostCtx {
 	}
 	std::unordered_multimap<uint64_t, uint32_t> tile_multi;
 	uint32_t tile_index(const TileRec* t) const { return (uint32_t)(t - tile_recs.data()); }
+	const TileRec* tile_at(uint32_t idx) const { return &tile_recs[idx]; }
+	void prefetch(const void*) const {}
 	void wr32(uint32_t* p, uint32_t v) { *p = v; }
 	uint64_t rd64(const uint64_t* p) { return *p; }
 	void wr64(uint64_t* p, uint64_t v) { *p = v; }
@@ -327,7 +335,17 @@ static int run(unsigned k, unsigned kc, unsigned H, uint64_t m, unsigned trim, c
 		for (uint32_t i = 0; i < c.tile_recs.size(); ++i)
 			c.tile_multi.emplace(HostCtx::tkey(c.tile_recs[i].key, c.tile_recs[i].cls), i);
 		c.use_tiles = true;
-		fprintf(stderr, "host_walk: %zu tiles from %zu markers\n", c.tile_recs.size(), seen.size());
+		size_t linked = 0;
+		for (auto& t : c.tile_recs)
+			if (t.stop_kind == TS_MARKER && t.n) {
+				const TileRec* o = c.tile_lookup(t.end_key, ((unsigned)t.end_orient << 1) | (t.cls & 1u));
+				if (o) {
+					t.next = c.tile_index(o) + 1;
+					++linked;
+				}
+			}
+		c.tile_splices = 0;
+		fprintf(stderr, "host_walk: %zu tiles from %zu markers, %zu linked\n", c.tile_recs.size(), seen.size(), linked);
 	}
 
 	Assembly as;
