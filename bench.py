@@ -44,6 +44,9 @@ ERR = 0.005
 SEED = 2
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "abyss-bloom-dbg-ref")
 ALG_BYTES_PER_KMER = 64 * H + L / (L - K + 1)  # 257.7 B
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_commit launch over a 2^19-slot window of this filter
+# (ncu --set full, cold caches; profiles/r01_k_commit_w19_full_raw.csv): 387.9 MB + 87.0 MB
+NCU_TRAFFIC_PER_COMMIT_LAUNCH = 474.9e6
 
 
 def peaks():
@@ -301,7 +304,11 @@ def main():
     kmers_per_launch = ist.kmers / max(1, ist.commit_launches)  # k-mers this rank inserted per k_commit launch
     achieved = ALG_BYTES_PER_KMER * kmers_per_launch / (commit_ms * 1e-3) / 1e9 if commit_ms > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": "k_commit (ordered counting-Bloom min-increment)", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": achieved / peak,
+                "traffic": NCU_TRAFFIC_PER_COMMIT_LAUNCH if (args.window in (0, 1 << 19) and args.reads == N_READS) else None,
+                "traffic_note": "bytes per launch, ncu cold-cache capture profiles/r01_k_commit_w19_full_raw.csv; algorithmic bytes per launch = "
+                                f"{ALG_BYTES_PER_KMER * kmers_per_launch:.3e}",
+                "peak_source": peak_src,
                 "alg_bytes_per_kmer": ALG_BYTES_PER_KMER, "launches": int(ist.commit_launches),
                 "avg_launch_ms": commit_ms, "share_of_step": ist.ms_commit / ms_step}
 
