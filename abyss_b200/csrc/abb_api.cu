@@ -83,7 +83,8 @@ static int ensure_workspace(abb_filter* f)
 	f->d_deferred = nullptr;
 	ABB_CUDA(cudaMalloc((void**)&f->d_tags, 2 * want * sizeof(unsigned long long)));
 	ABB_CUDA(cudaMemsetAsync(f->d_tags, 0, 2 * want * sizeof(unsigned long long), f->stream));
-	ABB_CUDA(cudaMalloc((void**)&f->d_deferred, f->window * sizeof(unsigned)));
+	// two carry lists (slots that lost a reservation travel to the next window), worst case everything defers
+	ABB_CUDA(cudaMalloc((void**)&f->d_deferred, 2 * (f->window + kCarryLanes) * sizeof(uint64_t)));
 	f->tag_slots = want;
 	f->epoch = 0;
 	f->epoch2[0] = f->epoch2[1] = 0;
@@ -132,6 +133,11 @@ static int ordered_insert(abb_filter* f, const uint64_t* d_hashes, const uint8_t
 	ABB_CUDA(cudaEventRecord(f->ev_in, s_main));
 	ABB_CUDA(cudaStreamWaitEvent(s_res, f->ev_in, 0));
 	const uint64_t n_windows = (n_slots + f->window - 1) / f->window;
+	const unsigned age_off = (unsigned)(kAge * f->window);
+	uint64_t* carry[2] = { reinterpret_cast<uint64_t*>(f->d_deferred),
+		                   reinterpret_cast<uint64_t*>(f->d_deferred) + (f->window + kCarryLanes) };
+	unsigned* n_carry[2] = { f->d_ndef, f->d_ndef + 1 };
+	ABB_CUDA(cudaMemsetAsync(f->d_ndef, 0, 2 * sizeof(unsigned), s_main));
 	bool done_recorded[2] = { false, false };
 	unsigned epoch_of[2] = { 0, 0 };
 	auto issue_reserve = [&](uint64_t w) -> int {
@@ -139,18 +145,19 @@ static int ordered_insert(abb_filter* f, const uint64_t* d_hashes, const uint8_t
 		const uint64_t w0 = w * f->window;
 		const unsigned n = (unsigned)std::min<uint64_t>(f->window, n_slots - w0);
 		const TagTable tab = { f->d_tags + (uint64_t)p * f->tag_slots, f->tag_slots - 1 };
-		if (done_recorded[p]) // table p is free again once window w-2 has been resolved
+		if (done_recorded[p]) // table p is free again once window w-2 is through
 			ABB_CUDA(cudaStreamWaitEvent(s_res, f->ev_done[p], 0));
 		if (f->epoch2[p] >= kMaxEpoch) {
 			ABB_CUDA(cudaMemsetAsync(tab.e, 0, f->tag_slots * sizeof(unsigned long long), s_res));
 			f->epoch2[p] = 0;
 		}
 		epoch_of[p] = ++f->epoch2[p];
-		ABB_DISPATCH_H(f->H, (k_reserve<LITERAL, MAXH><<<blocks_for(n, 256), 256, 0, s_res>>>(d_hashes, d_valid, w0, n, f->cfg, tab, epoch_of[p])));
+		ABB_DISPATCH_H(f->H, (k_reserve<LITERAL, MAXH><<<blocks_for(n, 256), 256, 0, s_res>>>(d_hashes, d_valid, w0, n, f->cfg, tab, epoch_of[p], age_off)));
 		ABB_CUDA(cudaEventRecord(f->ev_res[p], s_res));
 		return ABB_OK;
 	};
 	ABB_CHECK(issue_reserve(0));
+	int in = 0; // carry list read by this window
 	for (uint64_t w = 0; w < n_windows; ++w) {
 		const int p = (int)(w & 1);
 		const uint64_t w0 = w * f->window;
@@ -158,25 +165,35 @@ static int ordered_insert(abb_filter* f, const uint64_t* d_hashes, const uint8_t
 		const TagTable tab = { f->d_tags + (uint64_t)p * f->tag_slots, f->tag_slots - 1 };
 		const unsigned epoch = epoch_of[p];
 		if (w + 1 < n_windows)
-			ABB_CHECK(issue_reserve(w + 1)); // overlaps this window's commit + resolve
+			ABB_CHECK(issue_reserve(w + 1)); // overlaps this window's commit
 		ABB_CUDA(cudaStreamWaitEvent(s_main, f->ev_res[p], 0));
-		const unsigned grid = blocks_for(n, 256);
+		const unsigned grid = blocks_for((uint64_t)kCarryLanes + n, 256);
+		// pending slots are drained when the list grows, every 8 windows (bounded age) and at the end
+		const bool force = (w % 8 == 7) || (w + 1 == n_windows);
+		const unsigned min_count = force ? 1u : kCarryLanes / 2;
 		ABB_DISPATCH_H(f->H, {
-			if (f->kind == ABB_COUNTING) {
-				if (f->profile && f->prof_used + 2 <= f->prof_ev.size())
-					cudaEventRecord(f->prof_ev[f->prof_used++], s_main);
-				k_commit<0, LITERAL, MAXH><<<grid, 256, 0, s_main>>>(d_hashes, d_valid, w0, n, f->cfg, tab, epoch, fv, f->d_deferred, f->d_ndef);
-				if (f->profile && (f->prof_used & 1))
-					cudaEventRecord(f->prof_ev[f->prof_used++], s_main);
-				k_resolve<0, LITERAL, MAXH><<<1, 1024, 0, s_main>>>(d_hashes, w0, f->cfg, tab, epoch, fv, f->d_deferred, f->d_ndef, f->d_stats);
-			} else {
-				k_commit<1, LITERAL, MAXH><<<grid, 256, 0, s_main>>>(d_hashes, d_valid, w0, n, f->cfg, tab, epoch, fv, f->d_deferred, f->d_ndef);
-				k_resolve<1, LITERAL, MAXH><<<1, 1024, 0, s_main>>>(d_hashes, w0, f->cfg, tab, epoch, fv, f->d_deferred, f->d_ndef, f->d_stats);
-			}
+			k_reserve_carry<LITERAL, MAXH><<<kCarryLanes / 256, 256, 0, s_main>>>(d_hashes, carry[in], n_carry[in], w0, f->cfg, tab, epoch, age_off);
+			if (f->profile && f->prof_used + 2 <= f->prof_ev.size())
+				cudaEventRecord(f->prof_ev[f->prof_used++], s_main);
+			if (f->kind == ABB_COUNTING)
+				k_commit<0, LITERAL, MAXH><<<grid, 256, 0, s_main>>>(d_hashes, d_valid, w0, n, f->cfg, tab, epoch, fv, age_off, carry[in], n_carry[in],
+				                                                    carry[1 - in], n_carry[1 - in], f->d_stats);
+			else
+				k_commit<1, LITERAL, MAXH><<<grid, 256, 0, s_main>>>(d_hashes, d_valid, w0, n, f->cfg, tab, epoch, fv, age_off, carry[in], n_carry[in],
+				                                                    carry[1 - in], n_carry[1 - in], f->d_stats);
+			if (f->profile && (f->prof_used & 1))
+				cudaEventRecord(f->prof_ev[f->prof_used++], s_main);
+			if (f->kind == ABB_COUNTING)
+				k_drain<0, LITERAL, MAXH><<<1, 1024, 0, s_main>>>(d_hashes, w0, f->cfg, tab, epoch, fv, age_off, carry[1 - in], n_carry[1 - in],
+				                                                 n_carry[in], min_count, f->d_stats);
+			else
+				k_drain<1, LITERAL, MAXH><<<1, 1024, 0, s_main>>>(d_hashes, w0, f->cfg, tab, epoch, fv, age_off, carry[1 - in], n_carry[1 - in],
+				                                                 n_carry[in], min_count, f->d_stats);
 		});
 		ABB_CUDA(cudaEventRecord(f->ev_done[p], s_main));
 		done_recorded[p] = true;
-		f->st.launches += 3;
+		in = 1 - in;
+		f->st.launches += 4;
 		f->st.windows += 1;
 	}
 	ABB_CUDA(cudaGetLastError());
@@ -455,8 +472,8 @@ int abb_filter_create(abb_filter** out, int kind, uint64_t size, unsigned num_ha
 	ABB_TRY(cudaEventCreate(&f->ev1));
 	ABB_TRY(cudaMalloc((void**)&f->d_data, f->bytes_per_level * levels));
 	ABB_TRY(cudaMemsetAsync(f->d_data, 0, f->bytes_per_level * levels, f->stream));
-	ABB_TRY(cudaMalloc((void**)&f->d_ndef, sizeof(unsigned)));
-	ABB_TRY(cudaMemsetAsync(f->d_ndef, 0, sizeof(unsigned), f->stream));
+	ABB_TRY(cudaMalloc((void**)&f->d_ndef, 2 * sizeof(unsigned)));
+	ABB_TRY(cudaMemsetAsync(f->d_ndef, 0, 2 * sizeof(unsigned), f->stream));
 	ABB_TRY(cudaMalloc((void**)&f->d_stats, 8 * sizeof(unsigned long long)));
 	ABB_TRY(cudaMemsetAsync(f->d_stats, 0, 8 * sizeof(unsigned long long), f->stream));
 	if (!f->mask.empty()) {
@@ -550,7 +567,7 @@ int abb_filter_set_window(abb_filter* f, uint64_t window_slots)
 	ABB_REQUIRE(f, "NULL filter");
 	if (window_slots == 0)
 		window_slots = kDefaultWindow;
-	ABB_REQUIRE(window_slots >= 32 && window_slots < kSlotMask, "window must be in [32, 2^%u - 1)", kSlotBits);
+	ABB_REQUIRE(window_slots >= 32 && window_slots <= (1ULL << 20) - 64, "window must be in [32, 2^20 - 64]");
 	ABB_CUDA(cudaSetDevice(f->device));
 	ABB_CUDA(cudaStreamSynchronize(f->stream));
 	f->window = window_slots;

@@ -107,7 +107,7 @@ struct abb_filter {
 	unsigned epoch2[2] = { 0, 0 };          // per tag table
 	cudaStream_t stream2 = nullptr;         // reservation pass of the next window
 	cudaEvent_t ev_res[2] = { nullptr, nullptr }, ev_done[2] = { nullptr, nullptr }, ev_in = nullptr;
-	unsigned* d_deferred = nullptr;
+	unsigned* d_deferred = nullptr;          // two carry lists of uint64 slot ids
 	unsigned* d_ndef = nullptr;
 	unsigned long long* d_stats = nullptr; // [0] deferred [1] max rounds [2] serial [3..4] popcount scratch
 

@@ -21,20 +21,26 @@
 //     before it (it does not own the shared position), so applying it now is what the sequential
 //     order would do; owners touch pairwise disjoint positions, so plain byte loads/stores are
 //     race free.  Slots that lost a reservation are appended to a deferred list.
-//     Owners "release" their table entries (slot field := all ones) after applying.
-//   * resolve: one CTA replays the deferred list with the same reserve/commit/release rule, one
-//     round per link of the longest dependency chain; after kMaxRounds it degrades to a strict
-//     in-order replay by one warp (pathological inputs only, e.g. one k-mer repeated thousands
-//     of times inside a window).
-// Table entries are [epoch:8 | position:36 | slot:20]; an entry from an older epoch is free, so
-// the table is cleared only once every 255 windows.
+//     Owners "release" their table entries (priority field := all ones) after applying.
+//   * carry: the slots that lost a reservation are simply carried into the next window, where they
+//     are the oldest pending events: priority = slot - window_start + kAge * W, so pending slots of
+//     up to kAge earlier windows sort before every slot of the current window, in file order.  A
+//     tiny kernel adds their reservations to the next window's table, the next commit kernel
+//     gives them threads of their own.  Nothing serial remains on the per-window critical path.
+//   * drain: one CTA replays whatever is still pending with the same reserve/commit/release rule
+//     round by round (then strictly in order) -- every 8 windows, when the carry list grows large
+//     (one k-mer repeated thousands of times), and at the end of a call.
+// Table entries are [epoch:4 | position:36 | priority:24]; an entry from an older epoch is free, so
+// a table is cleared only once every 15 uses.
 #pragma once
 #include "abb_device.cuh"
 #include <cuda_runtime.h>
 
 namespace abb {
 
-constexpr unsigned kSlotBits = 20;                  // W <= 2^20 slots per window
+constexpr unsigned kSlotBits = 24;                  // priority = slot - window start + kAge * W  <  (kAge + 1) * W
+constexpr unsigned kAge = 15;                       // a pending slot is drained before it is this many windows old
+constexpr unsigned kCarryLanes = 1u << 16;          // threads a commit launch reserves for carried slots
 constexpr unsigned kPosBits = 36;                   // filters up to 2^36 counters / bits
 constexpr unsigned kEpochBits = 64 - kSlotBits - kPosBits;
 constexpr uint64_t kSlotMask = (1ULL << kSlotBits) - 1;
@@ -380,7 +386,7 @@ ABB_D void apply_owner(const FilterView& f, const uint64_t* pos, unsigned H)
 template <bool LITERAL, int MAXH>
 __global__ void __launch_bounds__(256)
 k_reserve(const uint64_t* __restrict__ hashes, const uint8_t* __restrict__ valid, uint64_t w0,
-          unsigned n, HashCfg cfg, TagTable tab, unsigned epoch)
+          unsigned n, HashCfg cfg, TagTable tab, unsigned epoch, unsigned age_off)
 {
 	const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
 	if (t >= n)
@@ -393,24 +399,54 @@ k_reserve(const uint64_t* __restrict__ hashes, const uint8_t* __restrict__ valid
 #pragma unroll
 	for (int i = 0; i < MAXH; ++i)
 		if (i < (int)cfg.H)
-			tag_reserve(tab, epoch, pos[i], t);
+			tag_reserve(tab, epoch, pos[i], age_off + t);
 }
 
-/** K2b: owners apply and release, everybody else is deferred.
- *  The counter loads are issued before the ownership probes (they are wasted only for the <1 % of
- *  slots that lose a reservation) so that the HBM round trip overlaps the L2 round trip. */
+/** reservations of the slots carried over from earlier windows (they precede every slot of this one) */
+template <bool LITERAL, int MAXH>
+__global__ void __launch_bounds__(256)
+k_reserve_carry(const uint64_t* __restrict__ hashes, const uint64_t* __restrict__ carry, const unsigned* __restrict__ n_carry,
+                uint64_t w0, HashCfg cfg, TagTable tab, unsigned epoch, unsigned age_off)
+{
+	const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= *n_carry)
+		return;
+	const uint64_t s = carry[i];
+	uint64_t pos[MAXH];
+	slot_positions<LITERAL, MAXH>(hashes, s, cfg, pos);
+	const uint64_t prio = s + age_off - w0;
+#pragma unroll
+	for (int j = 0; j < MAXH; ++j)
+		if (j < (int)cfg.H)
+			tag_reserve(tab, epoch, pos[j], prio);
+}
+
+/** K2b: owners apply and release, everybody else is carried into the next window.
+ *  Threads [0, kCarryLanes) serve the slots carried in from earlier windows, the rest the n slots
+ *  of this window.  The counter loads are issued before the ownership probes (wasted only for the
+ *  <1 % of slots that lose a reservation) so that the HBM round trip overlaps the L2 round trip. */
 template <int KIND, bool LITERAL, int MAXH>
 __global__ void __launch_bounds__(256)
 k_commit(const uint64_t* __restrict__ hashes, const uint8_t* __restrict__ valid, uint64_t w0,
-         unsigned n, HashCfg cfg, TagTable tab, unsigned epoch, FilterView f,
-         unsigned* __restrict__ deferred, unsigned* __restrict__ n_deferred)
+         unsigned n, HashCfg cfg, TagTable tab, unsigned epoch, FilterView f, unsigned age_off,
+         const uint64_t* __restrict__ carry_in, const unsigned* __restrict__ n_in,
+         uint64_t* __restrict__ carry_out, unsigned* __restrict__ n_out, unsigned long long* __restrict__ stats)
 {
-	const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
-	if (t >= n)
-		return;
-	const uint64_t s = w0 + t;
-	if (valid && !valid[s])
-		return;
+	const unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
+	uint64_t s;
+	if (id < kCarryLanes) {
+		if (id >= *n_in)
+			return;
+		s = carry_in[id];
+	} else {
+		const unsigned t = id - kCarryLanes;
+		if (t >= n)
+			return;
+		s = w0 + t;
+		if (valid && !valid[s])
+			return;
+	}
+	const uint64_t prio = s + age_off - w0;
 	uint64_t pos[MAXH];
 	slot_positions<LITERAL, MAXH>(hashes, s, cfg, pos);
 	unsigned v[MAXH];
@@ -425,7 +461,7 @@ k_commit(const uint64_t* __restrict__ hashes, const uint8_t* __restrict__ valid,
 #pragma unroll
 	for (int i = 0; i < MAXH; ++i)
 		if (i < (int)cfg.H)
-			owner &= tag_owner_at(tab, epoch, pos[i], &where[i]) == t;
+			owner &= tag_owner_at(tab, epoch, pos[i], &where[i]) == prio;
 	if (owner) {
 		if (KIND == 0) {
 			// CountingBloomFilter::incrementMin by the single owner (CountingBloomFilter.hpp:138-162)
@@ -446,59 +482,66 @@ k_commit(const uint64_t* __restrict__ hashes, const uint8_t* __restrict__ valid,
 		for (int i = 0; i < MAXH; ++i)
 			if (i < (int)cfg.H)
 				__stcg(&tab.e[where[i]], (unsigned long long)tag_pack(epoch, pos[i], kSlotMask));
-	} else
-		deferred[atomicAdd(n_deferred, 1u)] = t;
+	} else {
+		carry_out[atomicAdd(n_out, 1u)] = s;
+		if (id >= kCarryLanes)
+			atomicAdd(&stats[0], 1ULL); // slots that did not commit in their own window
+	}
 }
 
-/** K2c: one CTA replays the deferred slots in dependency order.
- *  stats[0] += deferred slots, stats[1] = max rounds seen, stats[2] += serial-replayed slots.
- *  Leaves *n_deferred = 0 for the next window. */
+/** K2c: one CTA applies every pending slot of `list` in dependency order (see the header comment).
+ *  Does nothing when fewer than min_count slots are pending.  Clears *n_consumed (the list the
+ *  preceding commit launch has just read) so that it can collect the next window's carries.
+ *  stats[1] = max rounds seen, stats[2] += slots replayed strictly in order. */
 template <int KIND, bool LITERAL, int MAXH>
 __global__ void __launch_bounds__(1024)
-k_resolve(const uint64_t* __restrict__ hashes, uint64_t w0, HashCfg cfg, TagTable tab, unsigned epoch,
-          FilterView f, unsigned* __restrict__ deferred, unsigned* __restrict__ n_deferred,
-          unsigned long long* __restrict__ stats)
+k_drain(const uint64_t* __restrict__ hashes, uint64_t w0, HashCfg cfg, TagTable tab, unsigned epoch, FilterView f, unsigned age_off,
+        uint64_t* __restrict__ list, unsigned* __restrict__ n_list, unsigned* __restrict__ n_consumed, unsigned min_count,
+        unsigned long long* __restrict__ stats)
 {
 	__shared__ unsigned s_left;
 	__shared__ unsigned long long s_key[32];
-	const unsigned n = *n_deferred;
-	if (n == 0)
+	if (threadIdx.x == 0)
+		*n_consumed = 0;
+	const unsigned n = *n_list;
+	if (n < min_count || n == 0)
 		return;
+	constexpr uint64_t kDone = ~0ULL;
 	unsigned left = n, round = 0;
 	while (left > 0 && round < kMaxRounds) {
 		for (unsigned x = threadIdx.x; x < n; x += blockDim.x) {
-			const unsigned t = deferred[x];
-			if (t == 0xffffffffu)
+			const uint64_t s = list[x];
+			if (s == kDone)
 				continue;
 			uint64_t pos[MAXH];
-			slot_positions<LITERAL, MAXH>(hashes, w0 + t, cfg, pos);
+			slot_positions<LITERAL, MAXH>(hashes, s, cfg, pos);
 #pragma unroll
 			for (int i = 0; i < MAXH; ++i)
 				if (i < (int)cfg.H)
-					tag_reserve(tab, epoch, pos[i], t);
+					tag_reserve(tab, epoch, pos[i], s + age_off - w0);
 		}
 		if (threadIdx.x == 0)
 			s_left = 0;
 		__threadfence();
 		__syncthreads();
 		for (unsigned x = threadIdx.x; x < n; x += blockDim.x) {
-			const unsigned t = deferred[x];
-			if (t == 0xffffffffu)
+			const uint64_t s = list[x];
+			if (s == kDone)
 				continue;
 			uint64_t pos[MAXH];
-			slot_positions<LITERAL, MAXH>(hashes, w0 + t, cfg, pos);
+			slot_positions<LITERAL, MAXH>(hashes, s, cfg, pos);
 			bool owner = true;
 #pragma unroll
 			for (int i = 0; i < MAXH; ++i)
 				if (i < (int)cfg.H)
-					owner &= tag_owner(tab, epoch, pos[i]) == t;
+					owner &= tag_owner(tab, epoch, pos[i]) == s + age_off - w0;
 			if (owner) {
 				apply_owner<KIND, MAXH>(f, pos, cfg.H);
 #pragma unroll
 				for (int i = 0; i < MAXH; ++i)
 					if (i < (int)cfg.H)
 						tag_release(tab, epoch, pos[i]);
-				deferred[x] = 0xffffffffu;
+				list[x] = kDone;
 			} else
 				atomicAdd(&s_left, 1u);
 		}
@@ -511,16 +554,17 @@ k_resolve(const uint64_t* __restrict__ hashes, uint64_t w0, HashCfg cfg, TagTabl
 	const unsigned serial = left;
 	// strict in-order replay of whatever is left (only reachable through very long chains)
 	while (left > 0) {
-		unsigned best = 0xffffffffu, bestx = 0;
+		unsigned long long best = ~0ULL;
+		unsigned bestx = 0;
 		for (unsigned x = threadIdx.x; x < n; x += blockDim.x) {
-			const unsigned t = deferred[x];
-			if (t < best) {
-				best = t;
+			const uint64_t s = list[x];
+			if (s < best) {
+				best = s;
 				bestx = x;
 			}
 		}
-		// block-wide argmin on (t, x)
-		unsigned long long key = ((unsigned long long)best << 32) | bestx;
+		// block-wide argmin on (slot, x): slots fit in 40 bits
+		unsigned long long key = best == ~0ULL ? ~0ULL : ((best << 24) | bestx);
 		for (int d = 16; d; d >>= 1) {
 			unsigned long long o = __shfl_down_sync(0xffffffffu, key, d);
 			key = o < key ? o : key;
@@ -532,19 +576,19 @@ k_resolve(const uint64_t* __restrict__ hashes, uint64_t w0, HashCfg cfg, TagTabl
 			unsigned long long m = s_key[0];
 			for (unsigned w = 1; w < (blockDim.x >> 5); ++w)
 				m = s_key[w] < m ? s_key[w] : m;
-			const unsigned t = (unsigned)(m >> 32), x = (unsigned)m;
+			const uint64_t s = m >> 24;
+			const unsigned x = (unsigned)(m & 0xffffff);
 			uint64_t pos[MAXH];
-			slot_positions<LITERAL, MAXH>(hashes, w0 + t, cfg, pos);
+			slot_positions<LITERAL, MAXH>(hashes, s, cfg, pos);
 			apply_owner<KIND, MAXH>(f, pos, cfg.H);
-			deferred[x] = 0xffffffffu;
+			list[x] = kDone;
 		}
 		__threadfence();
 		__syncthreads();
 		--left;
 	}
 	if (threadIdx.x == 0) {
-		*n_deferred = 0;
-		atomicAdd(&stats[0], (unsigned long long)n);
+		*n_list = 0;
 		atomicMax(&stats[1], (unsigned long long)round);
 		atomicAdd(&stats[2], (unsigned long long)serial);
 	}

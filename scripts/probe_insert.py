@@ -10,7 +10,8 @@ n_reads = int(float(sys.argv[1])) if len(sys.argv) > 1 else 2_000_000
 budget = int(float(sys.argv[2])) if len(sys.argv) > 2 else 8 << 30
 k, H, L = 64, 4, 150
 counters = int(round(budget / 1.125)); counters += (-counters) % 64
-rs = ReadSet.from_coverage(2, int(n_reads * L / 40), 40, L, 0.005)
+genome = int(float(sys.argv[4])) if len(sys.argv) > 4 else int(n_reads * L / 40)
+rs = ReadSet(2, genome, n_reads, L, 0.005)
 t = TorchReadSet(rs, "cuda")
 t0 = time.time()
 chunks = [t.ascii(s, min(rs.n, s + (1 << 20))).reshape(-1) for s in range(0, rs.n, 1 << 20)]
