@@ -79,6 +79,7 @@ SIGNATURES = {
     "abb_hash_reads": (C.c_int, [C.c_uint, C.c_char_p, _vp, _vp, C.c_uint64, _vp, _vp, _u64p, C.c_int]),
     "abb_hash_reads_dev": (C.c_int, [_vp, _vp, _vp, C.c_uint64, _vp, _vp, C.c_uint64, _u64p]),
     "abb_insert_h0_dev": (C.c_int, [_vp, _vp, C.c_uint64]),
+    "abb_route_h0_dev": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint, _vp, _vp]),
     "abb_filter_device_ptr": (_vp, [_vp, C.c_int]),
     "abb_filter_download": (C.c_int, [_vp, C.c_int, _vp, C.c_uint64]),
     "abb_filter_upload": (C.c_int, [_vp, C.c_int, _vp, C.c_uint64]),
@@ -235,6 +236,11 @@ class Filter:
         check(self._lib.abb_hash_reads_dev(self._h, _vp(d_bases_ptr), _vp(d_offs_ptr), n_reads, _vp(d_h0_ptr), _vp(d_valid_ptr), capacity,
                                            C.byref(n)))
         return n.value
+
+    def route_h0_dev(self, d_h0_ptr: int, d_valid_ptr: int, n: int, world: int, d_send_ptr: int) -> np.ndarray:
+        counts = np.zeros(world, dtype=np.uint64)
+        check(self._lib.abb_route_h0_dev(self._h, _vp(d_h0_ptr), _vp(d_valid_ptr), n, world, _vp(d_send_ptr), _ptr(counts)))
+        return counts
 
     def insert_h0_dev(self, d_h0_ptr: int, n: int):
         check(self._lib.abb_insert_h0_dev(self._h, _vp(d_h0_ptr), n))

@@ -4,6 +4,8 @@
 #include "abb_common.h"
 #include "abb_insert.cuh"
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+#include <thrust/iterator/counting_iterator.h>
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -234,6 +236,14 @@ __global__ void k_chunk_bounds(const uint64_t* __restrict__ slot_offs, uint64_t 
 	if (r < n_reads)
 		bounds[++c] = n_reads;
 	*n_chunks = c;
+}
+
+__global__ void __launch_bounds__(256)
+k_gather_u64(const uint64_t* __restrict__ src, const uint64_t* __restrict__ idx, uint64_t n, uint64_t* __restrict__ dst)
+{
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n)
+		dst[i] = src[idx[i]];
 }
 
 /** count valid flags (k-mers actually inserted) */
@@ -651,6 +661,68 @@ int abb_hash_reads_dev(abb_filter* f, const char* d_bases, const uint64_t* d_off
 	ABB_CHECK(launch_hash(f, f->k, f->d_care, (const uint8_t*)d_bases, d_offsets, f->slot_offs.p, 0, n_reads, 0, d_h0, d_valid, f->stream,
 	                      &f->st.launches));
 	ABB_CUDA(cudaStreamSynchronize(f->stream));
+	return ABB_OK;
+}
+
+/** owner of a canonical hash among `world` contiguous hash ranges (abyss_b200/multigpu.py owner_of) */
+struct OwnedBy {
+	const uint64_t* h0;
+	const uint8_t* valid;
+	unsigned world, g;
+	__host__ __device__ bool operator()(uint64_t i) const
+	{
+		return valid[i] && (unsigned)((((h0[i] >> 48) & 0xFFFF) * world) >> 16) == g;
+	}
+};
+struct GatherH0 {
+	const uint64_t* h0;
+	__host__ __device__ uint64_t operator()(uint64_t i) const { return h0[i]; }
+};
+
+int abb_route_h0_dev(abb_filter* f, const uint64_t* d_h0, const uint8_t* d_valid, uint64_t n, unsigned world, uint64_t* d_send,
+                     uint64_t* counts_out)
+{
+	ABB_REQUIRE(f && counts_out, "NULL argument");
+	ABB_REQUIRE(world >= 1 && world <= 65536, "world size out of range");
+	for (unsigned g = 0; g < world; ++g)
+		counts_out[g] = 0;
+	if (n == 0)
+		return ABB_OK;
+	ABB_REQUIRE(d_h0 && d_valid && d_send, "NULL buffer");
+	ABB_REQUIRE(n < (1ULL << 40), "too many slots");
+	ABB_CUDA(cudaSetDevice(f->device));
+	// one order-preserving selection per destination: d_send = [slots owned by 0 | owned by 1 | ...]
+	DevBuf<uint64_t> idx; // selected slot indices of one destination, then gathered
+	unsigned long long* d_num = f->d_stats + 6;
+	uint64_t at = 0;
+	// select indices in pieces of < 2^31 items (cub's num_items is an int here)
+	const uint64_t piece = 1ULL << 30;
+	for (unsigned g = 0; g < world; ++g) {
+		uint64_t got = 0;
+		for (uint64_t lo = 0; lo < n; lo += piece) {
+			const int m = (int)std::min<uint64_t>(piece, n - lo);
+			OwnedBy pred{ d_h0, d_valid, world, g };
+			thrust::counting_iterator<uint64_t> first(lo);
+			size_t bytes = 0;
+			ABB_CHECK(idx.reserve((size_t)m));
+			ABB_CUDA(cub::DeviceSelect::If(nullptr, bytes, first, idx.p, d_num, m, pred, f->stream));
+			ABB_CHECK(f->scan_tmp.reserve(bytes));
+			ABB_CUDA(cub::DeviceSelect::If(f->scan_tmp.p, bytes, first, idx.p, d_num, m, pred, f->stream));
+			unsigned long long k = 0;
+			ABB_CUDA(cudaMemcpyAsync(&k, d_num, sizeof k, cudaMemcpyDeviceToHost, f->stream));
+			ABB_CUDA(cudaStreamSynchronize(f->stream));
+			if (k) {
+				k_gather_u64<<<blocks_for(k, 256), 256, 0, f->stream>>>(d_h0, idx.p, k, d_send + at + got);
+				ABB_CUDA(cudaGetLastError());
+			}
+			got += k;
+			f->st.launches += 2;
+		}
+		counts_out[g] = got;
+		at += got;
+	}
+	ABB_CUDA(cudaStreamSynchronize(f->stream));
+	idx.release();
 	return ABB_OK;
 }
 

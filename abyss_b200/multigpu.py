@@ -31,10 +31,16 @@ def route_by_owner(h0: torch.Tensor, valid: torch.Tensor, world: int):
     """stable partition of the valid hashes by owner: returns (send buffer, per-destination counts)"""
     # destination of every slot (world for invalid slots); one order-preserving selection per destination
     # (torch.sort is limited to 2^31 elements; a rank's slice of the 50 M-read workload has more)
-    own = torch.where(valid.bool(), owner_of(h0, world), torch.full_like(h0, world)).to(torch.uint8)
-    parts = [h0[own == g] for g in range(world)]
-    counts = torch.tensor([p.numel() for p in parts], dtype=torch.int64, device=h0.device)
-    return torch.cat(parts), counts
+    own = owner_of(h0, world).to(torch.uint8)
+    own[~valid.bool()] = world
+    counts = torch.bincount(own.to(torch.int32), minlength=world + 1)[:world].to(torch.int64)
+    send = torch.empty(int(counts.sum()), dtype=h0.dtype, device=h0.device)  # filled destination by destination
+    at = 0
+    for g in range(world):
+        n = int(counts[g])
+        torch.masked_select(h0, own == g, out=send[at:at + n])
+        at += n
+    return send, counts
 
 
 def exchange(send: torch.Tensor, counts: torch.Tensor, group=None) -> torch.Tensor:
@@ -71,8 +77,14 @@ def sharded_insert(filt, bases: torch.Tensor, offs: torch.Tensor, n_reads: int, 
     valid = torch.empty(max(slots, 1), dtype=torch.uint8, device=dev)
     if slots:
         filt.hash_reads_dev(bases.data_ptr(), offs.data_ptr(), n_reads, h0.data_ptr(), valid.data_ptr(), slots)
-    send, counts = route_by_owner(h0[:slots], valid[:slots], world)
+    # stable partition by owner with the library's selection kernels (route_by_owner is the torch statement
+    # of the same thing, kept for the CPU tests of the host logic)
+    send = torch.empty(max(slots, 1), dtype=torch.int64, device=dev)
+    cnt = filt.route_h0_dev(h0.data_ptr(), valid.data_ptr(), slots, world, send.data_ptr())
+    counts = torch.from_numpy(cnt.astype("int64")).to(dev)
+    send = send[:int(cnt.sum())]
     del h0, valid
+    torch.cuda.empty_cache()
     recv = exchange(send, counts, group)
     del send
     torch.cuda.synchronize(dev)
@@ -80,6 +92,8 @@ def sharded_insert(filt, bases: torch.Tensor, offs: torch.Tensor, n_reads: int, 
         filt.insert_h0_dev(recv.data_ptr(), recv.numel())
     owned = recv.numel()
     del recv
+    if dev.type == "cuda":
+        torch.cuda.empty_cache()  # hand the routing buffers back: the library allocates with cudaMalloc
     t = filter_tensor(filt, dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     torch.cuda.synchronize(dev)

@@ -109,6 +109,10 @@ int abb_hash_reads(unsigned k, const char* mask, const char* bases, const uint64
 int abb_hash_reads_dev(abb_filter* f, const char* d_bases, const uint64_t* d_offsets, uint64_t n_reads,
                        uint64_t* d_h0, uint8_t* d_valid, uint64_t capacity, uint64_t* n_slots_out);
 int abb_insert_h0_dev(abb_filter* f, const uint64_t* d_h0, uint64_t n);
+/* stable partition of the valid hashes by owning rank (world contiguous hash ranges over the top 16 bits):
+ * d_send = [owned by 0 | owned by 1 | ...], each part in slot order; counts_out[world] on the host. */
+int abb_route_h0_dev(abb_filter* f, const uint64_t* d_h0, const uint8_t* d_valid, uint64_t n, unsigned world,
+                     uint64_t* d_send, uint64_t* counts_out);
 void* abb_filter_device_ptr(abb_filter* f, int level);
 
 /* ---- raw array <-> host (operator<< / loadFilter: CountingBloomFilter.hpp:262-379,
