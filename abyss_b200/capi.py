@@ -91,6 +91,8 @@ SIGNATURES = {
     "abb_assembler_process_reads_dev": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.POINTER(C.POINTER(Contig)), _u64p, C.POINTER(C.c_char_p)]),
     "abb_assembler_stats": (C.c_int, [_vp, C.POINTER(AssemblyStats)]),
     "abb_assembler_reset": (C.c_int, [_vp]),
+    "abb_assembler_classify_dev": (C.c_int, [_vp, _vp, _vp, C.c_uint64, _vp]),
+    "abb_assembler_set_codes": (C.c_int, [_vp, _vp, C.c_uint64]),
     "abb_assembler_counters": (C.c_int, [_vp, C.POINTER(AssemblyCounters)]),
     "abb_assembler_read_results": (C.c_int, [_vp, C.POINTER(_u8p), _u64p]),
     "abb_assembler_assembled_filter": (_vp, [_vp]),
@@ -336,6 +338,12 @@ class Assembler:
 
     def reset(self):
         check(self._lib.abb_assembler_reset(self._h))
+
+    def classify_dev(self, d_bases_ptr: int, d_offs_ptr: int, n_reads: int, d_codes_ptr: int):
+        check(self._lib.abb_assembler_classify_dev(self._h, _vp(d_bases_ptr), _vp(d_offs_ptr), n_reads, _vp(d_codes_ptr)))
+
+    def set_codes(self, d_codes_ptr: int, n_reads: int):
+        check(self._lib.abb_assembler_set_codes(self._h, _vp(d_codes_ptr), n_reads))
 
     def stats(self) -> AssemblyStats:
         st = AssemblyStats()

@@ -1009,6 +1009,8 @@ struct abb_assembler {
 	cudaStream_t stream = nullptr;
 	uint64_t reads_seen = 0;
 	int kw = 0;
+	const uint8_t* ext_codes = nullptr; // classification supplied by the caller for the next batch (device)
+	uint64_t ext_n = 0;
 	const uint8_t* cur_bases = nullptr; // device reads of the batch being processed
 	const uint64_t* cur_offs = nullptr;
 
@@ -1757,6 +1759,35 @@ int abb_assembler_destroy(abb_assembler* a)
 	return ABB_OK;
 }
 
+/** slot offsets + K1 over the batch into a->h0 / a->valid, then (unless codes come from outside) K3a */
+static int hash_and_classify(abb_assembler* a, const uint8_t* d_bases, const uint64_t* d_offs, uint64_t n_reads, bool classify,
+                             uint64_t* total_out)
+{
+	abb_filter* f = a->solid;
+	cudaStream_t st = a->stream;
+	uint64_t total = 0;
+	ABB_CHECK(compute_slot_offsets(f->k, d_offs, n_reads, a->slot_offs, a->scan_tmp, st, &total, &a->st_launches));
+	ABB_CHECK(a->h0.reserve(total + 1));
+	ABB_CHECK(a->valid.reserve(total + 1));
+	ABB_CHECK(a->codes.reserve(n_reads));
+	if (total)
+		ABB_CHECK(launch_hash(nullptr, f->k, nullptr, d_bases, d_offs, a->slot_offs.p, 0, n_reads, 0, a->h0.p, a->valid.p, st,
+		                      &a->st_launches));
+	*total_out = total;
+	if (!classify)
+		return ABB_OK;
+	int sms = 148;
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, f->device);
+	const unsigned grid = (unsigned)std::min<uint64_t>(blocks_for(n_reads, kWalkWarps), (uint64_t)sms * 8);
+	ABB_CHECK(ensure_scratch(a, grid * kWalkWarps));
+	const WalkCfg w = walk_cfg(a);
+	ABB_DISPATCH_KW(a->kw, (k_classify<KW><<<grid, kWalkWarps * 32, 0, st>>>(d_bases, d_offs, a->slot_offs.p, a->h0.p, a->valid.p, n_reads, w,
+	                                                                        f->cfg, a->look.p, (int)a->params.read_log, a->codes.p)));
+	ABB_CUDA(cudaGetLastError());
+	++a->st_launches;
+	return ABB_OK;
+}
+
 static int process_batch(abb_assembler* a, const uint8_t* d_bases, const uint64_t* d_offs, uint64_t n_reads,
                          const abb_contig** contigs, uint64_t* n_contigs, const char** seqs)
 {
@@ -1772,23 +1803,14 @@ static int process_batch(abb_assembler* a, const uint8_t* d_bases, const uint64_
 	a->cur_offs = d_offs;
 	PhaseTimer tc(a, &a->ms_classify);
 	uint64_t total = 0;
-	ABB_CHECK(compute_slot_offsets(f->k, d_offs, n_reads, a->slot_offs, a->scan_tmp, st, &total, &a->st_launches));
-	ABB_CHECK(a->h0.reserve(total + 1));
-	ABB_CHECK(a->valid.reserve(total + 1));
-	ABB_CHECK(a->codes.reserve(n_reads));
-	if (total)
-		ABB_CHECK(launch_hash(nullptr, f->k, nullptr, d_bases, d_offs, a->slot_offs.p, 0, n_reads, 0, a->h0.p, a->valid.p, st,
-		                      &a->st_launches));
-	// ---- K3a
-	int sms = 148;
-	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, f->device);
-	const unsigned grid = (unsigned)std::min<uint64_t>(blocks_for(n_reads, kWalkWarps), (uint64_t)sms * 8);
-	ABB_CHECK(ensure_scratch(a, grid * kWalkWarps));
-	const WalkCfg w = walk_cfg(a);
-	ABB_DISPATCH_KW(a->kw, (k_classify<KW><<<grid, kWalkWarps * 32, 0, st>>>(d_bases, d_offs, a->slot_offs.p, a->h0.p, a->valid.p, n_reads, w,
-	                                                                        f->cfg, a->look.p, (int)a->params.read_log, a->codes.p)));
-	ABB_CUDA(cudaGetLastError());
-	++a->st_launches;
+	const bool external = a->ext_codes != nullptr;
+	ABB_CHECK(hash_and_classify(a, d_bases, d_offs, n_reads, !external, &total));
+	if (external) { // classification done elsewhere (sharded over several GPUs): take it as is
+		ABB_REQUIRE(a->ext_n == n_reads, "abb_assembler_set_codes: %llu codes for %llu reads", (unsigned long long)a->ext_n,
+		            (unsigned long long)n_reads);
+		ABB_CUDA(cudaMemcpyAsync(a->codes.p, a->ext_codes, n_reads, cudaMemcpyDeviceToDevice, st));
+		a->ext_codes = nullptr;
+	}
 	ABB_CUDA(cudaMemcpyAsync(a->out_codes.data(), a->codes.p, n_reads, cudaMemcpyDeviceToHost, st));
 	ABB_CUDA(cudaStreamSynchronize(st));
 	tc.stop();
@@ -1895,6 +1917,31 @@ int abb_assembler_stats(const abb_assembler* a, abb_assembly_stats* out)
 	out->markers = a->st_markers;
 	out->tiles = a->st_tiles;
 	out->serial_fallbacks = a->st_fallbacks;
+	return ABB_OK;
+}
+
+int abb_assembler_classify_dev(abb_assembler* a, const char* d_bases, const uint64_t* d_offsets, uint64_t n_reads, uint8_t* d_codes)
+{
+	ABB_REQUIRE(a, "NULL assembler");
+	if (n_reads == 0)
+		return ABB_OK;
+	ABB_REQUIRE(d_bases && d_offsets && d_codes, "NULL buffer");
+	ABB_CUDA(cudaSetDevice(a->solid->device));
+	ABB_CUDA(cudaStreamSynchronize(a->solid->stream));
+	PhaseTimer tc(a, &a->ms_classify);
+	uint64_t total = 0;
+	ABB_CHECK(hash_and_classify(a, (const uint8_t*)d_bases, d_offsets, n_reads, true, &total));
+	ABB_CUDA(cudaMemcpyAsync(d_codes, a->codes.p, n_reads, cudaMemcpyDeviceToDevice, a->stream));
+	ABB_CUDA(cudaStreamSynchronize(a->stream));
+	tc.stop();
+	return ABB_OK;
+}
+
+int abb_assembler_set_codes(abb_assembler* a, const uint8_t* d_codes, uint64_t n_reads)
+{
+	ABB_REQUIRE(a, "NULL assembler");
+	a->ext_codes = d_codes;
+	a->ext_n = n_reads;
 	return ABB_OK;
 }
 

@@ -98,3 +98,22 @@ def sharded_insert(filt, bases: torch.Tensor, offs: torch.Tensor, n_reads: int, 
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     torch.cuda.synchronize(dev)
     return owned
+
+
+def sharded_classify(asm, bases_slice: torch.Tensor, offs_slice: torch.Tensor, n_slice: int, n_total: int, group=None) -> torch.Tensor:
+    """K3a on this rank's slice of the reads, all-gather of the per-read codes; the returned tensor holds the
+    codes of all n_total reads (file order) and has been handed to `asm` for its next process_reads call.
+    Slices are the contiguous ranges [r * n // world, (r + 1) * n // world)."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = bases_slice.device
+    sizes = [(r + 1) * n_total // world - r * n_total // world for r in range(world)]
+    assert sizes[rank] == n_slice
+    mx = max(sizes)
+    mine = torch.zeros(mx, dtype=torch.uint8, device=dev)
+    if n_slice:
+        asm.classify_dev(bases_slice.data_ptr(), offs_slice.data_ptr(), n_slice, mine.data_ptr())
+    gathered = torch.empty(world * mx, dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(gathered, mine, group=group)
+    codes = torch.cat([gathered[r * mx:r * mx + sizes[r]] for r in range(world)])
+    asm.set_codes(codes.data_ptr(), n_total)
+    return codes  # keep alive until process_reads has run

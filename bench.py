@@ -149,7 +149,8 @@ def workload_config(args, extra=None):
                      "(BASELINE.json configs[1])",
          "reads": args.reads, "read_len": L, "k": K, "kc": KC, "num_hashes": H, "bloom_bytes": BLOOM_BYTES,
          "l2_policy": "inputs (7.5 GB reads) and filters (8.6 GB) far exceed the 126 MB L2; no flush needed",
-         "parallelism": (f"pass 1 sharded by k-mer hash range over {args.gpus} GPUs (NCCL all-to-all + all-reduce max), pass 2 replicated"
+         "parallelism": (f"pass 1 sharded by k-mer hash range over {args.gpus} GPUs (NCCL all-to-all + all-reduce max), read classification "
+                         "sharded by reads (all-gather), rest of pass 2 replicated"
                          if args.gpus > 1 else "1 GPU")}
     if extra:
         c.update(extra)
@@ -234,7 +235,9 @@ def main():
             multigpu.sharded_insert(filt, bases[lo * L:up * L], offs_slice, up - lo)
             nk = n_kmers_expected
             p1.record(ext)
+            codes = multigpu.sharded_classify(asm, bases[lo * L:up * L], offs_slice, up - lo, rs.n)
             contigs = asm.process_reads_dev(bases.data_ptr(), offs.data_ptr(), rs.n)
+            del codes
         elif host is None:
             nk = filt.insert_reads_dev(bases.data_ptr(), offs.data_ptr(), rs.n, bases.numel())
             p1.record(ext)

@@ -162,6 +162,13 @@ int abb_assembler_process_reads(abb_assembler* a, const char* bases, const uint6
 int abb_assembler_process_reads_dev(abb_assembler* a, const char* d_bases, const uint64_t* d_offsets,
                                     uint64_t n_reads, const abb_contig** contigs, uint64_t* n_contigs,
                                     const char** seqs);
+/* Several GPUs: the per-read classification (K3a) is a pure function of the read and the solid filter, so
+ * ranks may classify disjoint slices (abb_assembler_classify_dev writes one code per read, the internal
+ * RC_* values, to a device buffer), exchange the codes, and hand the complete array to the rank that
+ * assembles: abb_assembler_set_codes applies to the next process_reads call only. */
+int abb_assembler_classify_dev(abb_assembler* a, const char* d_bases, const uint64_t* d_offsets, uint64_t n_reads,
+                               uint8_t* d_codes);
+int abb_assembler_set_codes(abb_assembler* a, const uint8_t* d_codes, uint64_t n_reads);
 /* Start a new assembly on the same handle (the solid filter has been refilled): clears the assembled
  * filter, the contig-end table, the tile store, counters and statistics, keeps all device buffers. */
 int abb_assembler_reset(abb_assembler* a);

@@ -26,6 +26,19 @@ offs = torch.arange(up - lo + 1, dtype=torch.int64, device=dev) * L
 f = capi.Filter.counting(m, H, k, kc, device=rank)
 owned = multigpu.sharded_insert(f, bases, offs, up - lo)
 merged = f.download()
+# sharded classification: codes gathered from both ranks == codes of an unsharded run on the merged filter
+all_bases = torch.from_numpy(asc.reshape(-1).copy()).to(dev)
+all_offs = torch.arange(rs.n + 1, dtype=torch.int64, device=dev) * L
+a1 = capi.Assembler(f)
+codes = multigpu.sharded_classify(a1, bases, offs, up - lo, rs.n)
+out_sharded = a1.process_reads_dev(all_bases.data_ptr(), all_offs.data_ptr(), rs.n)
+res_sharded = a1.read_results().copy()
+a1.close()
+a2 = capi.Assembler(f)
+out_plain = a2.process_reads_dev(all_bases.data_ptr(), all_offs.data_ptr(), rs.n)
+res_plain = a2.read_results().copy()
+a2.close()
+assert out_sharded == out_plain and (res_sharded == res_plain).all()
 tot = torch.tensor([owned], device=dev); dist.all_reduce(tot)
 assert int(tot.item()) == rs.n * (L - k + 1), (int(tot.item()), rs.n * (L - k + 1))
 # every rank holds the same merged filter
