@@ -384,16 +384,37 @@ def counters_for_budget(bloom_size_bytes: int) -> int:
     return r if r % 64 == 0 else r + 64 - r % 64
 
 
+def kmer_pair_seed(k: int, K: int) -> str:
+    """-K: two k-mers of size K at the ends of a k-bit seed (SpacedSeed::kmerPair, BloomDBG/SpacedSeed.h:30-37)"""
+    if K > k // 2:
+        raise ValueError("value of `-K' must be <= k/2")
+    return "1" * K + "0" * (k - 2 * K) + "1" * K
+
+
+def qr_seed_pair(k: int, length: int) -> str:
+    """--qr-seed: a quadratic-residue seed and its mirror image (SpacedSeed::qrSeedPair, SpacedSeed.h:55-95)"""
+    if length < 11 or length > k // 2:
+        raise ValueError("value of `--qr-seed' must be >= 11 and <= k/2")
+    qr = ["1"] * length
+    for i in range(length):
+        if any(j * j % length == i for j in range(1, length)):
+            qr[i] = "0"
+    m = ["0"] * k
+    for i, c in enumerate(qr):
+        m[i] = m[k - 1 - i] = c
+    return "".join(m)
+
+
 def bloom_dbg(read_ids, seqs_or_arrays, k: int, kc: int = 2, num_hashes: int = 4, bloom_size: int | None = None,
               counters: int | None = None, trim: int | None = None, batch_reads: int | None = None, read_log: bool = False,
-              device: int = 0):
-    """abyss-bloom-dbg -k K --kc KC -H H -b B (countingBloomAssembly, bloom-dbg.cc:347-386) on one GPU.
+              device: int = 0, mask: str = ""):
+    """abyss-bloom-dbg -k K --kc KC -H H -b B [-s MASK] (countingBloomAssembly, bloom-dbg.cc:347-386) on one GPU.
     Returns (fasta_text, read_codes)."""
     if counters is None:
         counters = counters_for_budget(bloom_size)
     bases, offs = seqs_or_arrays if isinstance(seqs_or_arrays, tuple) else pack_reads(seqs_or_arrays)
     n = len(offs) - 1
-    f = Filter.counting(counters, num_hashes, k, kc, device=device)
+    f = Filter.counting(counters, num_hashes, k, kc, mask=mask, device=device)
     f.insert_reads((bases, offs))
     a = Assembler(f, trim, read_log)
     out, codes = [], []

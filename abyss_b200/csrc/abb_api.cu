@@ -284,8 +284,9 @@ int launch_hash(abb_filter* f, unsigned k, const uint8_t* d_care, const uint8_t*
 }
 
 /** K1 over explicit (possibly overlapping) segments, see k_hash_segments */
-int launch_hash_segments(unsigned k, const uint8_t* d_bases, const uint64_t* d_seg_beg, const unsigned* d_seg_len,
-                         const uint64_t* d_seg_slot, uint64_t n_segs, uint64_t* d_h0, uint8_t* d_valid, cudaStream_t stream)
+int launch_hash_segments(unsigned k, const uint8_t* d_care, const uint8_t* d_bases, const uint64_t* d_seg_beg,
+                         const unsigned* d_seg_len, const uint64_t* d_seg_slot, uint64_t n_segs, uint64_t* d_h0, uint8_t* d_valid,
+                         cudaStream_t stream)
 {
 	if (n_segs == 0)
 		return ABB_OK;
@@ -293,7 +294,11 @@ int launch_hash_segments(unsigned k, const uint8_t* d_bases, const uint64_t* d_s
 	cudaGetDevice(&dev);
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 	const unsigned grid = (unsigned)std::min<uint64_t>((n_segs + kHashWarps - 1) / kHashWarps, (uint64_t)sms * 32);
-	k_hash_segments<<<grid, kHashWarps * 32, 0, stream>>>(d_bases, d_seg_beg, d_seg_len, d_seg_slot, n_segs, k, d_h0, d_valid);
+	if (d_care)
+		k_hash_segments_masked<<<grid, kHashWarps * 32, 0, stream>>>(d_bases, d_seg_beg, d_seg_len, d_seg_slot, n_segs, k, d_care,
+		                                                             d_h0, d_valid);
+	else
+		k_hash_segments<<<grid, kHashWarps * 32, 0, stream>>>(d_bases, d_seg_beg, d_seg_len, d_seg_slot, n_segs, k, d_h0, d_valid);
 	ABB_CUDA(cudaGetLastError());
 	return ABB_OK;
 }

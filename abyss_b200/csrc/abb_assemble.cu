@@ -91,8 +91,7 @@ struct WarpCtx {
 	__device__ Probe neighbors_issue(const Vtx<KW>& v) const
 	{
 		const unsigned n = lane >> 2, hs = lane & 3;
-		const HashPair h = n < 4 ? roll_right(v.h, rt, kmer_first(v.km, k), n) : roll_left(v.h, rt, kmer_last(v.km), n - 4);
-		const uint64_t h0 = h.canonical();
+		const uint64_t h0 = neighbor_bloom(v, k, rt, n < 4 ? FWD : REV, n & 3);
 		unsigned mn = 255;
 		for (unsigned i = hs; i < cfg->H; i += 4)
 			mn = min(mn, (unsigned)__ldcg(counters + nth_pos(h0, *cfg, i)));
@@ -124,8 +123,7 @@ struct WarpCtx {
 		const bool mine = (n < 4) == (d == FWD);
 		bool ok = true;
 		if (mine) {
-			const HashPair h = n < 4 ? roll_right(v.h, rt, kmer_first(v.km, k), n) : roll_left(v.h, rt, kmer_last(v.km), n - 4);
-			const uint64_t h0 = h.canonical();
+			const uint64_t h0 = neighbor_bloom(v, k, rt, n < 4 ? FWD : REV, n & 3);
 			unsigned mn = 255;
 			for (unsigned i = hs; i < cfg->H; i += 4)
 				mn = min(mn, (unsigned)__ldcg(counters + nth_pos(h0, *cfg, i)));
@@ -437,8 +435,12 @@ k_classify(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offs,
 			const unsigned nk = L - w.k + 1;
 			// allACGT(seq): every base of a read with L >= k lies in some window
 			bool bad = false;
-			for (unsigned j = lane; j < nk; j += 32)
-				bad |= valid[s0 + j] == 0;
+			if (w.rt.nmask) { // with a spaced seed the window flags only cover the '1' positions
+				for (unsigned j = lane; j < L; j += 32)
+					bad |= base_code(bases[beg + j]) >= 4;
+			} else
+				for (unsigned j = lane; j < nk; j += 32)
+					bad |= valid[s0 + j] == 0;
 			if (__any_sync(0xffffffffu, bad)) {
 				code = RC_NON_ACGT;
 			} else {
@@ -459,10 +461,10 @@ k_classify(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offs,
 				} else {
 					// hasBluntEnd (bloom-dbg.h:494-532): lookAhead(first k-mer, REVERSE, 5) on the read and on
 					// its reverse complement
-					const Vtx<KW> first = vtx_from_codes<KW>(bases + beg, w.k, true);
+					const Vtx<KW> first = vtx_from_codes<KW>(bases + beg, w.k, true, w.rt);
 					bool blunt = !look_ahead(c, first, REV, kFpTrim);
 					if (!blunt) {
-						const Vtx<KW> last = vtx_from_codes<KW>(bases + beg + L - w.k, w.k, true);
+						const Vtx<KW> last = vtx_from_codes<KW>(bases + beg + L - w.k, w.k, true, w.rt);
 						blunt = !look_ahead(c, vtx_revcomp(last, w.k), REV, kFpTrim);
 					}
 					code = blunt ? RC_BLUNT_END : (solid ? RC_CANDIDATE : RC_NOT_SOLID);
@@ -613,7 +615,7 @@ k_make_tiles(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ off
 		const unsigned long long mk = markers[item >> 2];
 		const uint64_t r = mk >> 24;
 		const unsigned pos = (unsigned)(mk & 0xffffff);
-		Vtx<KW> v = vtx_from_codes<KW>(bases + offs[r] + pos, w.k, true);
+		Vtx<KW> v = vtx_from_codes<KW>(bases + offs[r] + pos, w.k, true, w.rt);
 		if (item & 2)
 			v = vtx_revcomp(v, w.k);
 		TileRec t;
@@ -746,7 +748,8 @@ k_repeat_check(const ContigRec* __restrict__ recs, unsigned n_contigs, const uin
 /** dense ASCII copies of the ordered unitigs (pathToSeq output as characters) */
 __global__ void __launch_bounds__(256)
 k_gather(const ContigRec* __restrict__ recs, const unsigned* __restrict__ seg_contig, const uint64_t* __restrict__ seg_beg,
-         const unsigned* __restrict__ seg_len, unsigned n_segs, const uint64_t* __restrict__ coffs, uint8_t* __restrict__ out)
+         const unsigned* __restrict__ seg_len, unsigned n_segs, const uint64_t* __restrict__ coffs, uint8_t* __restrict__ out,
+         unsigned k, const __grid_constant__ RollTab rt)
 {
 	// one block per segment of a unitig (long unitigs are cut so that the copy uses the whole GPU);
 	// seg_beg is the absolute offset in `out`, seg_len includes the k-1 overlap (harmlessly copied twice)
@@ -757,6 +760,15 @@ k_gather(const ContigRec* __restrict__ recs, const unsigned* __restrict__ seg_co
 		uint8_t* d = out + seg_beg[sgi];
 		for (unsigned i = threadIdx.x; i < seg_len[sgi]; i += blockDim.x)
 			d[i] = "ACGT"[s[i] & 3];
+		if (rt.nmask && recs[c].len < 2 * k - 2) {
+			// spaced seed: columns no vertex writes stay 'N' (pathToSeq, bloom-dbg.h:139-155); only paths of fewer than
+			// k-1 vertices have any, and those are a single segment
+			__syncthreads();
+			const unsigned n = recs[c].len - k + 1;
+			for (unsigned col = n + threadIdx.x; col + 1 < k; col += blockDim.x)
+				if (!column_written(rt, k, n, col))
+					d[col] = 'N';
+		}
 	}
 }
 
@@ -809,6 +821,30 @@ __global__ void k_endset_rehash(const unsigned long long* o, unsigned ocap, unsi
 	}
 }
 
+/** identity of outputContig's end vertices with a spaced seed (bloom-dbg.h:556-564): the k characters ('N' columns
+ *  included; 'N' is its own complement and sorts between G and T) are put in their string-canonical orientation
+ *  (Common/Sequence.h:39-44), and operator== then compares the '1' positions -- so the key is the masked forward hash
+ *  of that orientation. */
+__device__ uint64_t end_identity(const uint8_t* s, unsigned k, const uint8_t* care)
+{
+	bool use_rc = false;
+	for (unsigned i = 0; i < k; ++i) {
+		const uint8_t a = s[i], t = s[k - 1 - i];
+		const uint8_t b = t == 'A' ? 'T' : t == 'C' ? 'G' : t == 'G' ? 'C' : t == 'T' ? 'A' : t;
+		if (a != b) {
+			use_rc = b < a;
+			break;
+		}
+	}
+	uint64_t f = 0;
+	for (unsigned i = 0; i < k; ++i)
+		if (care[i]) {
+			const unsigned code = use_rc ? 3 - (base_code(s[k - 1 - i]) & 3) : (base_code(s[i]) & 3);
+			f ^= srol_n(seed_of(code), k - 1 - i);
+		}
+	return f;
+}
+
 struct ReplayIO {
 	// speculated reads, in file order
 	const unsigned* spec;        // read index in the batch
@@ -821,6 +857,10 @@ struct ReplayIO {
 	const uint64_t* cslot;       // [n_contigs + 1] k-mer slot offsets into ch0
 	const uint64_t* ch0;
 	const unsigned* clen;
+	// spaced seed only (care == nullptr otherwise): the unitig characters, for the identity of the end k-mers
+	const uint8_t* cseq;
+	const uint64_t* coffs;
+	const uint8_t* care;
 	// outputs
 	uint8_t* rcode;              // per speculated read: RC_ALL_KMERS_VISITED or RC_GENERATED_CONTIGS
 	uint8_t* caccept;            // per contig: 1 = printed
@@ -883,7 +923,12 @@ k_replay(ReplayIO io, unsigned s0, unsigned cs, unsigned ce, const __grid_consta
 			if (len < k + kFpTrim - 1) {
 				// very short contigs: exact table of end k-mers (bloom-dbg.h:576-586)
 				if (tid == 0) {
-					const uint64_t v1 = io.ch0[c0], v2 = io.ch0[c0 + nk - 1];
+					uint64_t v1 = io.ch0[c0], v2 = io.ch0[c0 + nk - 1];
+					if (io.care) {
+						const uint8_t* cs = io.cseq + io.coffs[c];
+						v1 = end_identity(cs, k, io.care);
+						v2 = end_identity(cs + len - k, k, io.care);
+					}
 					int red = endset_contains(ends, v1) && endset_contains(ends, v2);
 					if (!red) {
 						endset_insert(ends, v1);
@@ -1009,6 +1054,8 @@ struct abb_assembler {
 	cudaStream_t stream = nullptr;
 	uint64_t reads_seen = 0;
 	int kw = 0;
+	RollTab rt; // per-k roll constants + spaced-seed positions
+	uint8_t* d_mpos = nullptr;
 	const uint8_t* ext_codes = nullptr; // classification supplied by the caller for the next batch (device)
 	uint64_t ext_n = 0;
 	const uint8_t* cur_bases = nullptr; // device reads of the batch being processed
@@ -1138,7 +1185,7 @@ WalkCfg walk_cfg(const abb_assembler* a)
 	w.k = a->solid->k;
 	w.trim = a->params.trim;
 	w.threshold = a->solid->threshold;
-	w.rt = make_rolltab(a->solid->k);
+	w.rt = a->rt;
 	w.counters = a->solid->d_data;
 	return w;
 }
@@ -1388,9 +1435,9 @@ int stage_contigs(abb_assembler* a, const std::vector<ContigRec>& recs, const Ro
 		ABB_CHECK(h2d(a->seg_slot, seg_slot, st));
 		cudaEventRecord(a->ev2[0], st);
 		k_gather<<<std::min<unsigned>(ns, 148 * 16), 256, 0, st>>>(a->recs_sorted.p, a->seg_contig.p, a->seg_beg.p, a->seg_len.p, ns, a->coffs.p,
-		                                                          a->cseq.p);
+		                                                          a->cseq.p, f->k, a->rt);
 		ABB_CUDA(cudaGetLastError());
-		ABB_CHECK(launch_hash_segments(f->k, a->cseq.p, a->seg_beg.p, a->seg_len.p, a->seg_slot.p, ns, a->ch0.p, a->cvalid.p, st));
+		ABB_CHECK(launch_hash_segments(f->k, f->d_care, a->cseq.p, a->seg_beg.p, a->seg_len.p, a->seg_slot.p, ns, a->ch0.p, a->cvalid.p, st));
 		cudaEventRecord(a->ev2[1], st);
 		cudaEventSynchronize(a->ev2[1]);
 		float ms = 0;
@@ -1584,6 +1631,9 @@ int speculate_round(abb_assembler* a, const std::vector<unsigned>& cand, size_t*
 		io.cslot = a->cslot.p;
 		io.ch0 = a->ch0.p;
 		io.clen = a->clen.p;
+		io.cseq = a->cseq.p;
+		io.coffs = a->coffs.p;
+		io.care = a->solid->d_care;
 		io.rcode = a->rcode.p;
 		io.caccept = a->caccept.p;
 		io.ccov = a->ccov.p;
@@ -1679,9 +1729,11 @@ int abb_assembler_create(abb_assembler** out, abb_filter* solid, const abb_assem
 		set_error("the assembler needs a counting filter (CountingBloomFilter<uint8_t>), like abyss-bloom-dbg");
 		return ABB_ESTATE;
 	}
-	if (!solid->mask.empty()) {
-		set_error("spaced seeds are not supported by the unitig extension stage yet");
-		return ABB_ESTATE;
+	if (!solid->mask.empty()) { // MaskedKmer::setMask / RollingBloomDBGVertex::compare (RollingBloomDBG.h:141-145)
+		const std::string& m = solid->mask;
+		ABB_REQUIRE(m.size() == solid->k, "spaced seed must be k characters long");
+		ABB_REQUIRE(m.front() == '1' && m.back() == '1', "spaced seed must begin and end with '1's");
+		ABB_REQUIRE(std::equal(m.begin(), m.end(), m.rbegin()), "spaced seed must be symmetric");
 	}
 	ABB_REQUIRE(solid->k >= 2, "k must be at least 2 for graph traversal");
 	ABB_CUDA(cudaSetDevice(solid->device));
@@ -1695,7 +1747,26 @@ int abb_assembler_create(abb_assembler** out, abb_filter* solid, const abb_assem
 	if (a->params.trim == 0xffffffffu)
 		a->params.trim = solid->k; // bloom-dbg.cc:518-520
 	a->kw = (int)((2 * solid->k + 63) / 64);
-	a->tiles_on = getenv("ABB_NO_TILES") == nullptr; // debugging switch: vertex-by-vertex walks only
+	a->rt = make_rolltab(solid->k);
+	if (!solid->mask.empty()) {
+		std::vector<uint8_t> mpos;
+		for (unsigned i = 0; i < solid->k; ++i)
+			if (solid->mask[i] == '0')
+				mpos.push_back((uint8_t)i);
+		if (!mpos.empty()) {
+			if (cudaMalloc((void**)&a->d_mpos, mpos.size()) != cudaSuccess ||
+			    cudaMemcpy(a->d_mpos, mpos.data(), mpos.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+				set_error("cudaMalloc of the spaced-seed table failed");
+				delete a;
+				return ABB_ECUDA;
+			}
+			a->rt.nmask = (unsigned)mpos.size();
+			a->rt.mpos = a->d_mpos;
+		}
+	}
+	// tiles are keyed by vertex hash and assume that equal hashes continue identically; with a spaced seed two k-mers
+	// can share the hash and differ on the don't-care positions, so those runs walk vertex by vertex
+	a->tiles_on = getenv("ABB_NO_TILES") == nullptr && solid->mask.empty(); // env: debugging switch
 	if (const char* sp = getenv("ABB_SPEC")) // tuning switch: fixed speculation width
 		a->spec_fixed = a->spec_target = (unsigned)std::max(1, atoi(sp));
 	// BloomFilter assembledKmerSet(solid.size(), solid.getHashNum(), solid.getKmerSize()) (bloom-dbg.h:910-911)
@@ -1737,6 +1808,7 @@ int abb_assembler_destroy(abb_assembler* a)
 	a->offs.release(); a->slot_offs.release(); a->h0.release(); a->coffs.release(); a->cslot.release(); a->ch0.release();
 	a->cand.release(); a->spec.release(); a->spec_cbeg.release(); a->clen.release(); a->ccov.release(); a->status.release();
 	a->recs.release(); a->recs_sorted.release(); a->frames.release(); a->look.release();
+	cudaFree(a->d_mpos);
 	cudaFree(a->d_tiles);
 	cudaFree(a->d_tile_tab);
 	cudaFree(a->d_tile_n);
@@ -1771,7 +1843,7 @@ static int hash_and_classify(abb_assembler* a, const uint8_t* d_bases, const uin
 	ABB_CHECK(a->valid.reserve(total + 1));
 	ABB_CHECK(a->codes.reserve(n_reads));
 	if (total)
-		ABB_CHECK(launch_hash(nullptr, f->k, nullptr, d_bases, d_offs, a->slot_offs.p, 0, n_reads, 0, a->h0.p, a->valid.p, st,
+		ABB_CHECK(launch_hash(nullptr, f->k, f->d_care, d_bases, d_offs, a->slot_offs.p, 0, n_reads, 0, a->h0.p, a->valid.p, st,
 		                      &a->st_launches));
 	*total_out = total;
 	if (!classify)

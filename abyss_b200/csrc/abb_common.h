@@ -81,7 +81,7 @@ namespace abb {
 int launch_hash(abb_filter* f, unsigned k, const uint8_t* d_care, const uint8_t* d_bases, const uint64_t* d_offs,
                 const uint64_t* d_slot_offs, uint64_t r0, uint64_t r1, uint64_t slot_base, uint64_t* d_h0, uint8_t* d_valid,
                 cudaStream_t stream, uint64_t* launches);
-int launch_hash_segments(unsigned k, const uint8_t* d_bases, const uint64_t* d_seg_beg, const unsigned* d_seg_len,
+int launch_hash_segments(unsigned k, const uint8_t* d_care, const uint8_t* d_bases, const uint64_t* d_seg_beg, const unsigned* d_seg_len,
                          const uint64_t* d_seg_slot, uint64_t n_segs, uint64_t* d_h0, uint8_t* d_valid, cudaStream_t stream);
 }
 

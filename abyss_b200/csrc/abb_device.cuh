@@ -88,12 +88,18 @@ ABB_HD uint64_t sror1(uint64_t v)
 /** Per-k constants for O(1) rolls: R^k(seed(c)) for c = A,C,G,T (msTab*[c][k%31|k%33]). */
 struct RollTab {
 	uint64_t rk[4];
+	// spaced seed (MaskedKmer::mask(), Common/MaskedKmer.h:22-60): the don't-care positions of the k-mer, ascending,
+	// none of them 0 or k-1, in memory the code using the table can read; nmask == 0 when there is no mask
+	unsigned nmask;
+	const uint8_t* mpos;
 };
 ABB_HD RollTab make_rolltab(unsigned k)
 {
 	RollTab t;
 	for (unsigned c = 0; c < 4; ++c)
 		t.rk[c] = srol_n(seed_of(c), k);
+	t.nmask = 0;
+	t.mpos = nullptr;
 	return t;
 }
 

@@ -324,6 +324,39 @@ k_hash_reads_masked(const uint8_t* __restrict__ bases, const uint64_t* __restric
 	}
 }
 
+/** k_hash_segments for a spaced seed (unitigs of the extension stage: 'N' can only sit on '0' positions there) */
+static __global__ void __launch_bounds__(kHashWarps * 32)
+k_hash_segments_masked(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ seg_beg,
+                       const unsigned* __restrict__ seg_len, const uint64_t* __restrict__ seg_slot, uint64_t n_segs, unsigned k,
+                       const uint8_t* __restrict__ care, uint64_t* __restrict__ h0_out, uint8_t* __restrict__ valid_out)
+{
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	for (uint64_t r = (uint64_t)blockIdx.x * kHashWarps + warp; r < n_segs; r += (uint64_t)gridDim.x * kHashWarps) {
+		const uint64_t beg = seg_beg[r];
+		const unsigned L = seg_len[r];
+		if (L < k)
+			continue;
+		const uint64_t slot0 = seg_slot[r];
+		for (unsigned j = lane; j + k <= L; j += 32) {
+			uint64_t fh = 0, rh = 0;
+			bool ok = true;
+			for (unsigned t = 0; t < k; ++t) {
+				if (!care[t])
+					continue;
+				unsigned code = base_code(bases[beg + j + t]);
+				if (code >= 4) {
+					ok = false;
+					break;
+				}
+				fh ^= srol_n(seed_of(code), k - 1 - t);
+				rh ^= srol_n(seed_of(3 - code), t);
+			}
+			h0_out[slot0 + j] = rh < fh ? rh : fh;
+			valid_out[slot0 + j] = ok ? 1 : 0;
+		}
+	}
+}
+
 /** per-read window counts -> (exclusive scan done by the caller with cub-free two-pass code) */
 static __global__ void k_window_counts(const uint64_t* __restrict__ offs, uint64_t n_reads, unsigned k,
                                 uint64_t* __restrict__ counts)

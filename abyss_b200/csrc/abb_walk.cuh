@@ -106,14 +106,164 @@ ABB_HD bool kmer_equal(const Kmer<KW>& a, const Kmer<KW>& b)
 		eq &= a.w[j] == b.w[j];
 	return eq;
 }
+/** MaskedKmer equality (Common/MaskedKmer.h:100-118): don't-care positions are not compared */
+template <int KW>
+ABB_HD bool kmer_equal_masked(const Kmer<KW>& a, const Kmer<KW>& b, unsigned k, const RollTab& rt)
+{
+	if (rt.nmask == 0)
+		return kmer_equal(a, b);
+	Kmer<KW> x;
+#pragma unroll
+	for (int j = 0; j < KW; ++j)
+		x.w[j] = a.w[j] ^ b.w[j];
+	for (unsigned j = 0; j < rt.nmask; ++j) { // clear the differences at the masked positions
+		const unsigned p = 2 * (k - 1 - rt.mpos[j]);
+#pragma unroll
+		for (int w = 0; w < KW; ++w)
+			if ((unsigned)w == (p >> 6))
+				x.w[w] &= ~(3ULL << (p & 63));
+	}
+	bool eq = true;
+#pragma unroll
+	for (int j = 0; j < KW; ++j)
+		eq &= x.w[j] == 0;
+	return eq;
+}
 
-/** A vertex: k-mer + rolling hash state (RollingBloomDBGVertex, RollingBloomDBG.h:33-159) */
+/** XOR of the hash terms of the masked positions (maskHash, BloomDBG/MaskedKmer... RollingHash.h:207-218 via
+ *  nthash.hpp:417-436): position i holds base km[i + shift] (shift = +1 / -1: the k-mer after a step right / left,
+ *  whose inner positions are all still present in km). */
+template <int KW>
+ABB_HD HashPair mask_corr(const Kmer<KW>& km, unsigned k, const RollTab& rt, int shift)
+{
+	HashPair c;
+	c.fh = c.rh = 0;
+	for (unsigned j = 0; j < rt.nmask; ++j) {
+		const unsigned i = rt.mpos[j];
+		const unsigned b = kmer_base(km, k, (unsigned)((int)i + shift));
+		c.fh ^= srol_n(seed_of(b), k - 1 - i);
+		c.rh ^= srol_n(seed_of(3 - b), i);
+	}
+	return c;
+}
+ABB_HD bool mask_is_care(const RollTab& rt, unsigned p)
+{
+	for (unsigned j = 0; j < rt.nmask; ++j)
+		if (rt.mpos[j] == p)
+			return false;
+	return true;
+}
+/** pathToSeq (bloom-dbg.h:131-158) writes only the '1' positions of each vertex, so with a spaced seed column c of
+ *  an n-vertex path stays 'N' when no vertex has a '1' over it.  The mask begins and ends with '1': only the columns
+ *  n..k-2 of a path shorter than k-1 vertices can be affected. */
+ABB_HD bool column_written(const RollTab& rt, unsigned k, unsigned n, unsigned c)
+{
+	if (rt.nmask == 0 || c < n || c + 1 >= k)
+		return true;
+	for (unsigned i = 0; i < n; ++i)
+		if (mask_is_care(rt, c - i))
+			return true;
+	return false;
+}
+ABB_HD uint64_t masked_canon(const HashPair& h, const HashPair& corr)
+{
+	const uint64_t f = h.fh ^ corr.fh, r = h.rh ^ corr.rh;
+	return r < f ? r : f;
+}
+
+/** reverse the 2-bit groups of a word */
+ABB_HD uint64_t rev2_u64(uint64_t x)
+{
+	x = ((x >> 2) & 0x3333333333333333ULL) | ((x & 0x3333333333333333ULL) << 2);
+	x = ((x >> 4) & 0x0F0F0F0F0F0F0F0FULL) | ((x & 0x0F0F0F0F0F0F0F0FULL) << 4);
+	x = ((x >> 8) & 0x00FF00FF00FF00FFULL) | ((x & 0x00FF00FF00FF00FFULL) << 8);
+	x = ((x >> 16) & 0x0000FFFF0000FFFFULL) | ((x & 0x0000FFFF0000FFFFULL) << 16);
+	return (x >> 32) | (x << 32);
+}
+/** packed reverse complement */
+template <int KW>
+ABB_HD Kmer<KW> kmer_revcomp(const Kmer<KW>& km, unsigned k)
+{
+	Kmer<KW> r;
+#pragma unroll
+	for (int j = 0; j < KW; ++j)
+		r.w[j] = ~rev2_u64(km.w[KW - 1 - j]); // complement of code c is 3 - c == ~c on two bits
+	// the k-mer now sits in the top 2k bits: shift it down
+	unsigned sh = 64u * KW - 2u * k;
+	while (sh >= 64) {
+#pragma unroll
+		for (int j = 0; j < KW - 1; ++j)
+			r.w[j] = r.w[j + 1];
+		r.w[KW - 1] = 0;
+		sh -= 64;
+	}
+	if (sh) {
+#pragma unroll
+		for (int j = 0; j < KW - 1; ++j)
+			r.w[j] = (r.w[j] >> sh) | (r.w[j + 1] << (64 - sh));
+		r.w[KW - 1] >>= sh;
+	}
+	return r;
+}
+/** LightweightKmer::isCanonical (BloomDBG/LightweightKmer.h:88-101): the k-mer is <= its reverse complement */
+template <int KW>
+ABB_HD bool kmer_is_canonical(const Kmer<KW>& km, unsigned k)
+{
+	const Kmer<KW> r = kmer_revcomp(km, k);
+	for (int j = KW - 1; j >= 0; --j)
+		if (km.w[j] != r.w[j])
+			return km.w[j] < r.w[j];
+	return true;
+}
+
+/** A vertex: k-mer + rolling hash state (RollingBloomDBGVertex, RollingBloomDBG.h:33-159).
+ *  mh is the value the Bloom filters are probed with (RollingHash::m_hash).  id is what vertex *identity* is decided
+ *  on (operator==, RollingBloomDBG.h:92-158): without a spaced seed the canonical hash again; with one, operator==
+ *  compares the '1' positions of the two k-mers after orienting each by its FULL k-mer (isCanonical looks at the
+ *  don't-care positions too), so two k-mers that agree on every '1' position can still be different vertices.  That
+ *  relation is exactly "equal masked forward hash of the full-canonical orientation", which is what id holds. */
 template <int KW>
 struct Vtx {
 	Kmer<KW> km;
-	HashPair h;
-	ABB_HD uint64_t canon() const { return h.canonical(); }
+	HashPair h;  // unmasked rolling state
+	uint64_t mh;
+	uint64_t id;
+	ABB_HD uint64_t canon() const { return id; }
+	ABB_HD uint64_t bloom() const { return mh; }
 };
+template <int KW>
+ABB_HD void vtx_rehash(Vtx<KW>& v, unsigned k, const RollTab& rt)
+{
+	if (rt.nmask == 0) {
+		v.mh = v.id = v.h.canonical();
+		return;
+	}
+	const HashPair c = mask_corr(v.km, k, rt, 0);
+	const uint64_t f = v.h.fh ^ c.fh, r = v.h.rh ^ c.rh;
+	v.mh = r < f ? r : f;
+	v.id = kmer_is_canonical(v.km, k) ? f : r;
+}
+/** Bloom hash of the neighbour of v in direction d with new base b, without building its k-mer */
+template <int KW>
+ABB_HD uint64_t neighbor_bloom(const Vtx<KW>& v, unsigned k, const RollTab& rt, Dir d, unsigned b)
+{
+	const HashPair h = d == FWD ? roll_right(v.h, rt, kmer_first(v.km, k), b) : roll_left(v.h, rt, kmer_last(v.km), b);
+	if (rt.nmask == 0)
+		return h.canonical();
+	return masked_canon(h, mask_corr(v.km, k, rt, d == FWD ? 1 : -1));
+}
+template <int KW>
+ABB_HD unsigned vtx_step(Vtx<KW>& v, unsigned k, const RollTab& rt, Dir d, unsigned b);
+/** identity of that neighbour */
+template <int KW>
+ABB_HD uint64_t neighbor_canon(const Vtx<KW>& v, unsigned k, const RollTab& rt, Dir d, unsigned b)
+{
+	if (rt.nmask == 0)
+		return neighbor_bloom(v, k, rt, d, b);
+	Vtx<KW> t = v;
+	vtx_step(t, k, rt, d, b);
+	return t.id;
+}
 
 /** Move to the neighbour in direction d with new base b; returns the base that fell off.
  *  (vertex.shift + setLastBase, RollingBloomDBG.h:56-70; RollingHash.h:88-128,175-193) */
@@ -130,6 +280,7 @@ ABB_HD unsigned vtx_step(Vtx<KW>& v, unsigned k, const RollTab& rt, Dir d, unsig
 		v.h = roll_left(v.h, rt, out, b);
 		kmer_prepend(v.km, k, b);
 	}
+	vtx_rehash(v, k, rt);
 	return out;
 }
 /** undo a vtx_step(d, .) that dropped `out` */
@@ -141,7 +292,7 @@ ABB_HD void vtx_unstep(Vtx<KW>& v, unsigned k, const RollTab& rt, Dir d, unsigne
 
 /** vertex of the k bases at s[0..k) given as 2-bit codes (NTC64 from scratch, nthash.hpp:220-239) */
 template <int KW>
-ABB_HD Vtx<KW> vtx_from_codes(const uint8_t* s, unsigned k, bool ascii)
+ABB_HD Vtx<KW> vtx_from_codes(const uint8_t* s, unsigned k, bool ascii, const RollTab& rt)
 {
 	Vtx<KW> v;
 #pragma unroll
@@ -157,6 +308,7 @@ ABB_HD Vtx<KW> vtx_from_codes(const uint8_t* s, unsigned k, bool ascii)
 		const unsigned c = ascii ? base_code(s[k - 1 - i]) : s[k - 1 - i];
 		v.h.rh = srol1(v.h.rh) ^ seed_of(3 - c);
 	}
+	vtx_rehash(v, k, rt);
 	return v;
 }
 
@@ -165,13 +317,11 @@ template <int KW>
 ABB_HD Vtx<KW> vtx_revcomp(const Vtx<KW>& v, unsigned k)
 {
 	Vtx<KW> r;
-#pragma unroll
-	for (int j = 0; j < KW; ++j)
-		r.km.w[j] = 0;
-	for (unsigned i = 0; i < k; ++i)
-		kmer_append(r.km, k, 3 - kmer_base(v.km, k, k - 1 - i));
+	r.km = kmer_revcomp(v.km, k);
 	r.h.fh = v.h.rh;
 	r.h.rh = v.h.fh;
+	r.mh = v.mh; // the mask is symmetric
+	r.id = v.id;
 	return r;
 }
 
@@ -631,7 +781,7 @@ ABB_HD Vtx<KW> rebuild_head(Ctx& c, const Vtx<KW>& start, const ByteVec& v, unsi
 		uint8_t tmp[kMaxK];
 		for (unsigned i = 0; i < k; ++i)
 			tmp[i] = d == FWD ? c.rd8(v.p + v.n - k + i) : c.rd8(v.p + v.n - 1 - i);
-		return vtx_from_codes<KW>(tmp, k, false);
+		return vtx_from_codes<KW>(tmp, k, false, c.rt);
 	}
 	for (unsigned i = from; i < v.n; ++i)
 		vtx_step(h, k, c.rt, d, c.rd8(v.p + i));
@@ -653,9 +803,7 @@ ABB_HD void make_tile(Ctx& c, const Vtx<KW>& m, Dir dir, TileRec* t, uint8_t* ba
 		t->lb_code = (uint8_t)lb;
 		t->lb_t = 0;
 		if (lb == ER_LENGTH_LIMIT) {
-			const HashPair th = dir == FWD ? roll_left(head.h, c.rt, kmer_last(head.km), b)
-			                               : roll_right(head.h, c.rt, kmer_first(head.km, c.k), b);
-			t->lb_t = th.canonical();
+			t->lb_t = neighbor_canon(head, c.k, c.rt, opposite(dir), b);
 		}
 	}
 	t->key = m.canon();
@@ -674,9 +822,7 @@ ABB_HD void make_tile(Ctx& c, const Vtx<KW>& m, Dir dir, TileRec* t, uint8_t* ba
 				t->stop_code = (uint8_t)ER_AMBI_IN;
 				break;
 			}
-			const HashPair th = dir == FWD ? roll_left(head.h, c.rt, kmer_last(head.km), b)
-			                               : roll_right(head.h, c.rt, kmer_first(head.km, c.k), b);
-			if (th.canonical() != prev_h) {
+			if (neighbor_canon(head, c.k, c.rt, opposite(dir), b) != prev_h) {
 				t->stop_kind = TS_CODE;
 				t->stop_code = (uint8_t)ER_AMBI_IN;
 				break;
@@ -738,9 +884,7 @@ ABB_HD ExtCode extend_dir(Ctx& c, Vtx<KW>& head, Dir dir, unsigned* psize, ByteV
 				if (r == ER_DEAD_END)
 					return ER_AMBI_IN;
 				// canonical hash of the unique predecessor t (hash only: no need to build its k-mer)
-				const HashPair th = dir == FWD ? roll_left(head.h, c.rt, kmer_last(head.km), b)
-				                               : roll_right(head.h, c.rt, kmer_first(head.km, c.k), b);
-				if (th.canonical() != prev_h) // we are on a tip rejoining the graph
+				if (neighbor_canon(head, c.k, c.rt, opposite(dir), b) != prev_h) // we are on a tip rejoining the graph
 					return ER_AMBI_IN;
 			}
 		}
@@ -898,6 +1042,7 @@ ABB_HD bool extend_seed(Ctx& c, const Vtx<KW>& seed, PathSet& ps, ContigOut* o)
 	// ---- trimBranchKmers (bloom-dbg.h:720-756) ----
 	unsigned l = psize;
 	bool pushed_front = false, pushed_back = false;
+	uint64_t second_id = 0, penult_id = 0;
 	{ // getContigType (bloom-dbg.h:629-644): is there an edge back -> front?
 		const unsigned om = c.neighbors(back) & 15;
 		bool edge = false;
@@ -909,14 +1054,17 @@ ABB_HD bool extend_seed(Ctx& c, const Vtx<KW>& seed, PathSet& ps, ContigOut* o)
 		if (edge && psize > 2) { // preprocessCircularContig (bloom-dbg.h:648-697)
 			Vtx<KW> v = front;
 			vtx_step(v, k, c.rt, REV, kmer_first(back.km, k)); // v.shift(ANTISENSE, back.getBase(0))
-			const bool circular = kmer_equal(v.km, back.km);
+			const bool circular = kmer_equal_masked(v.km, back.km, k, c.rt);
 			const bool branch_start = ambiguous(c, front, FWD) || ambiguous(c, front, REV);
 			const bool branch_end = ambiguous(c, back, FWD) || ambiguous(c, back, REV);
 			if (branch_start && !branch_end) {
 				// push_back(front) / push_back(rc(front)): pathToSeq lets the last k-mer overwrite its k columns
 				const Vtx<KW> x = circular ? front : vtx_revcomp(front, k);
+				// (with a spaced seed only its '1' positions are written; the others are columns of earlier vertices)
 				for (unsigned i = 0; i < k; ++i)
-					c.wr8(s + (l - 1) + 1 + i, (uint8_t)kmer_base(x.km, k, i));
+					if (mask_is_care(c.rt, i))
+						c.wr8(s + (l - 1) + 1 + i, (uint8_t)kmer_base(x.km, k, i));
+				penult_id = back.canon();
 				back = x;
 				pushed_back = true;
 				++l;
@@ -925,6 +1073,7 @@ ABB_HD bool extend_seed(Ctx& c, const Vtx<KW>& seed, PathSet& ps, ContigOut* o)
 				const Vtx<KW> x = circular ? back : vtx_revcomp(back, k);
 				--s;
 				c.wr8(s, (uint8_t)kmer_first(x.km, k));
+				second_id = front.canon();
 				front = x;
 				pushed_front = true;
 				++l;
@@ -932,13 +1081,26 @@ ABB_HD bool extend_seed(Ctx& c, const Vtx<KW>& seed, PathSet& ps, ContigOut* o)
 			c.sync();
 		}
 	}
-	// path[1] and path[l-2] read back from the overlay: the old front occupies columns 1..k after a
-	// push_front, and a pushed back vertex is a consistent edge (back -> front, or back -> rc(front)
-	// in a hairpin), so it leaves the old back's columns unchanged
-	const Vtx<KW> second = vtx_from_codes<KW>(s + 1, k, false);
-	const Vtx<KW> penult = vtx_from_codes<KW>(s + (l - 2), k, false);
-	const bool amb1 = ambiguous_expected(c, front, second.canon(), FWD);
-	const bool amb2 = ambiguous_expected(c, back, penult.canon(), REV);
+	// path[1] and path[l-2]: the vertices next to a pushed one are the old ends; otherwise they are read back from
+	// the string (a path of consecutive k-mers spells its vertices exactly, don't-care positions included)
+	if (!pushed_front)
+		second_id = vtx_from_codes<KW>(s + 1, k, false, c.rt).canon();
+	if (!pushed_back)
+		penult_id = vtx_from_codes<KW>(s + (l - 2), k, false, c.rt).canon();
+	const bool amb1 = ambiguous_expected(c, front, second_id, FWD);
+	const bool amb2 = ambiguous_expected(c, back, penult_id, REV);
+	if (c.rt.nmask && pushed_front && !amb1) {
+		// spaced seed, pathToSeq: a '1' position of the pushed front vertex survives where no later vertex writes the
+		// column (columns <= l-1 are position 0 of a later vertex)
+		for (unsigned p = l; p < k; ++p) {
+			bool later = !mask_is_care(c.rt, p);
+			for (unsigned j = 1; j < l && !later; ++j)
+				later = mask_is_care(c.rt, p - j);
+			if (!later)
+				c.wr8(s + p, (uint8_t)kmer_base(front.km, k, p));
+		}
+		c.sync();
+	}
 	unsigned begin = 0, end = l + k - 1;
 	if (amb1) {
 		++begin;
@@ -978,7 +1140,7 @@ ABB_HD bool walk_read(Ctx& c, const uint8_t* read_ascii, unsigned L, Emit& emit)
 	if (!rh || !cov)
 		return false;
 	{ // seqToPath (bloom-dbg.h:115-125): canonical hash of every read k-mer
-		Vtx<KW> v = vtx_from_codes<KW>(read_ascii, k, true);
+		Vtx<KW> v = vtx_from_codes<KW>(read_ascii, k, true, c.rt);
 		c.wr64(rh, v.canon());
 		for (unsigned i = 1; i < nk; ++i) {
 			vtx_step(v, k, c.rt, FWD, base_code(read_ascii[i + k - 1]) & 3);
@@ -986,7 +1148,7 @@ ABB_HD bool walk_read(Ctx& c, const uint8_t* read_ascii, unsigned L, Emit& emit)
 		}
 		c.sync();
 	}
-	Vtx<KW> rv = vtx_from_codes<KW>(read_ascii, k, true);
+	Vtx<KW> rv = vtx_from_codes<KW>(read_ascii, k, true, c.rt);
 	unsigned ri = 0;
 	for (unsigned i = 0; i < nk; ++i) {
 		if (c.rd8(cov + i)) // assembledKmers.find(*it) != end

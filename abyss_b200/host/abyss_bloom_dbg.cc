@@ -273,10 +273,44 @@ int main(int argc, char** argv)
 		std::cerr << PROGRAM ": -g, -C, -T and --checkpoint are not supported by the B200 implementation\n";
 		exit(EXIT_FAILURE);
 	}
-	if (params.K > 0 || params.qrSeedLen > 0 || !params.spacedSeed.empty()) {
-		std::cerr << PROGRAM ": spaced seeds are not supported by the unitig extension stage yet\n";
-		exit(EXIT_FAILURE);
-	}
+	/* initGlobals (bloom-dbg.cc:215-233) + MaskedKmer::setMask (BloomDBG/MaskedKmer.h:25-48), once k is known */
+	auto spacedSeedMask = [&]() {
+		std::string mask;
+		const unsigned k = params.k;
+		if (params.K > 0) { // SpacedSeed::kmerPair (BloomDBG/SpacedSeed.h:30-37)
+			mask.assign(k, '0');
+			std::fill(mask.begin(), mask.begin() + params.K, '1');
+			std::fill(mask.rbegin(), mask.rbegin() + params.K, '1');
+		} else if (params.qrSeedLen > 0) { // qrSeedPair (SpacedSeed.h:55-95): a quadratic-residue seed and its mirror image
+			const unsigned len = params.qrSeedLen;
+			std::string qr(len, '1');
+			for (size_t i = 0; i < len; ++i)
+				for (size_t j = 1; j < len; ++j)
+					if (j * j % len == i) {
+						qr[i] = '0';
+						break;
+					}
+			mask.assign(k, '0');
+			for (unsigned i = 0; i < len; ++i)
+				mask[i] = mask[k - 1 - i] = qr[i];
+		} else
+			mask = params.spacedSeed;
+		if (mask.empty())
+			return mask;
+		if (mask.size() != k) {
+			std::cerr << "error: spaced seed must be exactly k bits long\n";
+			exit(EXIT_FAILURE);
+		} else if (mask.find_first_not_of("01") != std::string::npos) {
+			std::cerr << "error: spaced seed must contain only '0's or '1's\n";
+			exit(EXIT_FAILURE);
+		} else if (mask.front() != '1' || mask.back() != '1') {
+			std::cerr << "error: spaced seed must begin and end with '1's\n";
+			exit(EXIT_FAILURE);
+		}
+		if (params.verbose)
+			std::cerr << "Using spaced seed " << mask << "\n";
+		return mask;
+	};
 
 	/* the `:' separator: files before it load the filter, files after it are assembled (BloomIO.h:104-113) */
 	std::vector<std::string> loadFiles, asmFiles;
@@ -317,7 +351,10 @@ int main(int argc, char** argv)
 		params.bloomSize = h.sizeInBytes;
 		if (params.trim == UINT_MAX)
 			params.trim = params.k;
-		check(abb_filter_create(&bloom, ABB_COUNTING, h.size, h.hashNum, h.kmerSize, params.minCov, "", params.device), "filter");
+		if (params.verbose)
+			std::cerr << "Assembling with k-mer size " << params.k << "\n";
+		const std::string mask = spacedSeedMask();
+		check(abb_filter_create(&bloom, ABB_COUNTING, h.size, h.hashNum, h.kmerSize, params.minCov, mask.c_str(), params.device), "filter");
 		check(abb_filter_upload(bloom, 0, raw.data(), raw.size()), "upload");
 		printCountingBloomStats(bloom, std::cerr);
 	} else {
@@ -328,7 +365,8 @@ int main(int argc, char** argv)
 		uint64_t counters = (uint64_t)std::llround(sz);
 		if (counters % 64)
 			counters += 64 - counters % 64;
-		check(abb_filter_create(&bloom, ABB_COUNTING, counters, params.numHashes, params.k, params.minCov, "", params.device), "filter");
+		const std::string mask = spacedSeedMask();
+		check(abb_filter_create(&bloom, ABB_COUNTING, counters, params.numHashes, params.k, params.minCov, mask.c_str(), params.device), "filter");
 		uint64_t readCount = 0;
 		for_each_batch(loadFiles, [&](ReadBatch& b) {
 			check(abb_insert_reads(bloom, b.bases.data(), b.offsets.data(), b.size(), nullptr), "insert");

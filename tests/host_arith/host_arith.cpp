@@ -10,6 +10,7 @@ extern "C" {
 #include <cstdlib>
 #include <random>
 #include <string>
+#include <vector>
 using namespace abb;
 
 static int fails = 0;
@@ -49,7 +50,7 @@ int main(int argc, char** argv)
 		uint64_t fh, rh;
 		abo_base_hash(s.data(), k, &fh, &rh);
 		HashPair h = { fh, rh };
-		Vtx<6> v = vtx_from_codes<6>((const uint8_t*)s.data(), k, true);
+		Vtx<6> v = vtx_from_codes<6>((const uint8_t*)s.data(), k, true, rt);
 		CHECK(v.h.fh == fh && v.h.rh == rh);
 		for (unsigned i = 0; i + k < s.size(); ++i) { // roll right along the string, and check rolling back left
 			abo_roll_right(&fh, &rh, k, (unsigned char)s[i], (unsigned char)s[i + k]);
@@ -67,6 +68,37 @@ int main(int argc, char** argv)
 		CHECK(rc.h.fh == v.h.rh && rc.h.rh == v.h.fh && rc.canon() == v.canon());
 		const Vtx<6> rr = vtx_revcomp(rc, k);
 		CHECK(kmer_equal(rr.km, v.km));
+		{ // the packed reverse complement against the base-by-base definition, and isCanonical (string order)
+			const std::string tail = s.substr(s.size() - k);
+			std::string rcs(tail.rbegin(), tail.rend());
+			for (auto& c : rcs)
+				c = c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : 'A';
+			bool same = true;
+			for (unsigned i = 0; i < k; ++i)
+				same &= kmer_base(rc.km, k, i) == base_code(rcs[i]) && kmer_base(v.km, k, i) == base_code(tail[i]);
+			CHECK(same);
+			CHECK(kmer_is_canonical(v.km, k) == (tail <= rcs));
+			// spaced seed: hash of the '1' positions only, from the rolled state (maskHash, nthash.hpp:417-436)
+			std::string mask(k, '1');
+			std::vector<uint8_t> mpos;
+			for (unsigned i = 1; i + 1 < k; ++i)
+				if ((i * 7 + k) % 3 == 0) {
+					mask[i] = '0';
+					mpos.push_back((uint8_t)i);
+				}
+			RollTab mrt = rt;
+			mrt.nmask = (unsigned)mpos.size();
+			mrt.mpos = mpos.data();
+			Vtx<6> mv = v;
+			vtx_rehash(mv, k, mrt);
+			uint64_t hs[1];
+			CHECK(abo_hash_seq(tail.data(), k, k, 1, mask.c_str(), hs, NULL) == 1 && hs[0] == mv.bloom());
+			if (k > 2) {
+				const std::string nxt = tail.substr(1) + "G", prv = "C" + tail.substr(0, k - 1);
+				CHECK(abo_hash_seq(nxt.data(), k, k, 1, mask.c_str(), hs, NULL) == 1 && hs[0] == neighbor_bloom(mv, k, mrt, FWD, 2));
+				CHECK(abo_hash_seq(prv.data(), k, k, 1, mask.c_str(), hs, NULL) == 1 && hs[0] == neighbor_bloom(mv, k, mrt, REV, 1));
+			}
+		}
 	}
 	// base codes
 	CHECK(base_code('A') == 0 && base_code('c') == 1 && base_code('G') == 2 && base_code('t') == 3 && base_code('N') == 4 &&

@@ -27,6 +27,7 @@ using namespace abb;
 struct HostCtx {
 	unsigned k, trim, H, threshold;
 	RollTab rt;
+	const char* mask = nullptr; // spaced seed (HOST_WALK_MASK)
 	HashCfg cfg;
 	const uint8_t* counters;
 	Frame* frames;
@@ -48,8 +49,7 @@ struct HostCtx {
 		++probes;
 		unsigned m = 0;
 		for (unsigned n = 0; n < 8; ++n) {
-			HashPair h = n < 4 ? roll_right(v.h, rt, kmer_first(v.km, k), n) : roll_left(v.h, rt, kmer_last(v.km), n - 4);
-			if (contains(h.canonical()))
+			if (contains(neighbor_bloom(v, k, rt, n < 4 ? FWD : REV, n & 3)))
 				m |= 1u << n;
 		}
 		return m;
@@ -195,9 +195,12 @@ struct Assembly {
 	void operator()(HostCtx&, unsigned, const ContigOut& o)
 	{
 		Collected x;
+		if (getenv("HOST_WALK_DEBUG"))
+			fprintf(stderr, "contig: len %u psize %u left %u right %u tip %d\n", o.len, o.psize, (unsigned)o.left, (unsigned)o.right, (int)o.tip);
 		x.seq.assign(o.len, 'N');
 		for (unsigned i = 0; i < o.len; ++i)
-			x.seq[i] = "ACGT"[o.seq[i]];
+			if (column_written(c->rt, c->k, o.len - c->k + 1, i))
+				x.seq[i] = "ACGT"[o.seq[i]];
 		x.pushed_front = o.pushed_front; x.pushed_back = o.pushed_back;
 		x.popped_front = o.popped_front; x.popped_back = o.popped_back;
 		x.front_h = o.front_h; x.back_h = o.back_h;
@@ -207,7 +210,7 @@ struct Assembly {
 	{
 		const unsigned k = c->k;
 		std::vector<uint64_t> tmp((seq.size() - k + 1) * c->H), hs(seq.size() - k + 1);
-		size_t n = abo_hash_seq(seq.data(), seq.size(), k, c->H, NULL, tmp.data(), NULL);
+		size_t n = abo_hash_seq(seq.data(), seq.size(), k, c->H, c->mask, tmp.data(), NULL);
 		if (n != hs.size()) { fprintf(stderr, "host_walk: contig hashing mismatch\n"); exit(3); }
 		for (size_t i = 0; i < n; ++i)
 			hs[i] = tmp[i * c->H];
@@ -228,6 +231,23 @@ struct Assembly {
 			return true;
 		return false;
 	}
+	/** identity of outputContig's end vertices v1/v2 (bloom-dbg.h:556-564): the k-mer string is canonicalized as a
+	 *  string ('N' columns included), and operator== then compares the '1' positions */
+	uint64_t end_identity(const std::string& kmer, uint64_t h0) const
+	{
+		if (!c->mask)
+			return h0;
+		const unsigned k = c->k;
+		std::string rc(kmer.rbegin(), kmer.rend());
+		for (auto& ch : rc)
+			ch = ch == 'A' ? 'T' : ch == 'C' ? 'G' : ch == 'G' ? 'C' : ch == 'T' ? 'A' : ch;
+		const std::string& cs = rc < kmer ? rc : kmer;
+		uint64_t f = 0;
+		for (unsigned i = 0; i < k; ++i)
+			if (c->mask[i] == '1')
+				f ^= srol_n(seed_of(base_code((uint8_t)cs[i])), k - 1 - i);
+		return f;
+	}
 	// outputContig (bloom-dbg.h:538-620)
 	void output(const Collected& x)
 	{
@@ -236,17 +256,18 @@ struct Assembly {
 		struct { unsigned len; } o = { (unsigned)seq.size() };
 		std::vector<uint64_t> hs(o.len - k + 1);
 		std::vector<uint64_t> tmp(hs.size() * c->H);
-		size_t n = abo_hash_seq(seq.data(), seq.size(), k, c->H, NULL, tmp.data(), NULL);
+		size_t n = abo_hash_seq(seq.data(), seq.size(), k, c->H, c->mask, tmp.data(), NULL);
 		if (n != hs.size()) { fprintf(stderr, "host_walk: contig hashing mismatch\n"); exit(3); }
 		for (size_t i = 0; i < n; ++i)
 			hs[i] = tmp[i * c->H];
 		bool redundant = false;
 		if (o.len < k + kFpTrim - 1) {
-			if (contigEnd.count(hs.front()) && contigEnd.count(hs.back()))
+			const uint64_t e1 = end_identity(seq.substr(0, k), hs.front()), e2 = end_identity(seq.substr(seq.size() - k), hs.back());
+			if (contigEnd.count(e1) && contigEnd.count(e2))
 				redundant = true;
 			else {
-				contigEnd.insert(hs.front());
-				contigEnd.insert(hs.back());
+				contigEnd.insert(e1);
+				contigEnd.insert(e2);
 			}
 		} else {
 			redundant = true;
@@ -287,13 +308,27 @@ static int run(unsigned k, unsigned kc, unsigned H, uint64_t m, unsigned trim, c
 			seqs.push_back(l2);
 		}
 	}
+	const char* mask = getenv("HOST_WALK_MASK");
+	if (mask && !mask[0])
+		mask = nullptr;
+	if (mask && strlen(mask) != k) {
+		fprintf(stderr, "host_walk: HOST_WALK_MASK must have k characters\n");
+		return 2;
+	}
 	std::vector<uint8_t> counters(m, 0);
 	for (auto& s : seqs)
-		abo_cbf_load_seq(counters.data(), m, s.data(), s.size(), k, H, NULL);
+		abo_cbf_load_seq(counters.data(), m, s.data(), s.size(), k, H, mask);
 
 	HostCtx c;
 	c.k = k; c.trim = trim; c.H = H; c.threshold = kc;
 	c.rt = make_rolltab(k);
+	c.mask = mask;
+	std::vector<uint8_t> mpos;
+	for (unsigned i = 0; mask && i < k; ++i)
+		if (mask[i] == '0')
+			mpos.push_back((uint8_t)i);
+	c.rt.nmask = (unsigned)mpos.size();
+	c.rt.mpos = mpos.data();
 	c.cfg.H = H; c.cfg.k = k; c.cfg.mod = make_fastmod(m);
 	for (unsigned i = 0; i < kMaxHashes; ++i)
 		c.cfg.mult[i] = (uint64_t)i ^ ((uint64_t)k * kMultiSeed);
@@ -314,8 +349,8 @@ static int run(unsigned k, unsigned kc, unsigned H, uint64_t m, unsigned trim, c
 			for (size_t j = 0; j + k <= s.size(); ++j) {
 				if (s.find_first_not_of("ACGT", j) < j + k)
 					continue;
-				Vtx<KW> v = vtx_from_codes<KW>((const uint8_t*)s.data() + j, k, true);
-				if (!is_marker(v.canon()) || !c.contains(v.canon()) || !seen.insert(v.canon()).second)
+				Vtx<KW> v = vtx_from_codes<KW>((const uint8_t*)s.data() + j, k, true, c.rt);
+				if (!is_marker(v.canon()) || !c.contains(v.bloom()) || !seen.insert(v.canon()).second)
 					continue;
 				const Vtx<KW> rc = vtx_revcomp(v, k);
 				for (int w = 0; w < 4; ++w) {
@@ -367,14 +402,14 @@ static int run(unsigned k, unsigned kc, unsigned H, uint64_t m, unsigned trim, c
 			code = RC_NON_ACGT;
 		else {
 			// hasBluntEnd (bloom-dbg.h:494-532)
-			Vtx<KW> first = vtx_from_codes<KW>((const uint8_t*)s.data(), k, true);
-			Vtx<KW> last = vtx_from_codes<KW>((const uint8_t*)s.data() + s.size() - k, k, true);
+			Vtx<KW> first = vtx_from_codes<KW>((const uint8_t*)s.data(), k, true, c.rt);
+			Vtx<KW> last = vtx_from_codes<KW>((const uint8_t*)s.data() + s.size() - k, k, true, c.rt);
 			bool blunt = !look_ahead(c, first, REV, kFpTrim) || !look_ahead(c, vtx_revcomp(last, k), REV, kFpTrim);
 			if (blunt)
 				code = RC_BLUNT_END;
 			else {
 				std::vector<uint64_t> tmp((s.size() - k + 1) * H);
-				size_t n = abo_hash_seq(s.data(), s.size(), k, H, NULL, tmp.data(), NULL);
+				size_t n = abo_hash_seq(s.data(), s.size(), k, H, c.mask, tmp.data(), NULL);
 				hs.resize(n);
 				for (size_t i = 0; i < n; ++i)
 					hs[i] = tmp[i * H];

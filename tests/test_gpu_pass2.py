@@ -73,6 +73,43 @@ def test_cycles_hairpins_tandems(abb, golden_dir, case):
     assert fasta == open(os.path.join(golden_dir, case["name"] + ".fa")).read()
 
 
+MASK_CASES = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "mask_cases.json")))
+
+
+@pytest.mark.parametrize("case", MASK_CASES, ids=lambda c: c["name"])
+def test_spaced_seeds_identical_to_reference(abb, golden_dir, case):
+    # -K / --qr-seed / -s: the spaced seed changes the hash (pass 1 and every Bloom probe), vertex identity
+    # (RollingBloomDBGVertex::compare orients by the full k-mer) and pathToSeq ('N' where no vertex writes a column)
+    from abyss_b200.capi import bloom_dbg, fixed_length_reads, kmer_pair_seed, qr_seed_pair, READ_CODES
+    if case["opt"].startswith("-K"):
+        assert kmer_pair_seed(case["k"], int(case["opt"][2:])) == case["mask"]
+    else:
+        assert qr_seed_pair(case["k"], int(case["opt"].split("=")[1])) == case["mask"]
+    if case["reads"].endswith(".gz"):
+        ids, seqs = _read_fasta_gz(os.path.join(golden_dir, case["reads"]))
+    else:
+        _, rs = load_case(golden_dir, case["reads"])
+        ids = [rs.read_id(i) for i in range(rs.n)]
+        seqs = fixed_length_reads(rs.ascii(0, rs.n))
+    fasta, codes = bloom_dbg(ids, seqs, case["k"], case["kc"], case["H"], counters=case["counters"], mask=case["mask"],
+                             read_log=True)
+    want = open(os.path.join(golden_dir, case["name"] + ".fa")).read()
+    assert fasta.count(">") == case["n_contigs"]
+    assert fasta == want
+    if case.get("readlog"):
+        log = open(os.path.join(golden_dir, case["name"] + ".readlog.tsv")).read().split("\n")[1:-1]
+        assert [f"{ids[i]}\t{READ_CODES[codes[i]]}" for i in range(len(ids))] == log
+
+
+def test_spaced_seed_validation(abb):
+    from abyss_b200.capi import Filter, Assembler, AbbError
+    for bad in ("0" + "1" * 30 + "0", "1" * 20 + "0" * 11 + "1"):  # must begin/end with '1'; must be symmetric
+        f = Filter.counting(4096, 4, 32, 2, mask=bad)
+        with pytest.raises(AbbError):
+            Assembler(f)
+        f.close()
+
+
 def test_tiles_on_off_same_output(abb, golden_dir, monkeypatch):
     from abyss_b200.capi import fixed_length_reads, bloom_dbg
     c, rs = load_case(golden_dir, "e2e_g20k_k32")
