@@ -100,6 +100,18 @@ int main(int argc, char** argv)
 			}
 		}
 	}
+	{ // pathToSeq with the mask 10001: ACGTA, CGTAC -> ACNNAC (Unittest/BloomDBG/BloomDBGTest.cpp:24-37)
+		const uint8_t mp[3] = { 1, 2, 3 };
+		RollTab rt = make_rolltab(5);
+		rt.nmask = 3;
+		rt.mpos = mp;
+		std::string out = "ACGTAC";
+		for (unsigned c = 0; c < 6; ++c)
+			if (!column_written(rt, 5, 2, c))
+				out[c] = 'N';
+		CHECK(out == "ACNNAC");
+		CHECK(column_written(rt, 5, 4, 4) && column_written(rt, 5, 4, 3) && !column_written(rt, 5, 3, 3)); // k-1 vertices or more: every column written
+	}
 	// base codes
 	CHECK(base_code('A') == 0 && base_code('c') == 1 && base_code('G') == 2 && base_code('t') == 3 && base_code('N') == 4 &&
 	      base_code('U') == 4 && base_code(0) == 4);

@@ -68,3 +68,27 @@ def test_cli_errors(cases):
     assert r.returncode != 0 and "missing mandatory option `-k'" in r.stderr
     r = subprocess.run([exe, "-b1M", "-k32"], capture_output=True, text=True)
     assert r.returncode != 0 and "missing input file arguments" in r.stderr
+
+
+@pytest.mark.parametrize("name", ["mask_g20k_K20", "mask_g20k_qr11", "mask_g10k_K5"])
+def test_abyss_bloom_dbg_cli_spaced_seed(cases, name):
+    # -K / --qr-seed through the option parser (bloom-dbg.cc:420-460, initGlobals :215-233)
+    mc = {c["name"]: c for c in json.load(open(os.path.join(ROOT, "tests", "golden", "mask_cases.json")))}[name]
+    _, fq, d = cases[mc["reads"]]
+    fa = str(d / (name + ".fa"))
+    r = subprocess.run([os.path.join(BIN, "abyss-bloom-dbg"), f"-k{mc['k']}", mc["opt"], f"--kc={mc['kc']}", f"-b{mc['b']}", f"-H{mc['H']}",
+                        "-v", "-o", fa, fq], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert f"Using spaced seed {mc['mask']}" in r.stderr
+    assert open(fa).read() == open(os.path.join(ROOT, "tests", "golden", name + ".fa")).read()
+    # the same pattern given literally with -s
+    r = subprocess.run([os.path.join(BIN, "abyss-bloom-dbg"), f"-k{mc['k']}", "-s", mc["mask"], f"--kc={mc['kc']}", f"-b{mc['b']}",
+                        f"-H{mc['H']}", fq], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == open(os.path.join(ROOT, "tests", "golden", name + ".fa")).read()
+
+
+def test_abyss_bloom_dbg_cli_bad_seed(cases):
+    _, fq, _ = cases["e2e_g20k_k32"]
+    r = subprocess.run([os.path.join(BIN, "abyss-bloom-dbg"), "-k32", "--qr-seed=16", "-b1M", fq], capture_output=True, text=True)
+    assert r.returncode != 0 and "spaced seed must begin and end with '1's" in r.stderr  # the reference's message for this k

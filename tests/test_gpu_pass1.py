@@ -220,3 +220,30 @@ def test_large_roundtrip_properties(abb):
         assert f.minCount(np.stack(hh, axis=1)).min() >= 1
         f.close()
     assert digests[0] == digests[1]
+
+
+def test_reference_unit_test_vectors(abb):
+    # Unittest/BloomDBG/CountingBloomFilterTest.cpp:9-46 (threshold semantics on the four 16-mers) and
+    # Unittest/BloomDBG/RollingBloomDBGTest.cpp (X-graph CGACT,TGACT -> GACTC -> ACTCT,ACTCG; k=5, H=2):
+    # the neighbours of every vertex as the extension kernels see them (shift + A,C,G,T + contains)
+    a, b, c, d = "AGATGTGCTGCCGCCT", "TGGACAGCGTTACCTC", "TAATAACAGTCCCTAT", "GATCGTGGCGGGCGAT"
+    f = abb.Filter.counting(1000, 1, 16, threshold=2)
+    f.insert_reads([a, a, b])
+    h0, valid, _ = abb.hash_reads(16, [a, b, c, d])
+    assert valid.all()
+    assert f.minCount(h0.reshape(-1, 1)).tolist() == [2, 1, 0, 0]
+    assert f.contains(h0.reshape(-1, 1)).tolist() == [True, False, False, False]
+    f.close()
+    kmers = ["CGACT", "TGACT", "GACTC", "ACTCT", "ACTCG"]
+    g = abb.Filter.counting(100000, 2, 5, threshold=1)
+    g.insert_reads(kmers)
+    edges = {"CGACT": ("", "C"), "TGACT": ("", "C"), "GACTC": ("CT", "GT"), "ACTCT": ("G", ""), "ACTCG": ("G", "")}
+    for v, (ins, outs) in edges.items():
+        cand = [x + v[:-1] for x in "ACGT"] + [v[1:] + x for x in "ACGT"]
+        h, ok, _ = abb.hash_reads(5, cand)
+        H = np.stack([h, (h * np.uint64(1 ^ ((5 * 0x90b45d39fb6da1fa) & (2**64 - 1))))], axis=1)
+        H[:, 1] ^= H[:, 1] >> np.uint64(27)  # NTE64, nthash.hpp:337-342
+        got = g.contains(H)
+        want = [x in ins for x in "ACGT"] + [x in outs for x in "ACGT"]
+        assert got.tolist() == want, v
+    g.close()

@@ -92,3 +92,26 @@ def test_counter_sizing(oracle):
     assert oracle.lib.abo_counters_for_budget(GiB) == 954437184
     assert oracle.lib.abo_counters_for_budget(8 * GiB) == 7635497472
     assert oracle.lib.abo_counters_for_budget(64 * GiB) == 61083979328
+
+
+def test_spaced_seed_known_answers():
+    # Unittest/BloomDBG/SpacedSeedTest.cpp:16,25 (host-side mirror of SpacedSeed::qrSeed / qrSeedPair / kmerPair)
+    from abyss_b200.capi import kmer_pair_seed, qr_seed_pair
+    assert qr_seed_pair(22, 11)[:11] == "10100011101"
+    assert qr_seed_pair(33, 11) == "101000111010000000000010111000101"
+    assert kmer_pair_seed(10, 3) == "1110000111"
+    with pytest.raises(ValueError):
+        qr_seed_pair(33, 10)
+    with pytest.raises(ValueError):
+        kmer_pair_seed(10, 6)
+
+
+def test_threshold_semantics_known_answer(oracle):
+    # Unittest/BloomDBG/CountingBloomFilterTest.cpp:9-46: size 1000, H=1, threshold 2, the four 16-mers a..d;
+    # a inserted twice and b once: only a passes the threshold
+    a, b, c, d = "AGATGTGCTGCCGCCT", "TGGACAGCGTTACCTC", "TAATAACAGTCCCTAT", "GATCGTGGCGGGCGAT"
+    counters = np.zeros(1000, dtype=np.uint8)
+    oracle.cbf_load(counters, [a, a, b], 16, 1)
+    mn = lambda s: int(oracle.cbf_min_hashes(counters, oracle.hash_seq(s, 16, 1)[0])[0])
+    assert mn(a) == 2 and mn(b) == 1 and mn(c) == 0 and mn(d) == 0
+    assert np.count_nonzero(counters) == 2 and np.count_nonzero(counters >= 2) == 1
