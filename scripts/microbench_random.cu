@@ -56,6 +56,11 @@ int main(int argc, char** argv) {
 	uint64_t m = argc > 1 ? strtoull(argv[1], 0, 10) : 7635497472ULL;
 	uint64_t n = argc > 2 ? strtoull(argv[2], 0, 10) : (1ULL << 28);
 	uint8_t* a; unsigned long long* sink;
+	if (const char* env = getenv("L2FETCH")) // cudaLimitMaxL2FetchGranularity: 32, 64 or 128
+		CK(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(env)));
+	size_t gran = 0;
+	CK(cudaDeviceGetLimit(&gran, cudaLimitMaxL2FetchGranularity));
+	printf("cudaLimitMaxL2FetchGranularity = %zu\n", gran);
 	CK(cudaMalloc(&a, m)); CK(cudaMemset(a, 0, m)); CK(cudaMalloc(&sink, 8));
 	printf("array %.2f GB, %llu k-mers per launch\n", m / 1e9, (unsigned long long)n);
 	run<4, 0, 1>("read-only", a, m, n, sink);
