@@ -60,7 +60,7 @@ def build_cli() -> None:
     """the C++ host programs (abyss-bloom-dbg, abyss-bloom) that link the C-ABI library"""
     host = os.path.join(ROOT, "host")
     for exe, src in (("abyss-bloom-dbg", "abyss_bloom_dbg.cc"), ("abyss-bloom", "abyss_bloom.cc")):
-        cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-o", os.path.join(LIBDIR, exe), os.path.join(host, src),
+        cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-pthread", "-o", os.path.join(LIBDIR, exe), os.path.join(host, src),
                "-L" + LIBDIR, "-labyssb200", "-Wl,-rpath,$ORIGIN"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:

@@ -78,7 +78,6 @@ int main(int argc, char** argv)
 			exit(EXIT_FAILURE);
 		}
 	}
-	(void)threads;
 	ropt.chastityFilter = chastity;
 	ropt.trimMasked = trimMasked;
 	ropt.qualityOffset = illuminaQ ? 64 : 0;
@@ -111,29 +110,16 @@ int main(int argc, char** argv)
 			levelBits += 64 - levelBits % 64;
 		check(abb_filter_create(&f, ABB_CASCADING, levelBits, numHashes, k, levels, "", device), "filter");
 	}
-	ReadBatch batch;
-	std::string id, seq;
 	uint64_t readCount = 0;
-	auto flush = [&]() {
-		if (!batch.size())
-			return;
-		check(abb_insert_reads(f, batch.bases.data(), batch.offsets.data(), batch.size(), nullptr), "insert");
-		readCount += batch.size();
-		if (verbose)
-			std::cerr << "Loaded " << readCount << " reads into Bloom filter\n";
-		batch.clear();
-	};
-	for (const auto& path : files) {
-		if (verbose)
-			std::cerr << "Reading `" << path << "'...\n";
-		SeqReader in(path, ropt);
-		while (in.next(id, seq)) {
-			batch.add(id, seq);
-			if (batch.size() >= batchReads)
-				flush();
+	{
+		host::BatchStream stream(files, ropt, batchReads, threads > 1 ? threads : 0, verbose != 0);
+		while (const ReadBatch* batch = stream.next()) {
+			check(abb_insert_reads(f, batch->bases.data(), batch->offsets.data(), batch->size(), nullptr), "insert");
+			readCount += batch->size();
+			if (verbose)
+				std::cerr << "Loaded " << readCount << " reads into Bloom filter\n";
 		}
 	}
-	flush();
 	if (verbose) {
 		uint64_t nz = 0, th = 0;
 		check(abb_filter_popcount(f, &nz, &th), "popcount");

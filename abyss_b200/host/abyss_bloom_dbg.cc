@@ -72,7 +72,7 @@ static const char USAGE_MESSAGE[] =
     "      --help                   display this help and exit\n"
     "  -H  --num-hashes=N           number of Bloom filter hash functions [4]\n"
     "  -i  --input-bloom=FILE       load Bloom filter from FILE\n"
-    "  -j, --threads=N              accepted for compatibility (the GPU does the work) [1]\n"
+    "  -j, --threads=N              host threads that parse the input files [up to 8]\n"
     "      --trim-masked            trim masked bases from the ends of reads [default]\n"
     "      --no-trim-masked         do not trim masked bases from the ends of reads\n"
     "  -k, --kmer=N                 the size of a k-mer [<=192]\n"
@@ -159,25 +159,14 @@ static void printCountingBloomStats(abb_filter* f, std::ostream& os)
 	   << "\n";
 }
 
+/** batches of --batch-reads reads, parsed by background threads while the GPU works on the previous batch */
 template <typename Fn>
 static void for_each_batch(const std::vector<std::string>& files, Fn fn)
 {
-	ReadBatch batch;
-	std::string id, seq;
-	for (const auto& path : files) {
-		if (params.verbose)
-			std::cerr << "Reading `" << path << "'...\n";
-		SeqReader in(path, ropt);
-		while (in.next(id, seq)) {
-			batch.add(id, seq);
-			if (batch.size() >= params.batchReads) {
-				fn(batch);
-				batch.clear();
-			}
-		}
-	}
-	if (batch.size())
-		fn(batch);
+	// -j N (N > 1) sets the number of parsing threads; otherwise up to 8 of the host's cores
+	host::BatchStream stream(files, ropt, params.batchReads, params.threads > 1 ? params.threads : 0, params.verbose != 0);
+	while (const ReadBatch* batch = stream.next())
+		fn(*batch);
 }
 
 int main(int argc, char** argv)
@@ -368,7 +357,7 @@ int main(int argc, char** argv)
 		const std::string mask = spacedSeedMask();
 		check(abb_filter_create(&bloom, ABB_COUNTING, counters, params.numHashes, params.k, params.minCov, mask.c_str(), params.device), "filter");
 		uint64_t readCount = 0;
-		for_each_batch(loadFiles, [&](ReadBatch& b) {
+		for_each_batch(loadFiles, [&](const ReadBatch& b) {
 			check(abb_insert_reads(bloom, b.bases.data(), b.offsets.data(), b.size(), nullptr), "insert");
 			readCount += b.size();
 			if (params.verbose)
@@ -396,7 +385,7 @@ int main(int argc, char** argv)
 		readLog << "read_id\tresult\n";
 	}
 	uint64_t contigID = 0, readBase = 0;
-	for_each_batch(asmFiles, [&](ReadBatch& b) {
+	for_each_batch(asmFiles, [&](const ReadBatch& b) {
 		const abb_contig* contigs = nullptr;
 		uint64_t n = 0;
 		const char* seqs = nullptr;
@@ -404,7 +393,7 @@ int main(int argc, char** argv)
 		for (uint64_t i = 0; i < n; ++i) {
 			const abb_contig& c = contigs[i];
 			/* printContig (bloom-dbg.h:455-487) */
-			out << '>' << contigID++ << ' ' << c.length << ' ' << c.coverage << " read:" << b.ids[c.seed_read - readBase] << '\n';
+			out << '>' << contigID++ << ' ' << c.length << ' ' << c.coverage << " read:" << b.id(c.seed_read - readBase) << '\n';
 			out.write(seqs + c.seq_offset, c.length);
 			out << '\n';
 		}
@@ -413,7 +402,7 @@ int main(int argc, char** argv)
 			uint64_t nc = 0;
 			check(abb_assembler_read_results(as, &codes, &nc), "read results");
 			for (uint64_t i = 0; i < nc; ++i)
-				readLog << b.ids[i] << '\t' << names[codes[i] > 6 ? 6 : codes[i]] << '\n';
+				readLog << b.id(i) << '\t' << names[codes[i] > 6 ? 6 : codes[i]] << '\n';
 		}
 		readBase += b.size();
 		if (params.verbose) {

@@ -15,7 +15,14 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <map>
+#include <memory>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace host {
@@ -28,24 +35,51 @@ struct ReadOpts {
 	int qualityOffset = 0; // 0 = format default (33)
 };
 
-/** a batch of reads: concatenated bases + offsets, ids kept for the FASTA comments */
+/** growable byte buffer that does not zero-fill (std::vector<char>::resize would touch every byte twice) */
+struct RawBuf {
+	std::unique_ptr<char[]> p;
+	size_t n = 0, cap = 0;
+	char* data() { return p.get(); }
+	const char* data() const { return p.get(); }
+	size_t size() const { return n; }
+	bool empty() const { return n == 0; }
+	void reserve(size_t want)
+	{
+		if (want <= cap)
+			return;
+		size_t c = cap ? cap : 4096;
+		while (c < want)
+			c *= 2;
+		std::unique_ptr<char[]> q(new char[c]);
+		if (n)
+			memcpy(q.get(), p.get(), n);
+		p = std::move(q);
+		cap = c;
+	}
+};
+
+/** a batch of reads: concatenated bases + offsets; ids concatenated the same way (for the FASTA comments) */
 struct ReadBatch {
 	std::vector<char> bases;
 	std::vector<uint64_t> offsets{ 0 };
-	std::vector<std::string> ids;
+	std::vector<char> id_chars;
+	std::vector<uint64_t> id_offsets{ 0 };
 	void clear()
 	{
 		bases.clear();
 		offsets.assign(1, 0);
-		ids.clear();
+		id_chars.clear();
+		id_offsets.assign(1, 0);
 	}
 	size_t size() const { return offsets.size() - 1; }
 	void add(const std::string& id, const std::string& seq)
 	{
-		ids.push_back(id);
+		id_chars.insert(id_chars.end(), id.begin(), id.end());
+		id_offsets.push_back(id_chars.size());
 		bases.insert(bases.end(), seq.begin(), seq.end());
 		offsets.push_back(bases.size());
 	}
+	std::string id(size_t i) const { return std::string(id_chars.data() + id_offsets[i], id_chars.data() + id_offsets[i + 1]); }
 };
 
 class SeqReader {
@@ -75,9 +109,16 @@ class SeqReader {
 			fprintf(stderr, "error: `%s': %s\n", p, strerror(errno)); // assert_good (Common/IOUtil.h:14-22)
 			exit(EXIT_FAILURE);
 		}
-		m_buf.resize(1 << 22);
-		setvbuf(m_f, m_buf.data(), _IOFBF, m_buf.size());
+		setvbuf(m_f, nullptr, _IONBF, 0); // the reader does its own buffering
+		m_buf.reserve(1 << 23);
 	}
+	/** parse an in-memory piece of a file (BatchStream): `data` holds whole records, numbered from `first_line` */
+	SeqReader(RawBuf&& data, const std::string& path, const ReadOpts& o, uint64_t first_line)
+	    : m_path(path), m_opt(o), m_eof(true), m_buf(std::move(data)), m_end(m_buf.size()), m_line(first_line)
+	{
+	}
+	/** give the buffer back (BatchStream recycles them: fresh 16 MB allocations page-fault on every use) */
+	RawBuf release() { return std::move(m_buf); }
 	~SeqReader()
 	{
 		if (m_f && m_f != stdin)
@@ -87,35 +128,36 @@ class SeqReader {
 	/** next record; false at end of file */
 	bool next(std::string& id, std::string& seq)
 	{
-		std::string comment, q, line;
+		const char* l;
+		size_t n;
 		for (;;) {
 			int c = peek();
 			while (c == '#') { // discard comments
-				getline(line);
+				line(l, n);
 				c = peek();
 			}
 			if (c == EOF)
 				return false;
 			if (c != '>' && c != '@') {
-				getline(line);
+				line(l, n);
 				die();
-				fprintf(stderr, "only FASTA ('>') and FASTQ ('@') input is supported by the B200 CLI, saw `%c' near\n%s\n", c, line.c_str());
+				fprintf(stderr, "only FASTA ('>') and FASTQ ('@') input is supported by the B200 CLI, saw `%c' near\n%.*s\n", c, (int)n, l);
 				exit(EXIT_FAILURE);
 			}
-			std::string header;
-			getline(header);
-			if (header.size() > 3 && header[0] == '@' && isalpha(header[1]) && isalpha(header[2]) && header[3] == '\t')
+			line(l, n); // header
+			if (n > 3 && l[0] == '@' && isalpha((unsigned char)l[1]) && isalpha((unsigned char)l[2]) && l[3] == '\t')
 				continue; // SAM header line
-			const char type = header[0];
+			const char type = l[0];
 			size_t i = 1;
-			while (i < header.size() && !isspace((unsigned char)header[i]))
+			while (i < n && !isspace((unsigned char)l[i]))
 				++i;
-			id = header.substr(1, i - 1);
-			while (i < header.size() && isspace((unsigned char)header[i]))
+			id.assign(l + 1, i - 1);
+			while (i < n && isspace((unsigned char)l[i]))
 				++i;
-			comment = header.substr(i);
+			const char* comment = l + i;
+			const size_t clen = n - i;
 			bool skip = false;
-			if (comment.size() > 3 && comment[1] == ':' && comment[3] == ':') { // Casava: read:chastity:flags:index
+			if (clen > 3 && comment[1] == ':' && comment[3] == ':') { // Casava: read:chastity:flags:index
 				if (m_opt.chastityFilter && comment[2] == 'Y')
 					skip = true;
 				else if (id.size() > 2 && id[id.size() - 2] != '/') {
@@ -123,22 +165,30 @@ class SeqReader {
 					id += comment[0];
 				}
 			}
-			getline(seq);
+			line(l, n);
+			seq.assign(l, n);
+			const bool needq = m_opt.qualityThreshold > 0 || m_opt.internalQThreshold > 0;
+			size_t qlen = 0;
+			bool haveq = false;
 			if (type == '>') {
 				for (int p = peek(); p != '>' && p != '#' && p != EOF; p = peek()) {
-					getline(line);
-					seq += line;
+					line(l, n);
+					seq.append(l, n);
 				}
-				q.clear();
+				m_q.clear();
 			} else {
-				int plus = getc(m_f);
+				int plus = peek();
 				if (plus != '+') {
 					die();
 					fprintf(stderr, "expected `+' and saw `%c'\n", plus);
 					exit(EXIT_FAILURE);
 				}
-				getline(line);
-				getline(q);
+				line(l, n);
+				line(l, n); // quality
+				qlen = n;
+				haveq = n > 0;
+				if (needq)
+					m_q.assign(l, n);
 			}
 			if (skip)
 				continue;
@@ -147,12 +197,15 @@ class SeqReader {
 				fprintf(stderr, "sequence with ID `%s' is empty\n", id.c_str());
 				exit(EXIT_FAILURE);
 			}
-			if (!q.empty() && q.size() != seq.size()) {
+			if (haveq && qlen != seq.size()) {
 				die();
-				fprintf(stderr, "sequence and quality must be the same length near\n%s\n%s\n", seq.c_str(), q.c_str());
+				fprintf(stderr, "sequence and quality must be the same length near\n%s\n%.*s\n", seq.c_str(), (int)n, l);
 				exit(EXIT_FAILURE);
 			}
-			if (m_opt.trimMasked) { // FastaReader.cpp:236-250
+			std::string& q = m_q;
+			if (!needq)
+				q.clear();
+			if (m_opt.trimMasked && (islower((unsigned char)seq.front()) || islower((unsigned char)seq.back()))) { // FastaReader.cpp:236-250
 				size_t front = 0, back = seq.size();
 				while (front < seq.size() && islower((unsigned char)seq[front]))
 					++front;
@@ -168,7 +221,8 @@ class SeqReader {
 				}
 			}
 			for (auto& ch : seq) // FOLD_CASE
-				ch = (char)toupper((unsigned char)ch);
+				if (ch >= 'a' && ch <= 'z')
+					ch = (char)(ch - 32);
 			const int qoff = m_opt.qualityOffset > 0 ? m_opt.qualityOffset : 33;
 			if (m_opt.qualityThreshold > 0 && !q.empty()) { // FastaReader.cpp:376-394
 				const int good = qoff + m_opt.qualityThreshold;
@@ -201,36 +255,439 @@ class SeqReader {
 		fprintf(stderr, "%s:%llu: error: ", m_path.c_str(), (unsigned long long)m_line);
 		return stderr;
 	}
-	int peek()
+	/** make at least one unread byte available; false at end of input */
+	bool fill()
 	{
-		int c = getc(m_f);
-		if (c != EOF)
-			ungetc(c, m_f);
-		return c;
+		if (m_pos < m_end)
+			return true;
+		if (m_eof || !m_f)
+			return false;
+		m_pos = 0;
+		m_end = fread(m_buf.data(), 1, m_buf.cap, m_f);
+		if (m_end == 0)
+			m_eof = true;
+		return m_end > 0;
 	}
-	bool getline(std::string& s)
+	int peek() { return fill() ? (unsigned char)m_buf.data()[m_pos] : EOF; }
+	/** next line without its terminator; the pointer stays valid until the next call */
+	bool line(const char*& p, size_t& n)
 	{
-		s.clear();
-		char* line = nullptr;
-		size_t cap = 0;
-		ssize_t n = ::getline(&line, &cap, m_f);
-		if (n < 0) {
-			free(line);
+		if (!fill()) {
+			p = m_buf.data();
+			n = 0;
 			return false;
 		}
+		for (;;) {
+			char* nl = (char*)memchr(m_buf.data() + m_pos, '\n', m_end - m_pos);
+			if (nl) {
+				p = m_buf.data() + m_pos;
+				n = (size_t)(nl - p);
+				m_pos += n + 1;
+				break;
+			}
+			if (m_eof || !m_f) { // last line without '\n'
+				p = m_buf.data() + m_pos;
+				n = m_end - m_pos;
+				m_pos = m_end;
+				break;
+			}
+			// the line continues past the buffer: move its head to the front and read more
+			const size_t have = m_end - m_pos;
+			memmove(m_buf.data(), m_buf.data() + m_pos, have);
+			if (have == m_buf.cap) {
+				m_buf.n = have;
+				m_buf.reserve(m_buf.cap * 2);
+			}
+			const size_t got = fread(m_buf.data() + have, 1, m_buf.cap - have, m_f);
+			m_pos = 0;
+			m_end = have + got;
+			if (got == 0)
+				m_eof = true;
+		}
 		++m_line;
-		while (n > 0 && (line[n - 1] == '\n' || line[n - 1] == '\r'))
+		while (n > 0 && p[n - 1] == '\r')
 			--n;
-		s.assign(line, (size_t)n);
-		free(line);
 		return true;
 	}
 	std::string m_path;
 	ReadOpts m_opt;
 	FILE* m_f = nullptr;
-	bool m_pipe = false;
-	std::vector<char> m_buf;
+	bool m_pipe = false, m_eof = false;
+	RawBuf m_buf;
+	size_t m_pos = 0, m_end = 0;
+	std::string m_q;
 	uint64_t m_line = 0;
+};
+
+/**
+ * Reads of a list of files as batches of `batch_reads` reads (the last one shorter), in file order, parsed in the
+ * background: one thread reads the files sequentially in pieces of ~16 MB cut at record boundaries, `threads` workers
+ * parse the pieces (the semantics are SeqReader's), and next() stitches them together in order -- so the host parses
+ * the next batch while the GPU works on the current one (the reference parses under `critical(in)`,
+ * BloomIO.h:50-94).  A piece boundary is a line that starts a record: in a file whose first byte is '>' a line
+ * starting with '>' (sequence lines cannot); in a file whose first byte is '@' a line starting with '@' whose second
+ * successor starts with '+' (a quality line that starts with '@' is followed by a header and a sequence line).
+ * Anything else ('#' comments first, SAM headers, stdin oddities) is parsed by the reading thread itself.
+ */
+class BatchStream {
+  public:
+	BatchStream(const std::vector<std::string>& files, const ReadOpts& o, uint64_t batch_reads, unsigned threads = 0,
+	            bool verbose = false, size_t piece_bytes = 16u << 20)
+	    : m_files(files), m_opt(o), m_batchReads(batch_reads ? batch_reads : 1), m_verbose(verbose), m_piece(piece_bytes)
+	{
+		if (threads == 0) {
+			threads = std::thread::hardware_concurrency();
+			threads = threads > 8 ? 8 : threads ? threads : 1;
+		}
+		m_maxInFlight = 2 * threads + 2;
+		for (unsigned i = 0; i < threads; ++i)
+			m_workers.emplace_back([this] { work(); });
+		m_reader = std::thread([this] { read_files(); });
+		m_stitcher = std::thread([this] { stitch(); });
+	}
+	~BatchStream()
+	{
+		{
+			std::lock_guard<std::mutex> l(m_mu);
+			m_stop = true;
+		}
+		m_cv.notify_all();
+		m_reader.join();
+		for (auto& w : m_workers)
+			w.join();
+		m_stitcher.join();
+		if (getenv("ABB_STREAM_STATS"))
+			fprintf(stderr, "BatchStream: consumer waited %.3f s, stitched %.3f s; reader read %.3f s, blocked %.3f s\n", m_tWait, m_tAppend,
+			        m_tRead, m_tThrottle);
+	}
+	/** next batch (owned by the stream, valid until the following call), nullptr at the end */
+	const ReadBatch* next()
+	{
+		const auto w0 = std::chrono::steady_clock::now();
+		std::unique_lock<std::mutex> l(m_mu);
+		if (m_given) {
+			m_outFree.push_back(std::move(m_given));
+			m_cv.notify_all();
+		}
+		m_cv.wait(l, [&] { return !m_outQ.empty() || m_stitchDone; });
+		m_tWait += std::chrono::duration<double>(std::chrono::steady_clock::now() - w0).count();
+		if (m_outQ.empty())
+			return nullptr;
+		m_given = std::move(m_outQ.front());
+		m_outQ.pop_front();
+		l.unlock();
+		m_cv.notify_all();
+		return m_given.get();
+	}
+
+  private:
+	struct Piece {
+		uint64_t seq;
+		RawBuf data;
+		std::string path;
+		uint64_t first_line;
+	};
+	/** background: cut the parsed pieces, in order, into batches of exactly m_batchReads reads (at most two wait) */
+	void stitch()
+	{
+		for (bool more = true; more;) {
+			std::unique_ptr<ReadBatch> out;
+			{
+				std::unique_lock<std::mutex> l(m_mu);
+				m_cv.wait(l, [&] { return m_stop || m_outQ.size() < 2; });
+				if (m_stop)
+					break;
+				if (!m_outFree.empty()) {
+					out = std::move(m_outFree.back());
+					m_outFree.pop_back();
+				}
+			}
+			if (!out)
+				out.reset(new ReadBatch());
+			out->clear();
+			m_outp = out.get();
+			while (out->size() < m_batchReads) {
+				if (!m_cur || m_curPos == m_cur->size()) {
+					std::unique_lock<std::mutex> l(m_mu);
+					m_cv.wait(l, [&] { return m_stop || m_done.count(m_nextOut) || (m_readerDone && m_nextOut == m_nextSeq); });
+					auto it = m_done.find(m_nextOut);
+					if (m_stop || it == m_done.end()) {
+						more = false; // no more pieces
+						break;
+					}
+					if (m_cur)
+						m_free.push_back(std::move(m_cur)); // recycled by the workers: its pages are already mapped
+					m_cur = std::move(it->second);
+					m_done.erase(it);
+					++m_nextOut;
+					m_curPos = 0;
+					l.unlock();
+					m_cv.notify_all();
+					continue;
+				}
+				const size_t take = (size_t)std::min<uint64_t>(m_batchReads - out->size(), m_cur->size() - m_curPos);
+				if (out->bases.capacity() == 0 && m_cur->size()) { // size a new output batch from the piece's average read
+					const double n = (double)m_cur->size();
+					const uint64_t want = m_batchReads;
+					out->bases.reserve((size_t)(1.05 * want * (m_cur->bases.size() / n)) + 4096);
+					out->id_chars.reserve((size_t)(1.25 * want * (m_cur->id_chars.size() / n)) + 4096);
+					out->offsets.reserve(want + 1);
+					out->id_offsets.reserve(want + 1);
+				}
+				const auto a0 = std::chrono::steady_clock::now();
+				append(*m_cur, m_curPos, take);
+				m_tAppend += std::chrono::duration<double>(std::chrono::steady_clock::now() - a0).count();
+				m_curPos += take;
+			}
+			if (out->size()) {
+				std::lock_guard<std::mutex> l(m_mu);
+				m_outQ.push_back(std::move(out));
+			}
+			m_cv.notify_all();
+		}
+		{
+			std::lock_guard<std::mutex> l(m_mu);
+			m_stitchDone = true;
+		}
+		m_cv.notify_all();
+	}
+	void append(const ReadBatch& b, size_t r0, size_t n)
+	{
+		ReadBatch& m_out = *m_outp;
+		const uint64_t b0 = b.offsets[r0], b1 = b.offsets[r0 + n], i0 = b.id_offsets[r0], i1 = b.id_offsets[r0 + n];
+		const uint64_t base = m_out.bases.size(), ibase = m_out.id_chars.size();
+		m_out.bases.insert(m_out.bases.end(), b.bases.begin() + b0, b.bases.begin() + b1);
+		m_out.id_chars.insert(m_out.id_chars.end(), b.id_chars.begin() + i0, b.id_chars.begin() + i1);
+		for (size_t r = r0 + 1; r <= r0 + n; ++r) {
+			m_out.offsets.push_back(base + (b.offsets[r] - b0));
+			m_out.id_offsets.push_back(ibase + (b.id_offsets[r] - i0));
+		}
+	}
+	/** hand a parsed piece to next() */
+	void publish(uint64_t seq, std::unique_ptr<ReadBatch> b)
+	{
+		{
+			std::lock_guard<std::mutex> l(m_mu);
+			m_done[seq] = std::move(b);
+		}
+		m_cv.notify_all();
+	}
+	/** wait until fewer than m_maxInFlight pieces are queued or parsed-but-unconsumed; false when stopping */
+	bool throttle()
+	{
+		const auto t0 = std::chrono::steady_clock::now();
+		std::unique_lock<std::mutex> l(m_mu);
+		m_cv.wait(l, [&] { return m_stop || m_nextSeq - m_nextOut < m_maxInFlight; });
+		m_tThrottle += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+		return !m_stop;
+	}
+	void work()
+	{
+		for (;;) {
+			Piece pc;
+			{
+				std::unique_lock<std::mutex> l(m_mu);
+				m_cv.wait(l, [&] { return m_stop || !m_tasks.empty() || m_readerDone; });
+				if (m_tasks.empty()) {
+					if (m_stop || m_readerDone)
+						return;
+					continue;
+				}
+				pc = std::move(m_tasks.front());
+				m_tasks.pop_front();
+			}
+			std::unique_ptr<ReadBatch> b;
+			{
+				std::lock_guard<std::mutex> l(m_mu);
+				if (!m_free.empty()) {
+					b = std::move(m_free.back());
+					m_free.pop_back();
+				}
+			}
+			if (b)
+				b->clear();
+			else {
+				b.reset(new ReadBatch());
+				b->bases.reserve(pc.data.size() / 2);
+			}
+			SeqReader in(std::move(pc.data), pc.path, m_opt, pc.first_line);
+			std::string id, seq;
+			while (in.next(id, seq))
+				b->add(id, seq);
+			{
+				std::lock_guard<std::mutex> l(m_mu);
+				m_freeBufs.push_back(in.release());
+			}
+			publish(pc.seq, std::move(b));
+		}
+	}
+	/** offset of the last record start in [1, n) of buf, or 0 if there is none */
+	static size_t last_record_start(const char* buf, size_t n, char mode)
+	{
+		size_t end = n;
+		for (;;) {
+			// start of the last line that begins before `end`
+			const char* nl = end > 1 ? (const char*)memrchr(buf, '\n', end - 1) : nullptr;
+			if (!nl)
+				return 0;
+			const size_t ls = (size_t)(nl - buf) + 1;
+			if (ls < n && buf[ls] == mode) {
+				if (mode == '>')
+					return ls;
+				// FASTQ: the line after next must be present and start with '+'
+				const char* l1 = (const char*)memchr(buf + ls, '\n', n - ls);
+				const char* l2 = l1 ? (const char*)memchr(l1 + 1, '\n', n - (size_t)(l1 + 1 - buf)) : nullptr;
+				if (l2 && (size_t)(l2 + 1 - buf) < n && l2[1] == '+')
+					return ls;
+			}
+			end = ls; // try the previous line
+			if (end <= 1)
+				return 0;
+		}
+	}
+	void read_files()
+	{
+		for (const auto& path : m_files) {
+			if (m_verbose)
+				fprintf(stderr, "Reading `%s'...\n", path.c_str());
+			if (!read_file(path))
+				break;
+		}
+		{
+			std::lock_guard<std::mutex> l(m_mu);
+			m_readerDone = true;
+		}
+		m_cv.notify_all();
+	}
+	RawBuf take_buf()
+	{
+		std::lock_guard<std::mutex> l(m_mu);
+		if (m_freeBufs.empty())
+			return RawBuf();
+		RawBuf b = std::move(m_freeBufs.back());
+		m_freeBufs.pop_back();
+		b.n = 0;
+		return b;
+	}
+	static FILE* open_input(const std::string& path, bool* is_pipe)
+	{
+		auto ends = [&](const char* suf) {
+			size_t n = strlen(suf);
+			return path.size() >= n && path.compare(path.size() - n, n, suf) == 0;
+		};
+		std::string cmd;
+		if (ends(".gz") || ends(".z") || ends(".Z"))
+			cmd = "gunzip -c '" + path + "'";
+		else if (ends(".bz2"))
+			cmd = "bunzip2 -c '" + path + "'";
+		else if (ends(".xz"))
+			cmd = "xzdec -c '" + path + "'";
+		*is_pipe = !cmd.empty();
+		FILE* f = !cmd.empty() ? popen(cmd.c_str(), "r") : path == "-" ? stdin : fopen(path.c_str(), "r");
+		if (!f) {
+			fprintf(stderr, "error: `%s': %s\n", path.c_str(), strerror(errno)); // assert_good (Common/IOUtil.h:14-22)
+			exit(EXIT_FAILURE);
+		}
+		setvbuf(f, nullptr, _IONBF, 0);
+		return f;
+	}
+	bool read_file(const std::string& path)
+	{
+		bool is_pipe = false;
+		FILE* f = open_input(path, &is_pipe);
+		const auto r0 = std::chrono::steady_clock::now();
+		RawBuf carry = take_buf(); // bytes read but not yet handed out
+		uint64_t line = 0;
+		char mode = 0;
+		bool eof = false, ok = true;
+		while (ok && !(eof && carry.empty())) {
+			RawBuf buf(std::move(carry));
+			carry = take_buf();
+			size_t want = buf.n + m_piece;
+			for (;;) { // read until the piece holds a record boundary (or the file ends)
+				buf.reserve(want);
+				while (!eof && buf.n < want) {
+					const size_t got = fread(buf.data() + buf.n, 1, want - buf.n, f);
+					if (got == 0)
+						eof = true;
+					buf.n += got;
+				}
+				if (!mode && buf.n)
+					mode = buf.data()[0] == '>' || buf.data()[0] == '@' ? buf.data()[0] : '?';
+				if (eof || mode == '?')
+					break;
+				const size_t cut = last_record_start(buf.data(), buf.n, mode);
+				if (cut) {
+					carry.reserve(buf.n - cut + m_piece);
+					memcpy(carry.data(), buf.data() + cut, buf.n - cut);
+					carry.n = buf.n - cut;
+					buf.n = cut;
+					break;
+				}
+				want += m_piece; // one record longer than the piece: keep reading
+			}
+			if (mode == '?') {
+				// not a plain FASTA/FASTQ start: one piece holds the rest of the file, i.e. it is parsed serially
+				while (!eof) {
+					buf.reserve(buf.n + m_piece);
+					const size_t got = fread(buf.data() + buf.n, 1, m_piece, f);
+					buf.n += got;
+					if (got == 0)
+						eof = true;
+				}
+			}
+			if (buf.empty())
+				break;
+			uint64_t nl = 0;
+			for (const char *q = buf.data(), *e = q + buf.size(); q < e && (q = (const char*)memchr(q, '\n', (size_t)(e - q))); ++q)
+				++nl;
+			if (!throttle()) {
+				ok = false;
+				break;
+			}
+			Piece pc;
+			pc.data = std::move(buf);
+			pc.path = path;
+			pc.first_line = line;
+			line += nl;
+			{
+				std::lock_guard<std::mutex> l(m_mu);
+				pc.seq = m_nextSeq++;
+				m_tasks.push_back(std::move(pc));
+			}
+			m_cv.notify_all();
+		}
+		if (f != stdin)
+			is_pipe ? pclose(f) : fclose(f);
+		m_tRead += std::chrono::duration<double>(std::chrono::steady_clock::now() - r0).count();
+		return ok;
+	}
+
+	std::vector<std::string> m_files;
+	ReadOpts m_opt;
+	uint64_t m_batchReads;
+	bool m_verbose;
+	size_t m_piece;
+	uint64_t m_maxInFlight = 4;
+	std::mutex m_mu;
+	std::condition_variable m_cv;
+	std::deque<Piece> m_tasks;
+	std::map<uint64_t, std::unique_ptr<ReadBatch>> m_done;
+	uint64_t m_nextSeq = 0, m_nextOut = 0;
+	bool m_readerDone = false, m_stop = false;
+	std::vector<std::thread> m_workers;
+	std::thread m_reader;
+	std::unique_ptr<ReadBatch> m_cur;
+	std::vector<std::unique_ptr<ReadBatch>> m_free;
+	std::vector<RawBuf> m_freeBufs;
+	size_t m_curPos = 0;
+	ReadBatch* m_outp = nullptr;                      // batch the stitcher is filling
+	std::deque<std::unique_ptr<ReadBatch>> m_outQ;    // finished batches
+	std::vector<std::unique_ptr<ReadBatch>> m_outFree;
+	std::unique_ptr<ReadBatch> m_given;               // the batch the caller holds
+	bool m_stitchDone = false;
+	std::thread m_stitcher;
+	double m_tWait = 0, m_tAppend = 0, m_tRead = 0, m_tThrottle = 0;
 };
 
 /** SIToBytes (Common/StringUtil.h:181-219): number with optional k/M/G suffix (powers of 1024) */

@@ -23,6 +23,8 @@
 #include "vendor/nthash/ntHashIterator.hpp"
 #include "vendor/btl_bloomfilter/CountingBloomFilter.hpp"
 #include "vendor/btl_bloomfilter/BloomFilter.hpp"
+#include "DataLayer/FastaReader.h"
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <iostream>
@@ -40,7 +42,7 @@ static void dumpRaw(const BloomFilter& bf)
 	fwrite(s.data() + p + tag.size(), 1, s.size() - p - tag.size(), stdout);
 }
 
-static void usage() { fprintf(stderr, "usage: ref_arith hashes|nthash|count|bits|casc|seeds ...\n"); exit(2); }
+static void usage() { fprintf(stderr, "usage: ref_arith hashes|nthash|count|bits|casc|seeds|reads ...\n"); exit(2); }
 
 int main(int argc, char** argv)
 {
@@ -52,6 +54,26 @@ int main(int argc, char** argv)
 			std::cout << SpacedSeed::qrSeedPair(atoi(argv[3]), atoi(argv[4])) << "\n";
 		else
 			std::cout << SpacedSeed::kmerPair(atoi(argv[3]), atoi(argv[4])) << "\n";
+		return 0;
+	}
+	if (cmd == "reads") {
+		// ref_arith reads dump|time FILE...: the reference's own reader (DataLayer/FastaReader.cpp, FOLD_CASE as in
+		// BloomIO.h:58 / bloom-dbg.h:917) -- "id<TAB>sequence" per record, or records/s
+		if (argc < 4) usage();
+		const bool dump = std::string(argv[2]) == "dump";
+		size_t n = 0, bases = 0;
+		auto t0 = std::chrono::steady_clock::now();
+		for (int i = 3; i < argc; ++i) {
+			FastaReader in(argv[i], FastaReader::FOLD_CASE);
+			for (FastaRecord rec; in >> rec;) {
+				++n;
+				bases += rec.seq.size();
+				if (dump)
+					std::cout << rec.id << '\t' << rec.seq << '\n';
+			}
+		}
+		double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+		fprintf(stderr, "%zu reads, %zu bases in %.3f s: %.2f M reads/s\n", n, bases, s, n / s / 1e6);
 		return 0;
 	}
 	if (argc < 4) usage();

@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def build(tmp_path):
     exe = str(tmp_path / "host_arith")
-    subprocess.run(["g++", "-std=c++17", "-O2", "-Wno-unknown-pragmas", "-o", exe, os.path.join(ROOT, "tests", "host_arith", "host_arith.cpp"),
+    subprocess.run(["g++", "-std=c++17", "-O2", "-pthread", "-Wno-unknown-pragmas", "-o", exe, os.path.join(ROOT, "tests", "host_arith", "host_arith.cpp"),
                     os.path.join(ROOT, "oracle", "abyss_oracle.c")], check=True, capture_output=True)
     return exe
 

@@ -1,0 +1,111 @@
+"""CPU: the CLI's read ingestion (abyss_b200/host/reads.h).  BatchStream -- pieces of the file parsed by worker threads
+while the GPU works on the previous batch -- must deliver exactly the records of the serial SeqReader
+(DataLayer/FastaReader.cpp:130-421 semantics), in order, in batches of the requested size, wherever the piece
+boundaries fall: quality lines that start with '@', '+' or '>', multi-line FASTA, Casava headers, CRLF, a last line
+without newline, comment-led files (parsed serially), several files, compressed input."""
+import gzip
+import os
+import random
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def exe(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("rd") / "host_reader")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-pthread", "-Wall", "-o", out, os.path.join(ROOT, "tests", "host_reader", "host_reader.cpp")],
+                   check=True, capture_output=True)
+    return out
+
+
+def run(exe, *args, env=None):
+    r = subprocess.run([exe, *map(str, args)], capture_output=True, text=True, env=dict(os.environ, **(env or {})))
+    assert r.returncode == 0, r.stderr
+    return r.stdout, [int(l.split()[2]) for l in r.stderr.splitlines() if l.startswith("# batch")]
+
+
+def fastq(n, seed, crlf=False, casava=False):
+    rng = random.Random(seed)
+    nl = "\r\n" if crlf else "\n"
+    out = []
+    for i in range(n):
+        L = rng.randint(1, 180)
+        seq = "".join(rng.choice("ACGTNacgt") for _ in range(L))
+        # qualities over the whole printable range: lines starting with '@', '+', '>' and '#' all occur
+        q = "".join(chr(rng.randint(33, 74)) for _ in range(L))
+        if i % 7 == 0:
+            q = rng.choice("@+>#") + q[1:]
+        head = f"@r{i}" + (f" {1 + i % 2}:{'Y' if i % 5 == 0 else 'N'}:0:ACGT" if casava else f"/{1 + i % 2} extra words")
+        out.append(f"{head}{nl}{seq}{nl}+{nl}{q}{nl}")
+    return "".join(out)
+
+
+def fasta(n, seed):
+    rng = random.Random(seed)
+    out = []
+    for i in range(n):
+        out.append(f">c{i} len\n")
+        for _ in range(rng.randint(1, 5)):
+            out.append("".join(rng.choice("ACGTacgtN") for _ in range(rng.randint(1, 70))) + "\n")
+    return "".join(out)
+
+
+@pytest.mark.parametrize("piece", [64, 1000, 1 << 16])
+@pytest.mark.parametrize("threads", [1, 3])
+def test_stream_equals_serial(exe, tmp_path, piece, threads):
+    files = {}
+    files["a.fq"] = fastq(3000, 1)
+    files["b.fq"] = fastq(1500, 2, crlf=True, casava=True)
+    files["c.fa"] = fasta(800, 3)
+    files["d.fq"] = fastq(5, 4)[:-1]                      # last line without '\n'
+    files["e.fq"] = "# comment first\n" + fastq(50, 5)    # not a plain FASTQ start: serial path
+    files["f.fa"] = ""                                    # empty file
+    paths = []
+    for name, text in files.items():
+        p = tmp_path / name
+        p.write_text(text, newline="")
+        paths.append(str(p))
+    gz = tmp_path / "g.fq.gz"
+    with gzip.open(gz, "wt", newline="") as f:
+        f.write(fastq(700, 6))
+    paths.append(str(gz))
+    want, _ = run(exe, "serial", *paths)
+    assert want.count("\n") > 5000
+    got, batches = run(exe, "stream", threads, 997, piece, *paths)
+    assert got == want
+    assert all(b == 997 for b in batches[:-1]) and 0 < batches[-1] <= 997 and sum(batches) == want.count("\n")
+
+
+def test_stream_quality_options(exe, tmp_path):
+    p = tmp_path / "q.fq"
+    p.write_text(fastq(2000, 9, casava=True))
+    for env in ({"READER_Q": "20"}, {"READER_MASKQ": "15"}, {"READER_NO_CHASTITY": "1"}):
+        want, _ = run(exe, "serial", p, env=env)
+        got, _ = run(exe, "stream", 4, 300, 777, p, env=env)
+        assert got == want
+
+
+REF_ARITH = os.path.join(ROOT, "oracle", "_ref", "ref_arith")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_ARITH), reason="oracle/_ref not built (needs /root/reference)")
+def test_reader_equals_reference_reader(exe, tmp_path):
+    # the UNMODIFIED reference reader (DataLayer/FastaReader.cpp through oracle/_ref/ref_arith reads dump):
+    # ids (Casava suffix), chastity filter, masked-end trimming, case folding, multi-line FASTA, CRLF, gz
+    files = {"a.fq": fastq(2000, 11), "b.fq": fastq(1000, 12, crlf=True, casava=True), "c.fa": fasta(500, 13)}
+    paths = []
+    for name, text in files.items():
+        p = tmp_path / name
+        p.write_text(text, newline="")
+        paths.append(str(p))
+    gz = tmp_path / "g.fq.gz"
+    with gzip.open(gz, "wt", newline="") as f:
+        f.write(fastq(300, 14))
+    paths.append(str(gz))
+    ref = subprocess.run([REF_ARITH, "reads", "dump", *paths], capture_output=True, text=True)
+    assert ref.returncode == 0, ref.stderr
+    got, _ = run(exe, "stream", 3, 500, 4096, *paths)
+    assert got == ref.stdout
