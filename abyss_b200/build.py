@@ -45,7 +45,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
-    cmd = [NVCC, *FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-o", LIB,
+    cmd = [NVCC, *FLAGS, "--threads", "2", *(["-Xptxas", "-v"] if verbose else []), "-o", LIB,
            *[os.path.join(CSRC, s) for s in SOURCES]]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

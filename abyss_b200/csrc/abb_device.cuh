@@ -13,9 +13,11 @@
 #if defined(__CUDACC__)
 #define ABB_HD __host__ __device__ __forceinline__
 #define ABB_D __device__ __forceinline__
+#define ABB_HD_NOINLINE __host__ __device__ __noinline__ // rarely taken slow paths: one copy, not one per call site
 #else
 #define ABB_HD inline
 #define ABB_D inline
+#define ABB_HD_NOINLINE __attribute__((noinline))
 #endif
 
 namespace abb {

@@ -231,26 +231,36 @@ struct Vtx {
 	ABB_HD uint64_t canon() const { return id; }
 	ABB_HD uint64_t bloom() const { return mh; }
 };
+/** spaced seed only; not inlined: the unmasked walk, which never gets here, stays as small as it was */
 template <int KW>
-ABB_HD void vtx_rehash(Vtx<KW>& v, unsigned k, const RollTab& rt)
+ABB_HD_NOINLINE void vtx_rehash_masked(Vtx<KW>& v, unsigned k, const RollTab& rt)
 {
-	if (rt.nmask == 0) {
-		v.mh = v.id = v.h.canonical();
-		return;
-	}
 	const HashPair c = mask_corr(v.km, k, rt, 0);
 	const uint64_t f = v.h.fh ^ c.fh, r = v.h.rh ^ c.rh;
 	v.mh = r < f ? r : f;
 	v.id = kmer_is_canonical(v.km, k) ? f : r;
 }
+template <int KW>
+ABB_HD void vtx_rehash(Vtx<KW>& v, unsigned k, const RollTab& rt)
+{
+	if (rt.nmask == 0)
+		v.mh = v.id = v.h.canonical();
+	else
+		vtx_rehash_masked(v, k, rt);
+}
 /** Bloom hash of the neighbour of v in direction d with new base b, without building its k-mer */
+template <int KW>
+ABB_HD_NOINLINE uint64_t neighbor_bloom_masked(const HashPair& h, const Kmer<KW>& km, unsigned k, const RollTab& rt, int shift)
+{
+	return masked_canon(h, mask_corr(km, k, rt, shift));
+}
 template <int KW>
 ABB_HD uint64_t neighbor_bloom(const Vtx<KW>& v, unsigned k, const RollTab& rt, Dir d, unsigned b)
 {
 	const HashPair h = d == FWD ? roll_right(v.h, rt, kmer_first(v.km, k), b) : roll_left(v.h, rt, kmer_last(v.km), b);
 	if (rt.nmask == 0)
 		return h.canonical();
-	return masked_canon(h, mask_corr(v.km, k, rt, d == FWD ? 1 : -1));
+	return neighbor_bloom_masked(h, v.km, k, rt, d == FWD ? 1 : -1);
 }
 template <int KW>
 ABB_HD unsigned vtx_step(Vtx<KW>& v, unsigned k, const RollTab& rt, Dir d, unsigned b);

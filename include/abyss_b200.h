@@ -151,6 +151,10 @@ typedef struct abb_assembly_counters {
 	uint64_t solid_reads, visited_reads, reads_processed, bases_assembled, contig_id;
 } abb_assembly_counters;
 
+/* The assembler works on a counting filter and takes k, H, the threshold and the spaced seed from it.  A seed must
+ * begin and end with '1' (MaskedKmer::setMask, BloomDBG/MaskedKmer.h:44-47) and be symmetric
+ * (RollingBloomDBGVertex::compare asserts it, RollingBloomDBG.h:141-145); sequences may then contain 'N' where no
+ * vertex of a short path writes a column (pathToSeq, bloom-dbg.h:131-158). */
 int abb_assembler_create(abb_assembler** out, abb_filter* solid, const abb_assembly_params* params);
 int abb_assembler_destroy(abb_assembler* a);
 /* Process the next batch of reads (file order).  On return *contigs / *seqs point at library-
