@@ -109,3 +109,17 @@ def test_reader_equals_reference_reader(exe, tmp_path):
     assert ref.returncode == 0, ref.stderr
     got, _ = run(exe, "stream", 3, 500, 4096, *paths)
     assert got == ref.stdout
+
+
+def test_long_records(exe, tmp_path):
+    # a FASTA record longer than the reader's 8 MB buffer and than any piece, on one line and folded
+    rng = random.Random(21)
+    big = "".join(rng.choice("ACGT") for _ in range(1 << 16)) * 160          # 10.5 Mbp
+    p = tmp_path / "big.fa"
+    p.write_text(">one line\n" + big + "\n>folded\n" + "\n".join(big[i:i + 70] for i in range(0, 3_000_000, 70)) + "\n>tail\nACGT\n")
+    want, _ = run(exe, "serial", p)
+    lines = want.split("\n")
+    assert [l.split("\t")[0] for l in lines[:3]] == ["one", "folded", "tail"]
+    assert len(lines[0]) == 4 + len(big) and len(lines[1]) == 7 + 3_000_060 and lines[2] == "tail\tACGT"
+    got, batches = run(exe, "stream", 2, 2, 1 << 20, p)
+    assert got == want and batches == [2, 1]
