@@ -115,3 +115,19 @@ def test_threshold_semantics_known_answer(oracle):
     mn = lambda s: int(oracle.cbf_min_hashes(counters, oracle.hash_seq(s, 16, 1)[0])[0])
     assert mn(a) == 2 and mn(b) == 1 and mn(c) == 0 and mn(d) == 0
     assert np.count_nonzero(counters) == 2 and np.count_nonzero(counters >= 2) == 1
+
+
+def test_cascading_known_answer(oracle):
+    # Unittest/BloomDBG/HashAgnosticCascadingBloomTest.cpp:9-46: 2 levels of 1000 bits... (size rounded to 1024 here),
+    # H=1; a inserted twice, b once: the last level holds a only
+    a, b, c = "AGATGTGCTGCCGCCT", "TGGACAGCGTTACCTC", "TAATAACAGTCCCTAT"
+    mbits, L = 1024, 2
+    levels = np.zeros(L * mbits // 8, dtype=np.uint8)
+    oracle.casc_load(levels, mbits, L, [a, a, b], 16, 1)
+    last = levels[(L - 1) * mbits // 8:]
+    def in_last(s):
+        p = int(oracle.hash_seq(s, 16, 1)[0][0][0] % np.uint64(mbits))
+        return bool(last[p >> 3] >> (p & 7) & 1)
+    assert in_last(a) and not in_last(b) and not in_last(c)
+    first = levels[:mbits // 8]
+    assert int(np.unpackbits(first).sum()) == 2 and int(np.unpackbits(last).sum()) == 1
