@@ -1,4 +1,4 @@
-"""CPU (gloo, world_size 2): the host logic of the hash-range sharded pass 1 -- ownership, stable
+"""CPU (gloo, world_size 2, 3 and 4): the host logic of the hash-range sharded pass 1 -- ownership, stable
 routing, the all-to-all, and the file-order property of the receive buffer.  No GPU needed."""
 import os
 import socket
@@ -42,8 +42,11 @@ def _worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
-def test_sharded_routing_world2():
-    world = 2
+import pytest
+
+
+@pytest.mark.parametrize("world", [2, 3, 4])
+def test_sharded_routing(world):
     mgr = mp.Manager()
     out = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
