@@ -458,9 +458,17 @@ class BatchStream {
 		const uint64_t base = m_out.bases.size(), ibase = m_out.id_chars.size();
 		m_out.bases.insert(m_out.bases.end(), b.bases.begin() + b0, b.bases.begin() + b1);
 		m_out.id_chars.insert(m_out.id_chars.end(), b.id_chars.begin() + i0, b.id_chars.begin() + i1);
-		for (size_t r = r0 + 1; r <= r0 + n; ++r) {
-			m_out.offsets.push_back(base + (b.offsets[r] - b0));
-			m_out.id_offsets.push_back(ibase + (b.id_offsets[r] - i0));
+		const size_t at = m_out.offsets.size();
+		m_out.offsets.resize(at + n);
+		m_out.id_offsets.resize(at + n);
+		uint64_t* o = m_out.offsets.data() + at;
+		uint64_t* io = m_out.id_offsets.data() + at;
+		const uint64_t* so = b.offsets.data() + r0 + 1;
+		const uint64_t* sio = b.id_offsets.data() + r0 + 1;
+		const uint64_t d = base - b0, di = ibase - i0; // modulo 2^64: fine when base < b0
+		for (size_t r = 0; r < n; ++r) {
+			o[r] = so[r] + d;
+			io[r] = sio[r] + di;
 		}
 	}
 	/** hand a parsed piece to next() */
