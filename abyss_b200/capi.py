@@ -28,7 +28,8 @@ class InsertStats(C.Structure):
     _fields_ = [("kmers", C.c_uint64), ("slots", C.c_uint64), ("windows", C.c_uint64),
                 ("deferred", C.c_uint64), ("launches", C.c_uint64),
                 ("ms_hash", C.c_float), ("ms_insert", C.c_float), ("ms_commit", C.c_float),
-                ("commit_launches", C.c_uint64)]
+                ("commit_launches", C.c_uint64), ("commit_slots", C.c_uint64), ("drains", C.c_uint64),
+                ("drained_slots", C.c_uint64)]
 
 
 class Contig(C.Structure):
@@ -79,7 +80,17 @@ SIGNATURES = {
     "abb_hash_reads": (C.c_int, [C.c_uint, C.c_char_p, _vp, _vp, C.c_uint64, _vp, _vp, _u64p, C.c_int]),
     "abb_hash_reads_dev": (C.c_int, [_vp, _vp, _vp, C.c_uint64, _vp, _vp, C.c_uint64, _u64p]),
     "abb_insert_h0_dev": (C.c_int, [_vp, _vp, C.c_uint64]),
-    "abb_route_h0_dev": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint, _vp, _vp]),
+    "abb_comm_unique_id": (C.c_int, [_vp]),
+    "abb_comm_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, _vp, C.c_int]),
+    "abb_comm_destroy": (C.c_int, [_vp]),
+    "abb_comm_rank": (C.c_int, [_vp]),
+    "abb_comm_world": (C.c_int, [_vp]),
+    "abb_insert_reads_sharded_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_uint64, C.c_int, _u64p]),
+    "abb_insert_reads_sharded": (C.c_int, [_vp, _vp, _vp, _vp, C.c_uint64, C.c_int, _u64p]),
+    "abb_filter_resident_reads": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), _u64p]),
+    "abb_filter_allgather": (C.c_int, [_vp, _vp]),
+    "abb_comm_allgather_bytes": (C.c_int, [_vp, _vp, C.c_uint64, _vp]),
+    "abb_comm_allreduce_max_u8": (C.c_int, [_vp, _vp, C.c_uint64, _vp]),
     "abb_filter_device_ptr": (_vp, [_vp, C.c_int]),
     "abb_filter_download": (C.c_int, [_vp, C.c_int, _vp, C.c_uint64]),
     "abb_filter_upload": (C.c_int, [_vp, C.c_int, _vp, C.c_uint64]),
@@ -167,6 +178,36 @@ def hash_reads(k: int, seqs_or_arrays, mask: str = "", device: int = 0):
     return h0, valid, slot_offs
 
 
+class Comm:
+    """the NCCL communicator behind the C ABI (one per process / GPU).  `bcast` ships rank 0's 128-byte id to the
+    other ranks: a callable (bytes | None) -> bytes, e.g. torch.distributed.broadcast_object_list."""
+
+    def __init__(self, rank: int, world: int, device: int, bcast):
+        self._lib = load()
+        self._h = _vp()
+        ident = np.zeros(128, dtype=np.uint8)
+        if rank == 0:
+            check(self._lib.abb_comm_unique_id(_ptr(ident)))
+        ident = np.frombuffer(bcast(ident.tobytes() if rank == 0 else None), dtype=np.uint8).copy()
+        check(self._lib.abb_comm_create(C.byref(self._h), rank, world, _ptr(ident), device))
+        self.rank, self.world = rank, world
+
+    @property
+    def handle(self):
+        return self._h
+
+    def allgather_bytes(self, d_buf_ptr: int, bytes_per_rank: int, stream: int = 0):
+        check(self._lib.abb_comm_allgather_bytes(self._h, _vp(d_buf_ptr), bytes_per_rank, _vp(stream)))
+
+    def allreduce_max_u8(self, d_buf_ptr: int, n: int, stream: int = 0):
+        check(self._lib.abb_comm_allreduce_max_u8(self._h, _vp(d_buf_ptr), n, _vp(stream)))
+
+    def close(self):
+        if self._h:
+            self._lib.abb_comm_destroy(self._h)
+            self._h = _vp()
+
+
 class Filter:
     """Host mirror of the reference's Bloom filter classes over a device-resident array.
 
@@ -239,10 +280,27 @@ class Filter:
                                            C.byref(n)))
         return n.value
 
-    def route_h0_dev(self, d_h0_ptr: int, d_valid_ptr: int, n: int, world: int, d_send_ptr: int) -> np.ndarray:
-        counts = np.zeros(world, dtype=np.uint64)
-        check(self._lib.abb_route_h0_dev(self._h, _vp(d_h0_ptr), _vp(d_valid_ptr), n, world, _vp(d_send_ptr), _ptr(counts)))
-        return counts
+    def insert_reads_sharded_dev(self, comm: "Comm", d_bases_ptr: int, d_offs_ptr: int, n_reads: int, finalize: bool = True) -> int:
+        """exact multi-GPU insert: EVERY rank passes all reads; counters sharded by position range (abb_shard.cuh)"""
+        n = C.c_uint64(0)
+        check(self._lib.abb_insert_reads_sharded_dev(self._h, comm.handle, _vp(d_bases_ptr), _vp(d_offs_ptr), n_reads, int(finalize),
+                                                     C.byref(n)))
+        return n.value
+
+    def insert_reads_sharded(self, comm: "Comm", seqs_or_arrays, finalize: bool = True) -> int:
+        bases, offs = seqs_or_arrays if isinstance(seqs_or_arrays, tuple) else pack_reads(seqs_or_arrays)
+        n = C.c_uint64(0)
+        check(self._lib.abb_insert_reads_sharded(self._h, comm.handle, _ptr(bases), _ptr(offs), len(offs) - 1, int(finalize), C.byref(n)))
+        return n.value
+
+    def resident_reads(self) -> tuple[int, int, int]:
+        """(device bases pointer, device offsets pointer, n_reads) of the last host-buffer insert"""
+        b, o, n = _vp(), _vp(), C.c_uint64(0)
+        check(self._lib.abb_filter_resident_reads(self._h, C.byref(b), C.byref(o), C.byref(n)))
+        return b.value or 0, o.value or 0, n.value
+
+    def allgather(self, comm: "Comm"):
+        check(self._lib.abb_filter_allgather(self._h, comm.handle))
 
     def insert_h0_dev(self, d_h0_ptr: int, n: int):
         check(self._lib.abb_insert_h0_dev(self._h, _vp(d_h0_ptr), n))
@@ -356,6 +414,7 @@ class Assembler:
         seqs = C.c_char_p()
         check(fn(self._h, bases_p, offs_p, n_reads, C.byref(contigs), C.byref(n), C.byref(seqs)))
         self.last_n_contigs = n.value
+        self._last = (contigs, n.value, seqs)
         if self.raw_results:  # (seed_read, length, coverage) only; sequences stay in the library buffer
             return [(contigs[i].seed_read, contigs[i].length, contigs[i].coverage) for i in range(n.value)]
         out = []
@@ -365,6 +424,24 @@ class Assembler:
                 c = contigs[i]
                 out.append((c.seed_read, C.string_at(base + c.seq_offset, c.length).decode(), c.coverage))
         return out
+
+    def last_digests(self, read_id, first_id: int = 0) -> dict:
+        """md5 of the FASTA the CLI would print for the last batch (`>ID LEN COV read:READID`, bloom-dbg.h:455-487) and an
+        order/strand independent md5 over the canonical unitig sequences; read straight from the library buffers"""
+        import hashlib
+        contigs, n, seqs = self._last
+        fasta, canon = hashlib.md5(), []
+        comp = bytes.maketrans(b"ACGT", b"TGCA")
+        base = C.cast(seqs, C.c_void_p).value
+        for i in range(n):
+            c = contigs[i]
+            s = C.string_at(base + c.seq_offset, c.length)
+            fasta.update(f">{first_id + i} {c.length} {c.coverage} read:{read_id(c.seed_read)}\n".encode())
+            fasta.update(s)
+            fasta.update(b"\n")
+            rc = s.translate(comp)[::-1]
+            canon.append(hashlib.md5(min(s, rc)).digest())
+        return {"fasta_md5": fasta.hexdigest(), "unitig_multiset_md5": hashlib.md5(b"".join(sorted(canon))).hexdigest(), "unitigs": n}
 
     def read_results(self) -> np.ndarray:
         codes = _u8p()

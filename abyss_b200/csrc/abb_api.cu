@@ -3,9 +3,10 @@
 // abb_device.cuh and the kernels in abb_insert.cuh.
 #include "abb_common.h"
 #include "abb_insert.cuh"
+#include "abb_shard.cuh"
+#include <dlfcn.h>
+#include <nccl.h>
 #include <cub/device/device_scan.cuh>
-#include <cub/device/device_select.cuh>
-#include <thrust/iterator/counting_iterator.h>
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -24,7 +25,7 @@ void set_error(const char* fmt, ...)
 	va_end(ap);
 }
 
-constexpr uint64_t kDefaultWindow = 1ULL << 19;
+constexpr uint64_t kDefaultWindow = 1ULL << 17;
 constexpr uint64_t kChunkSlots = 1ULL << 25; // h0 staging: 32 Mi slots = 256 MiB + 32 MiB flags
 
 static uint64_t next_pow2(uint64_t x)
@@ -70,34 +71,61 @@ static FilterView view_of(const abb_filter* f)
 	return v;
 }
 
-/** make sure the ordered-insert workspace exists for the current window size: two tag tables so that
- *  the reservation pass of window w+1 overlaps the commit/resolve of window w */
+/** conflict-map size: 2^25 two-bit entries (8 MiB per map: with the small default window both maps, the tag prefix
+ *  and the carry lists stay resident in the 126 MB L2 next to the streaming counter sectors); exact (no aliases)
+ *  for filters of up to 2^25 positions.  ABB_MAP_LOG2 overrides (tuning). */
+static uint64_t map_entries_for(uint64_t filter_size)
+{
+	unsigned lg = 25;
+	if (const char* e = getenv("ABB_MAP_LOG2")) {
+		const int v = atoi(e);
+		if (v >= 10 && v <= 32)
+			lg = (unsigned)v;
+	}
+	uint64_t want = 1ULL << lg;
+	const uint64_t fit = std::max<uint64_t>(next_pow2(filter_size), 1024);
+	return std::min(want, fit);
+}
+
+static unsigned age_windows_for(uint64_t window)
+{
+	return (unsigned)std::min<uint64_t>(kMaxAgeWindows, ((1ULL << kPrioBits) - 2) / window - 1);
+}
+
+/** make sure the ordered-insert workspace exists for the current window size and hash count */
 static int ensure_workspace(abb_filter* f)
 {
-	const uint64_t want = next_pow2(2 * f->window * f->H);
-	if (f->d_tags && f->tag_slots == want)
+	if (f->d_carry && f->ws_window == f->window && f->ws_H == f->H)
 		return ABB_OK;
-	if (f->d_tags)
-		cudaFree(f->d_tags);
-	if (f->d_deferred)
-		cudaFree(f->d_deferred);
-	f->d_tags = nullptr;
-	f->d_deferred = nullptr;
-	ABB_CUDA(cudaMalloc((void**)&f->d_tags, 2 * want * sizeof(unsigned long long)));
-	ABB_CUDA(cudaMemsetAsync(f->d_tags, 0, 2 * want * sizeof(unsigned long long), f->stream));
-	// two carry lists (slots that lost a reservation travel to the next window), worst case everything defers
-	ABB_CUDA(cudaMalloc((void**)&f->d_deferred, 2 * (f->window + kCarryLanes) * sizeof(uint64_t)));
-	f->tag_slots = want;
-	f->epoch = 0;
-	f->epoch2[0] = f->epoch2[1] = 0;
-	if (!f->stream2) {
-		ABB_CUDA(cudaStreamCreateWithFlags(&f->stream2, cudaStreamNonBlocking));
-		for (int i = 0; i < 2; ++i) {
-			ABB_CUDA(cudaEventCreateWithFlags(&f->ev_res[i], cudaEventDisableTiming));
-			ABB_CUDA(cudaEventCreateWithFlags(&f->ev_done[i], cudaEventDisableTiming));
-		}
-		ABB_CUDA(cudaEventCreateWithFlags(&f->ev_in, cudaEventDisableTiming));
+	for (int i = 0; i < 2; ++i) {
+		cudaFree(f->d_map[i]);
+		cudaFree(f->d_tags2[i]);
+		f->d_map[i] = nullptr;
+		f->d_tags2[i] = nullptr;
 	}
+	cudaFree(f->d_carry);
+	cudaFree(f->d_slotbits);
+	f->d_carry = nullptr;
+	f->d_slotbits = nullptr;
+	f->map_entries = map_entries_for(f->size);
+	const size_t map_bytes = std::max<size_t>(f->map_entries / 4, 256);
+	// at most kCarryLanes carried slots reserve H positions each; load factor <= 1/8.  Only a prefix sized to the
+	// carried slots of a window is in use (tag_mask_for)
+	f->tag_slots = next_pow2(8ULL * kCarryLanes * f->H);
+	for (int i = 0; i < 2; ++i) {
+		ABB_CUDA(cudaMalloc((void**)&f->d_map[i], map_bytes));
+		ABB_CUDA(cudaMemsetAsync(f->d_map[i], 0, map_bytes, f->stream));
+		ABB_CUDA(cudaMalloc((void**)&f->d_tags2[i], f->tag_slots * sizeof(unsigned long long)));
+		ABB_CUDA(cudaMemsetAsync(f->d_tags2[i], 0, f->tag_slots * sizeof(unsigned long long), f->stream));
+	}
+	// worst case everything defers: window slots + the carried lanes, twice, plus the drain's sorted copy
+	ABB_CUDA(cudaMalloc((void**)&f->d_carry, 3 * (f->window + kCarryLanes) * sizeof(uint64_t)));
+	// presence bitmap of the drain: pending slots span at most age_off + 2 windows
+	f->slotbit_words = ((uint64_t)age_windows_for(f->window) + 3) * f->window / 32 + 64;
+	ABB_CUDA(cudaMalloc((void**)&f->d_slotbits, f->slotbit_words * sizeof(unsigned)));
+	ABB_CUDA(cudaMemsetAsync(f->d_slotbits, 0, f->slotbit_words * sizeof(unsigned), f->stream));
+	f->ws_window = f->window;
+	f->ws_H = f->H;
 	return ABB_OK;
 }
 
@@ -115,7 +143,24 @@ static int ensure_workspace(abb_filter* f)
 		}                                 \
 	} while (0)
 
-/** ordered insert of slots [0, n_slots) of `hashes` (h0 per slot, or literal H per slot) */
+/** cooperative launch of the persistent window kernel with as many CTAs as fit on the device */
+template <int KIND, bool LITERAL, int MAXH>
+static int launch_windows(const InsertArgs& args, int device, cudaStream_t st)
+{
+	static int grid_cache[64] = { 0 };
+	int& grid = grid_cache[device & 63];
+	if (grid == 0) {
+		int per_sm = 0, sms = 0;
+		ABB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_insert_windows<KIND, LITERAL, MAXH>, 256, 0));
+		ABB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+		grid = std::max(1, per_sm) * sms;
+	}
+	void* params[] = { (void*)&args };
+	ABB_CUDA(cudaLaunchCooperativeKernel((void*)k_insert_windows<KIND, LITERAL, MAXH>, dim3((unsigned)grid), dim3(256), params, 0, st));
+	return ABB_OK;
+}
+
+/** ordered insert of slots [0, n_slots) of `hashes` (h0 per slot, or literal H per slot); see abb_insert.cuh */
 template <bool LITERAL>
 static int ordered_insert(abb_filter* f, const uint64_t* d_hashes, const uint8_t* d_valid, uint64_t n_slots)
 {
@@ -129,85 +174,83 @@ static int ordered_insert(abb_filter* f, const uint64_t* d_hashes, const uint8_t
 		return ABB_OK;
 	}
 	ABB_CHECK(ensure_workspace(f));
-	const FilterView fv = view_of(f);
-	cudaStream_t s_main = f->stream, s_res = f->stream2;
-	// the reservation stream may start once the hashes are there
-	ABB_CUDA(cudaEventRecord(f->ev_in, s_main));
-	ABB_CUDA(cudaStreamWaitEvent(s_res, f->ev_in, 0));
-	const uint64_t n_windows = (n_slots + f->window - 1) / f->window;
-	const unsigned age_off = (unsigned)(kAge * f->window);
-	uint64_t* carry[2] = { reinterpret_cast<uint64_t*>(f->d_deferred),
-		                   reinterpret_cast<uint64_t*>(f->d_deferred) + (f->window + kCarryLanes) };
-	unsigned* n_carry[2] = { f->d_ndef, f->d_ndef + 1 };
-	ABB_CUDA(cudaMemsetAsync(f->d_ndef, 0, 2 * sizeof(unsigned), s_main));
-	bool done_recorded[2] = { false, false };
-	unsigned epoch_of[2] = { 0, 0 };
-	auto issue_reserve = [&](uint64_t w) -> int {
-		const int p = (int)(w & 1);
-		const uint64_t w0 = w * f->window;
-		const unsigned n = (unsigned)std::min<uint64_t>(f->window, n_slots - w0);
-		const TagTable tab = { f->d_tags + (uint64_t)p * f->tag_slots, f->tag_slots - 1 };
-		if (done_recorded[p]) // table p is free again once window w-2 is through
-			ABB_CUDA(cudaStreamWaitEvent(s_res, f->ev_done[p], 0));
-		if (f->epoch2[p] >= kMaxEpoch) {
-			ABB_CUDA(cudaMemsetAsync(tab.e, 0, f->tag_slots * sizeof(unsigned long long), s_res));
-			f->epoch2[p] = 0;
-		}
-		epoch_of[p] = ++f->epoch2[p];
-		ABB_DISPATCH_H(f->H, (k_reserve<LITERAL, MAXH><<<blocks_for(n, 256), 256, 0, s_res>>>(d_hashes, d_valid, w0, n, f->cfg, tab, epoch_of[p], age_off)));
-		ABB_CUDA(cudaEventRecord(f->ev_res[p], s_res));
-		return ABB_OK;
-	};
-	ABB_CHECK(issue_reserve(0));
-	int in = 0; // carry list read by this window
-	for (uint64_t w = 0; w < n_windows; ++w) {
-		const int p = (int)(w & 1);
-		const uint64_t w0 = w * f->window;
-		const unsigned n = (unsigned)std::min<uint64_t>(f->window, n_slots - w0);
-		const TagTable tab = { f->d_tags + (uint64_t)p * f->tag_slots, f->tag_slots - 1 };
-		const unsigned epoch = epoch_of[p];
-		if (w + 1 < n_windows)
-			ABB_CHECK(issue_reserve(w + 1)); // overlaps this window's commit
-		ABB_CUDA(cudaStreamWaitEvent(s_main, f->ev_res[p], 0));
-		const unsigned grid = blocks_for((uint64_t)kCarryLanes + n, 256);
-		// pending slots are drained when the list grows, every 8 windows (bounded age) and at the end
-		const bool force = (w % 8 == 7) || (w + 1 == n_windows);
-		const unsigned min_count = force ? 1u : kCarryLanes / 2;
+	cudaStream_t st = f->stream;
+	const uint64_t W = f->window;
+	const uint64_t n_windows = (n_slots + W - 1) / W;
+	ABB_REQUIRE(n_windows < (1ULL << 31), "too many windows in one call");
+	const uint64_t cap = W + kCarryLanes;
+	InsertArgs a;
+	a.hashes = d_hashes;
+	a.valid = d_valid;
+	a.n_slots = n_slots;
+	a.window = (unsigned)W;
+	a.w_begin = 0;
+	a.n_windows = (unsigned)n_windows;
+	a.cfg = f->cfg;
+	for (int i = 0; i < 2; ++i) {
+		a.map[i].w = f->d_map[i];
+		a.map[i].mask = f->map_entries - 1;
+		a.tags[i] = f->d_tags2[i];
+		a.carry[i] = f->d_carry + (uint64_t)i * cap;
+	}
+	a.tag_cap = (unsigned)f->tag_slots;
+	a.f = view_of(f);
+	a.age_off = (unsigned)(age_windows_for(W) * W);
+	a.drain_age = a.age_off / 3 * 2;
+	a.ctl = reinterpret_cast<InsertCtl*>(f->d_ctl);
+	a.stats = f->d_stats;
+	uint64_t* sorted = f->d_carry + 2 * cap;
+	// both tag tables and the control block start clean (the maps are left clean by every call)
+	ABB_CUDA(cudaMemsetAsync(f->d_ctl, 0, sizeof(InsertCtl), st));
+	for (int i = 0; i < 2; ++i)
+		ABB_CUDA(cudaMemsetAsync(f->d_tags2[i], 0, f->tag_slots * sizeof(unsigned long long), st));
+	const bool counting = f->kind == ABB_COUNTING;
+	while (a.w_begin < a.n_windows) {
+		const bool timed = f->profile && f->prof_used + 2 <= f->prof_ev.size();
+		if (timed)
+			cudaEventRecord(f->prof_ev[f->prof_used++], st);
 		ABB_DISPATCH_H(f->H, {
-			k_reserve_carry<LITERAL, MAXH><<<kCarryLanes / 256, 256, 0, s_main>>>(d_hashes, carry[in], n_carry[in], w0, f->cfg, tab, epoch, age_off);
-			if (f->profile && f->prof_used + 2 <= f->prof_ev.size())
-				cudaEventRecord(f->prof_ev[f->prof_used++], s_main);
-			if (f->kind == ABB_COUNTING)
-				k_commit<0, LITERAL, MAXH><<<grid, 256, 0, s_main>>>(d_hashes, d_valid, w0, n, f->cfg, tab, epoch, fv, age_off, carry[in], n_carry[in],
-				                                                    carry[1 - in], n_carry[1 - in], f->d_stats);
+			if (counting)
+				ABB_CHECK((launch_windows<0, LITERAL, MAXH>(a, f->device, st)));
 			else
-				k_commit<1, LITERAL, MAXH><<<grid, 256, 0, s_main>>>(d_hashes, d_valid, w0, n, f->cfg, tab, epoch, fv, age_off, carry[in], n_carry[in],
-				                                                    carry[1 - in], n_carry[1 - in], f->d_stats);
-			if (f->profile && (f->prof_used & 1))
-				cudaEventRecord(f->prof_ev[f->prof_used++], s_main);
-			if (f->kind == ABB_COUNTING)
-				k_drain<0, LITERAL, MAXH><<<1, 1024, 0, s_main>>>(d_hashes, w0, f->cfg, tab, epoch, fv, age_off, carry[1 - in], n_carry[1 - in],
-				                                                 n_carry[in], min_count, f->d_stats);
-			else
-				k_drain<1, LITERAL, MAXH><<<1, 1024, 0, s_main>>>(d_hashes, w0, f->cfg, tab, epoch, fv, age_off, carry[1 - in], n_carry[1 - in],
-				                                                 n_carry[in], min_count, f->d_stats);
+				ABB_CHECK((launch_windows<1, LITERAL, MAXH>(a, f->device, st)));
 		});
-		ABB_CUDA(cudaEventRecord(f->ev_done[p], s_main));
-		done_recorded[p] = true;
-		in = 1 - in;
-		f->st.launches += 4;
-		f->st.windows += 1;
+		if (timed)
+			cudaEventRecord(f->prof_ev[f->prof_used++], st);
+		InsertCtl h;
+		ABB_CUDA(cudaMemcpyAsync(&h, f->d_ctl, sizeof h, cudaMemcpyDeviceToHost, st));
+		ABB_CUDA(cudaStreamSynchronize(st));
+		ABB_REQUIRE(h.resume > a.w_begin && h.resume <= a.n_windows, "insert kernel made no progress (window %u of %u)", h.resume, a.n_windows);
+		if (timed)
+			f->prof_slots += std::min<uint64_t>(n_slots, (uint64_t)h.resume * W) - (uint64_t)a.w_begin * W;
+		// the list the last processed window wrote: drained when the kernel stopped for it, and at the end of the call
+		const int which = 1 - (int)((h.resume - 1) & 1);
+		const uint64_t w0 = (uint64_t)(h.resume - 1) * W;
+		const uint64_t lo_slot = w0 > (uint64_t)a.age_off + W ? w0 - a.age_off - W : 0;
+		ABB_DISPATCH_H(f->H, {
+			if (counting)
+				k_drain<0, LITERAL, MAXH><<<1, kDrainThreads, 0, st>>>(d_hashes, f->cfg, a.f, a.carry[which], a.ctl, which, 0, 1, f->d_slotbits, lo_slot,
+				                                                      sorted, f->d_stats);
+			else
+				k_drain<1, LITERAL, MAXH><<<1, kDrainThreads, 0, st>>>(d_hashes, f->cfg, a.f, a.carry[which], a.ctl, which, 0, 1, f->d_slotbits, lo_slot,
+				                                                      sorted, f->d_stats);
+		});
+		f->st.launches += 2;
+		f->st.windows += h.resume - a.w_begin;
+		a.w_begin = h.resume;
 	}
 	ABB_CUDA(cudaGetLastError());
-	if (f->profile && f->prof_used) { // fold the per-launch k_commit times into the statistics
-		ABB_CUDA(cudaStreamSynchronize(s_main));
+	if (f->profile && f->prof_used) { // fold the timed k_insert_windows launches into the statistics
+		ABB_CUDA(cudaStreamSynchronize(st));
 		for (size_t i = 0; i + 1 < f->prof_used; i += 2) {
 			float ms = 0;
 			cudaEventElapsedTime(&ms, f->prof_ev[i], f->prof_ev[i + 1]);
 			f->st.ms_commit += ms;
 			f->st.commit_launches += 1;
 		}
+		f->st.commit_slots += f->prof_slots;
 		f->prof_used = 0;
+		f->prof_slots = 0;
 	}
 	return ABB_OK;
 }
@@ -236,14 +279,6 @@ __global__ void k_chunk_bounds(const uint64_t* __restrict__ slot_offs, uint64_t 
 	if (r < n_reads)
 		bounds[++c] = n_reads;
 	*n_chunks = c;
-}
-
-__global__ void __launch_bounds__(256)
-k_gather_u64(const uint64_t* __restrict__ src, const uint64_t* __restrict__ idx, uint64_t n, uint64_t* __restrict__ dst)
-{
-	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < n)
-		dst[i] = src[idx[i]];
 }
 
 /** count valid flags (k-mers actually inserted) */
@@ -324,8 +359,10 @@ int compute_slot_offsets(unsigned k, const uint64_t* d_offs, uint64_t n_reads, D
 	return ABB_OK;
 }
 
+static int sharded_ordered_insert(abb_filter* f, abb_comm* c, const uint64_t* d_h0, const uint8_t* d_valid, uint64_t n_slots);
+
 static int insert_reads_dev(abb_filter* f, const uint8_t* d_bases, const uint64_t* d_offs, uint64_t n_reads,
-                            uint64_t* n_kmers_out)
+                            uint64_t* n_kmers_out, abb_comm* comm = nullptr)
 {
 	uint64_t total = 0;
 	ABB_CHECK(compute_slot_offsets(f->k, d_offs, n_reads, f->slot_offs, f->scan_tmp, f->stream, &total, &f->st.launches));
@@ -372,7 +409,10 @@ static int insert_reads_dev(abb_filter* f, const uint8_t* d_bases, const uint64_
 		k_count_valid<<<std::min<unsigned>(blocks_for(slots, 256), 148 * 8), 256, 0, f->stream>>>(f->valid.p, slots, f->d_stats + 3);
 		f->st.launches += 1;
 		ABB_CUDA(cudaEventRecord(f->ev1, f->stream));
-		ABB_CHECK(ordered_insert<false>(f, f->h0.p, f->valid.p, slots));
+		if (comm)
+			ABB_CHECK(sharded_ordered_insert(f, comm, f->h0.p, f->valid.p, slots));
+		else
+			ABB_CHECK(ordered_insert<false>(f, f->h0.p, f->valid.p, slots));
 		cudaEvent_t ev2 = f->ev0; // reuse: record end of insert after reading the hash time
 		ABB_CUDA(cudaEventSynchronize(f->ev1));
 		float ms = 0;
@@ -390,6 +430,210 @@ static int insert_reads_dev(abb_filter* f, const uint8_t* d_bases, const uint64_
 	f->st.kmers += nk;
 	if (n_kmers_out)
 		*n_kmers_out = nk;
+	return ABB_OK;
+}
+
+// =============================================================================================
+// multi-GPU: NCCL behind the C ABI (dlopen, no link-time dependency) and the sharded ordered insert
+// =============================================================================================
+struct NcclApi {
+	void* h = nullptr;
+	ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+	ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+	ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+	const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+
+static int load_nccl()
+{
+	if (g_nccl.h)
+		return ABB_OK;
+	const char* names[] = { getenv("ABB_NCCL_LIB"), "libnccl.so.2", "libnccl.so" };
+	void* h = nullptr;
+	for (const char* n : names)
+		if (n && *n && (h = dlopen(n, RTLD_NOW | RTLD_GLOBAL)))
+			break;
+	if (!h) {
+		set_error("cannot load NCCL (libnccl.so.2): %s", dlerror());
+		return ABB_ENODEV;
+	}
+#define ABB_NCCL_SYM(field, name)                                        \
+	do {                                                                 \
+		*(void**)(&g_nccl.field) = dlsym(h, name);                       \
+		if (!g_nccl.field) {                                             \
+			set_error("NCCL library lacks %s", name);                    \
+			return ABB_ENODEV;                                           \
+		}                                                                \
+	} while (0)
+	ABB_NCCL_SYM(GetUniqueId, "ncclGetUniqueId");
+	ABB_NCCL_SYM(CommInitRank, "ncclCommInitRank");
+	ABB_NCCL_SYM(CommDestroy, "ncclCommDestroy");
+	ABB_NCCL_SYM(AllReduce, "ncclAllReduce");
+	ABB_NCCL_SYM(AllGather, "ncclAllGather");
+	ABB_NCCL_SYM(GetErrorString, "ncclGetErrorString");
+#undef ABB_NCCL_SYM
+	g_nccl.h = h;
+	return ABB_OK;
+}
+
+#define ABB_NCCL(call)                                                                                   \
+	do {                                                                                                 \
+		ncclResult_t r__ = (call);                                                                       \
+		if (r__ != ncclSuccess) {                                                                        \
+			abb::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call, g_nccl.GetErrorString(r__)); \
+			return ABB_ECUDA;                                                                            \
+		}                                                                                                \
+	} while (0)
+
+} // namespace abb
+
+struct abb_comm {
+	ncclComm_t comm = nullptr;
+	int rank = 0, world = 1, device = 0;
+};
+
+namespace abb {
+
+static uint64_t shard_chunk(uint64_t size, unsigned world) { return ((size + world - 1) / world + 15) & ~15ULL; }
+
+/** the window of the sharded pipeline: per-rank conflict-map load like the single-GPU window */
+static uint64_t sharded_window(const abb_filter* f, unsigned world)
+{
+	uint64_t w = f->window * world;
+	if (const char* e = getenv("ABB_SHARD_WINDOW"))
+		w = strtoull(e, nullptr, 10);
+	return std::min<uint64_t>(std::max<uint64_t>(w, 32), 1ULL << 21);
+}
+
+static int sharded_ordered_insert(abb_filter* f, abb_comm* c, const uint64_t* d_h0, const uint8_t* d_valid, uint64_t n_slots)
+{
+	if (n_slots == 0)
+		return ABB_OK;
+	const uint64_t user_window = f->window;
+	f->window = sharded_window(f, (unsigned)c->world);
+	int rc = ensure_workspace(f);
+	const uint64_t W = f->window;
+	f->window = user_window;
+	ABB_CHECK(rc);
+	ABB_CHECK(f->sh_buf.reserve(2 * (W + kCarryLanes) + 64));
+	cudaStream_t st = f->stream;
+	const uint64_t n_windows = (n_slots + W - 1) / W;
+	const unsigned age_off = (unsigned)(age_windows_for(W) * W);
+	const unsigned drain_age = age_off / 3 * 2;
+	const uint64_t cap = W + kCarryLanes;
+	uint64_t* carry[2] = { f->d_carry, f->d_carry + cap };
+	ShardCtl* ctl = reinterpret_cast<ShardCtl*>(f->d_ctl);
+	unsigned* d_nout = f->d_ctl + 4; // [n_out]; the ctl block has 8 words
+	const size_t map_bytes = std::max<size_t>(f->map_entries / 4, 256);
+	ConflictMap maps[2] = { { f->d_map[0], f->map_entries - 1 }, { f->d_map[1], f->map_entries - 1 } };
+	const uint64_t chunk = shard_chunk(f->size, (unsigned)c->world);
+	Shard sh;
+	sh.lo = std::min<uint64_t>(f->size, (uint64_t)c->rank * chunk);
+	sh.hi = std::min<uint64_t>(f->size, sh.lo + chunk);
+	{
+		ShardCtl init;
+		init.n_pending = 0;
+		init.pad = 0;
+		init.lo_pending = ~0ULL;
+		ABB_CUDA(cudaMemcpyAsync(ctl, &init, sizeof init, cudaMemcpyHostToDevice, st));
+		ABB_CUDA(cudaMemsetAsync(d_nout, 0, 4 * sizeof(unsigned), st));
+	}
+	unsigned n_in = 0; // host copy of the carry length (identical on every rank)
+	uint64_t oldest = 0;
+	int in = 0, p = 0;
+	uint8_t* buf = f->sh_buf.p;
+	// one step of the pipeline: the oldest carried slots + the n new slots of [w0, w0 + n); marks [w1, w1 + n_next)
+	auto step = [&](uint64_t w0, unsigned n, uint64_t w1, unsigned n_next) -> int {
+		const unsigned lanes_c = std::min<unsigned>(n_in, kCarryLanes);
+		// the tag table prefix this step uses (sized to the carried lanes), cleared first
+		uint64_t tslots = 4096;
+		while (tslots < 8ULL * lanes_c * f->H && tslots < f->tag_slots)
+			tslots <<= 1;
+		const TagTable tab = { f->d_tags2[0], std::min<uint64_t>(tslots, f->tag_slots) - 1 };
+		if (lanes_c)
+			ABB_CUDA(cudaMemsetAsync(tab.e, 0, (tab.mask + 1) * sizeof(unsigned long long), st));
+		const unsigned lanes = lanes_c + n;
+		const uint64_t lo_slot = w0 > (uint64_t)age_off + W ? w0 - age_off - W : 0;
+		uint8_t* pm = buf;
+		uint8_t* ok = buf + lanes;
+		const bool timed = f->profile && n && (f->st.windows % f->prof_stride) == 0 && f->prof_used + 2 <= f->prof_ev.size();
+		ABB_DISPATCH_H(f->H, {
+			if (lanes_c)
+				k_sh_mark_carry<false, MAXH><<<blocks_for(lanes_c, 256), 256, 0, st>>>(d_h0, carry[in], lanes_c, w0, f->cfg, tab, age_off, maps[p], sh);
+			if (timed)
+				cudaEventRecord(f->prof_ev[f->prof_used++], st);
+			k_sh_gather<false, MAXH><<<blocks_for((uint64_t)lanes_c + std::max(n, n_next), 256), 256, 0, st>>>(
+			    d_h0, d_valid, w0, n, w1, n_next, f->cfg, maps[p], maps[1 - p], tab, f->d_data, age_off, carry[in], lanes_c, sh, pm, ok);
+		});
+		if (lanes) {
+			ABB_NCCL(g_nccl.AllReduce(buf, buf, 2 * (size_t)lanes, ncclUint8, ncclMin, c->comm, st));
+			ABB_DISPATCH_H(f->H, (k_sh_apply<false, MAXH><<<blocks_for((uint64_t)n_in + n, 256), 256, 0, st>>>(
+			                         d_h0, d_valid, w0, n, f->cfg, tab, f->d_data, carry[in], n_in, lanes_c, sh, pm, ok, f->d_slotbits, lo_slot, ctl,
+			                         f->d_stats)));
+			if (timed) {
+				cudaEventRecord(f->prof_ev[f->prof_used++], st);
+				f->prof_slots += n;
+			}
+			k_sh_compact<<<1, kDrainThreads, 0, st>>>(f->d_slotbits, lo_slot, w0 + std::max<uint64_t>(n, 1), carry[1 - in], ctl, d_nout);
+			unsigned h_n = 0;
+			ABB_CUDA(cudaMemcpyAsync(&h_n, d_nout, sizeof h_n, cudaMemcpyDeviceToHost, st));
+			if (h_n || true) // the oldest pending slot bounds the priorities
+				ABB_CUDA(cudaMemcpyAsync(&oldest, carry[1 - in], sizeof oldest, cudaMemcpyDeviceToHost, st));
+			ABB_CUDA(cudaStreamSynchronize(st));
+			n_in = h_n;
+			in = 1 - in;
+			f->st.launches += 4;
+		} else {
+			if (timed)
+				f->prof_used--; // nothing was applied
+			f->st.launches += 1;
+		}
+		return ABB_OK;
+	};
+	// everything pending is retired by steps without new slots (the oldest kCarryLanes take part in each)
+	auto drain = [&](uint64_t w0, unsigned until) -> int {
+		while (n_in > until) {
+			ABB_CHECK(step(w0, 0, w0, 0));
+			f->sh_drains += 1;
+		}
+		return ABB_OK;
+	};
+	f->prof_stride = f->prof_ev.empty() ? 1 : std::max<uint64_t>(1, (2 * n_windows + f->prof_ev.size() - 1) / f->prof_ev.size());
+	ABB_CHECK(step(0, 0, 0, (unsigned)std::min<uint64_t>(W, n_slots))); // marks of window 0
+	p = 1 - p; // the marks went to maps[1 - p]
+	for (uint64_t w = 0; w < n_windows; ++w) {
+		const uint64_t w0 = w * W;
+		const unsigned n = (unsigned)std::min<uint64_t>(W, n_slots - w0);
+		const uint64_t w1 = w0 + W;
+		const unsigned n_next = w + 1 < n_windows ? (unsigned)std::min<uint64_t>(W, n_slots - w1) : 0u;
+		if (n_in > kCarryLanes)
+			ABB_CHECK(drain(w0, kCarryLanes / 2));
+		if (n_in && w0 - oldest > drain_age)
+			ABB_CHECK(drain(w0, 0));
+		ABB_CHECK(step(w0, n, w1, n_next));
+		ABB_CUDA(cudaMemsetAsync(maps[p].w, 0, map_bytes, st));
+		p = 1 - p;
+		f->st.windows += 1;
+	}
+	ABB_CHECK(drain(n_slots, 0));
+	ABB_CUDA(cudaGetLastError());
+	if (f->profile && f->prof_used) {
+		ABB_CUDA(cudaStreamSynchronize(st));
+		for (size_t i = 0; i + 1 < f->prof_used; i += 2) {
+			float ms = 0;
+			cudaEventElapsedTime(&ms, f->prof_ev[i], f->prof_ev[i + 1]);
+			f->st.ms_commit += ms;
+			f->st.commit_launches += 1;
+		}
+		f->st.commit_slots += f->prof_slots;
+		f->prof_used = 0;
+		f->prof_slots = 0;
+	}
+	// leave the shared control block in the single-GPU layout
+	ABB_CUDA(cudaMemsetAsync(f->d_ctl, 0, 8 * sizeof(unsigned), st));
 	return ABB_OK;
 }
 
@@ -485,10 +729,11 @@ int abb_filter_create(abb_filter** out, int kind, uint64_t size, unsigned num_ha
 	ABB_TRY(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
 	ABB_TRY(cudaEventCreate(&f->ev0));
 	ABB_TRY(cudaEventCreate(&f->ev1));
-	ABB_TRY(cudaMalloc((void**)&f->d_data, f->bytes_per_level * levels));
+	// slack: the in-place all-gather of position shards rounds each shard up to 16 bytes (abb_filter_allgather)
+	ABB_TRY(cudaMalloc((void**)&f->d_data, f->bytes_per_level * levels + 4096));
 	ABB_TRY(cudaMemsetAsync(f->d_data, 0, f->bytes_per_level * levels, f->stream));
-	ABB_TRY(cudaMalloc((void**)&f->d_ndef, 2 * sizeof(unsigned)));
-	ABB_TRY(cudaMemsetAsync(f->d_ndef, 0, 2 * sizeof(unsigned), f->stream));
+	ABB_TRY(cudaMalloc((void**)&f->d_ctl, 8 * sizeof(unsigned)));
+	ABB_TRY(cudaMemsetAsync(f->d_ctl, 0, 8 * sizeof(unsigned), f->stream));
 	ABB_TRY(cudaMalloc((void**)&f->d_stats, 8 * sizeof(unsigned long long)));
 	ABB_TRY(cudaMemsetAsync(f->d_stats, 0, 8 * sizeof(unsigned long long), f->stream));
 	if (!f->mask.empty()) {
@@ -513,9 +758,13 @@ int abb_filter_destroy(abb_filter* f)
 		cudaStreamSynchronize(f->stream);
 	cudaFree(f->d_data);
 	cudaFree(f->d_care);
-	cudaFree(f->d_tags);
-	cudaFree(f->d_deferred);
-	cudaFree(f->d_ndef);
+	cudaFree(f->d_tags2[0]);
+	cudaFree(f->d_tags2[1]);
+	cudaFree(f->d_map[0]);
+	cudaFree(f->d_map[1]);
+	cudaFree(f->d_carry);
+	cudaFree(f->d_slotbits);
+	cudaFree(f->d_ctl);
 	cudaFree(f->d_stats);
 	f->bases.release();
 	f->offs.release();
@@ -525,17 +774,9 @@ int abb_filter_destroy(abb_filter* f)
 	f->valid.release();
 	f->scan_tmp.release();
 	f->out8.release();
+	f->sh_buf.release();
 	for (auto e : f->prof_ev)
 		cudaEventDestroy(e);
-	if (f->stream2) {
-		cudaStreamSynchronize(f->stream2);
-		for (int i = 0; i < 2; ++i) {
-			cudaEventDestroy(f->ev_res[i]);
-			cudaEventDestroy(f->ev_done[i]);
-		}
-		cudaEventDestroy(f->ev_in);
-		cudaStreamDestroy(f->stream2);
-	}
 	if (f->ev0)
 		cudaEventDestroy(f->ev0);
 	if (f->ev1)
@@ -570,7 +811,7 @@ int abb_filter_set_profiling(abb_filter* f, int on)
 	ABB_CUDA(cudaSetDevice(f->device));
 	f->profile = on != 0;
 	if (f->profile && f->prof_ev.empty()) {
-		f->prof_ev.resize(256);
+		f->prof_ev.resize(2048);
 		for (auto& e : f->prof_ev)
 			ABB_CUDA(cudaEventCreate(&e));
 	}
@@ -614,7 +855,37 @@ int abb_insert_reads(abb_filter* f, const char* bases, const uint64_t* offsets, 
 	ABB_CHECK(f->offs.reserve(n_reads + 1));
 	ABB_CUDA(cudaMemcpyAsync(f->bases.p, bases, n_bases, cudaMemcpyHostToDevice, f->stream));
 	ABB_CUDA(cudaMemcpyAsync(f->offs.p, offsets, (n_reads + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, f->stream));
+	f->resident_reads = n_reads;
 	return insert_reads_dev(f, f->bases.p, f->offs.p, n_reads, n_kmers_out);
+}
+
+int abb_insert_reads_sharded(abb_filter* f, abb_comm* c, const char* bases, const uint64_t* offsets, uint64_t n_reads, int finalize,
+                             uint64_t* n_kmers_out)
+{
+	ABB_REQUIRE(f && c, "NULL argument");
+	if (n_kmers_out)
+		*n_kmers_out = 0;
+	ABB_REQUIRE(n_reads == 0 || (bases && offsets), "NULL read buffers");
+	ABB_REQUIRE(n_reads == 0 || offsets[0] == 0, "offsets[0] must be 0");
+	ABB_CUDA(cudaSetDevice(f->device));
+	if (n_reads) {
+		const uint64_t n_bases = offsets[n_reads];
+		ABB_CHECK(f->bases.reserve(n_bases + 16));
+		ABB_CHECK(f->offs.reserve(n_reads + 1));
+		ABB_CUDA(cudaMemcpyAsync(f->bases.p, bases, n_bases, cudaMemcpyHostToDevice, f->stream));
+		ABB_CUDA(cudaMemcpyAsync(f->offs.p, offsets, (n_reads + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, f->stream));
+	}
+	f->resident_reads = n_reads;
+	return abb_insert_reads_sharded_dev(f, c, (const char*)f->bases.p, f->offs.p, n_reads, finalize, n_kmers_out);
+}
+
+int abb_filter_resident_reads(abb_filter* f, const char** d_bases, const uint64_t** d_offsets, uint64_t* n_reads)
+{
+	ABB_REQUIRE(f && d_bases && d_offsets && n_reads, "NULL argument");
+	*d_bases = (const char*)f->bases.p;
+	*d_offsets = f->offs.p;
+	*n_reads = f->resident_reads;
+	return ABB_OK;
 }
 
 int abb_insert_hashes(abb_filter* f, const uint64_t* hashes, uint64_t n)
@@ -669,65 +940,104 @@ int abb_hash_reads_dev(abb_filter* f, const char* d_bases, const uint64_t* d_off
 	return ABB_OK;
 }
 
-/** owner of a canonical hash among `world` contiguous hash ranges (abyss_b200/multigpu.py owner_of) */
-struct OwnedBy {
-	const uint64_t* h0;
-	const uint8_t* valid;
-	unsigned world, g;
-	__host__ __device__ bool operator()(uint64_t i) const
-	{
-		return valid[i] && (unsigned)((((h0[i] >> 48) & 0xFFFF) * world) >> 16) == g;
-	}
-};
-struct GatherH0 {
-	const uint64_t* h0;
-	__host__ __device__ uint64_t operator()(uint64_t i) const { return h0[i]; }
-};
-
-int abb_route_h0_dev(abb_filter* f, const uint64_t* d_h0, const uint8_t* d_valid, uint64_t n, unsigned world, uint64_t* d_send,
-                     uint64_t* counts_out)
+int abb_comm_unique_id(uint8_t id_out[128])
 {
-	ABB_REQUIRE(f && counts_out, "NULL argument");
-	ABB_REQUIRE(world >= 1 && world <= 65536, "world size out of range");
-	for (unsigned g = 0; g < world; ++g)
-		counts_out[g] = 0;
-	if (n == 0)
-		return ABB_OK;
-	ABB_REQUIRE(d_h0 && d_valid && d_send, "NULL buffer");
-	ABB_REQUIRE(n < (1ULL << 40), "too many slots");
-	ABB_CUDA(cudaSetDevice(f->device));
-	// one order-preserving selection per destination: d_send = [slots owned by 0 | owned by 1 | ...]
-	DevBuf<uint64_t> idx; // selected slot indices of one destination, then gathered
-	unsigned long long* d_num = f->d_stats + 6;
-	uint64_t at = 0;
-	// select indices in pieces of < 2^31 items (cub's num_items is an int here)
-	const uint64_t piece = 1ULL << 30;
-	for (unsigned g = 0; g < world; ++g) {
-		uint64_t got = 0;
-		for (uint64_t lo = 0; lo < n; lo += piece) {
-			const int m = (int)std::min<uint64_t>(piece, n - lo);
-			OwnedBy pred{ d_h0, d_valid, world, g };
-			thrust::counting_iterator<uint64_t> first(lo);
-			size_t bytes = 0;
-			ABB_CHECK(idx.reserve((size_t)m));
-			ABB_CUDA(cub::DeviceSelect::If(nullptr, bytes, first, idx.p, d_num, m, pred, f->stream));
-			ABB_CHECK(f->scan_tmp.reserve(bytes));
-			ABB_CUDA(cub::DeviceSelect::If(f->scan_tmp.p, bytes, first, idx.p, d_num, m, pred, f->stream));
-			unsigned long long k = 0;
-			ABB_CUDA(cudaMemcpyAsync(&k, d_num, sizeof k, cudaMemcpyDeviceToHost, f->stream));
-			ABB_CUDA(cudaStreamSynchronize(f->stream));
-			if (k) {
-				k_gather_u64<<<blocks_for(k, 256), 256, 0, f->stream>>>(d_h0, idx.p, k, d_send + at + got);
-				ABB_CUDA(cudaGetLastError());
-			}
-			got += k;
-			f->st.launches += 2;
-		}
-		counts_out[g] = got;
-		at += got;
+	ABB_REQUIRE(id_out, "NULL id buffer");
+	ABB_CHECK(load_nccl());
+	static_assert(sizeof(ncclUniqueId) == 128, "NCCL unique id size");
+	ncclUniqueId id;
+	ABB_NCCL(g_nccl.GetUniqueId(&id));
+	memcpy(id_out, &id, sizeof id);
+	return ABB_OK;
+}
+
+int abb_comm_create(abb_comm** out, int rank, int world, const uint8_t id[128], int device)
+{
+	ABB_REQUIRE(out && id, "NULL argument");
+	*out = nullptr;
+	ABB_REQUIRE(world >= 1 && world <= 64 && rank >= 0 && rank < world, "rank %d / world %d out of range", rank, world);
+	ABB_CHECK(load_nccl());
+	ABB_CHECK(select_device(device));
+	abb_comm* c = new (std::nothrow) abb_comm();
+	if (!c) {
+		set_error("out of host memory");
+		return ABB_ENOMEM;
 	}
+	c->rank = rank;
+	c->world = world;
+	c->device = device;
+	ncclUniqueId nid;
+	memcpy(&nid, id, sizeof nid);
+	ncclResult_t r = g_nccl.CommInitRank(&c->comm, world, nid, rank);
+	if (r != ncclSuccess) {
+		set_error("ncclCommInitRank failed: %s", g_nccl.GetErrorString(r));
+		delete c;
+		return ABB_ECUDA;
+	}
+	*out = c;
+	return ABB_OK;
+}
+
+int abb_comm_destroy(abb_comm* c)
+{
+	if (!c)
+		return ABB_OK;
+	cudaSetDevice(c->device);
+	if (c->comm && g_nccl.CommDestroy)
+		g_nccl.CommDestroy(c->comm);
+	delete c;
+	return ABB_OK;
+}
+
+int abb_comm_rank(const abb_comm* c) { return c ? c->rank : 0; }
+int abb_comm_world(const abb_comm* c) { return c ? c->world : 1; }
+
+int abb_filter_allgather(abb_filter* f, abb_comm* c)
+{
+	ABB_REQUIRE(f && c, "NULL argument");
+	ABB_REQUIRE(f->levels == 1, "only single-level filters are sharded");
+	ABB_CUDA(cudaSetDevice(f->device));
+	if (c->world == 1)
+		return ABB_OK;
+	const uint64_t chunk = shard_chunk(f->bytes_per_level, (unsigned)c->world);
+	ABB_REQUIRE(chunk * c->world <= f->bytes_per_level + 4096, "too many ranks for the all-gather slack");
+	ABB_NCCL(g_nccl.AllGather(f->d_data + (uint64_t)c->rank * chunk, f->d_data, chunk, ncclUint8, c->comm, f->stream));
 	ABB_CUDA(cudaStreamSynchronize(f->stream));
-	idx.release();
+	return ABB_OK;
+}
+
+int abb_comm_allgather_bytes(abb_comm* c, void* d_buf, uint64_t bytes_per_rank, void* cuda_stream)
+{
+	ABB_REQUIRE(c && (d_buf || bytes_per_rank == 0), "NULL argument");
+	if (c->world == 1 || bytes_per_rank == 0)
+		return ABB_OK;
+	ABB_CUDA(cudaSetDevice(c->device));
+	ABB_NCCL(g_nccl.AllGather((const uint8_t*)d_buf + (uint64_t)c->rank * bytes_per_rank, d_buf, bytes_per_rank, ncclUint8, c->comm,
+	                          (cudaStream_t)cuda_stream));
+	return ABB_OK;
+}
+
+int abb_comm_allreduce_max_u8(abb_comm* c, void* d_buf, uint64_t n, void* cuda_stream)
+{
+	ABB_REQUIRE(c && (d_buf || n == 0), "NULL argument");
+	if (c->world == 1 || n == 0)
+		return ABB_OK;
+	ABB_CUDA(cudaSetDevice(c->device));
+	ABB_NCCL(g_nccl.AllReduce(d_buf, d_buf, n, ncclUint8, ncclMax, c->comm, (cudaStream_t)cuda_stream));
+	return ABB_OK;
+}
+
+int abb_insert_reads_sharded_dev(abb_filter* f, abb_comm* c, const char* d_bases, const uint64_t* d_offsets, uint64_t n_reads,
+                                 int finalize, uint64_t* n_kmers_out)
+{
+	ABB_REQUIRE(f && c, "NULL argument");
+	ABB_REQUIRE(f->kind == ABB_COUNTING, "the sharded insert is implemented for counting filters");
+	ABB_REQUIRE(n_reads == 0 || (d_bases && d_offsets), "NULL read buffers");
+	ABB_REQUIRE(f->device == c->device, "filter and communicator live on different devices");
+	ABB_CUDA(cudaSetDevice(f->device));
+	ABB_CHECK(insert_reads_dev(f, (const uint8_t*)d_bases, d_offsets, n_reads, n_kmers_out, c->world > 1 ? c : nullptr));
+	if (finalize)
+		ABB_CHECK(abb_filter_allgather(f, c));
 	return ABB_OK;
 }
 
@@ -901,9 +1211,12 @@ int abb_filter_insert_stats(abb_filter* f, abb_insert_stats* out, int reset)
 	ABB_CUDA(cudaMemcpyAsync(h, f->d_stats, sizeof h, cudaMemcpyDeviceToHost, f->stream));
 	ABB_CUDA(cudaStreamSynchronize(f->stream));
 	f->st.deferred = h[0];
+	f->st.drains = h[1] + f->sh_drains;
+	f->st.drained_slots = h[2];
 	if (out)
 		*out = f->st;
 	if (reset) {
+		f->sh_drains = 0;
 		f->st = abb_insert_stats{};
 		ABB_CUDA(cudaMemsetAsync(f->d_stats, 0, 3 * sizeof(unsigned long long), f->stream));
 	}

@@ -99,26 +99,30 @@ struct abb_filter {
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
-	// ordered-insert workspace
-	uint64_t window = 0; // slots per window
-	unsigned long long* d_tags = nullptr;
+	// ordered-insert workspace (abb_insert.cuh K2)
+	uint64_t window = 0;      // slots per window
+	uint64_t ws_window = 0;   // window the workspace below was sized for
+	unsigned ws_H = 0;
+	uint64_t map_entries = 0; // two-bit entries per conflict map (power of two)
+	unsigned* d_map[2] = { nullptr, nullptr };
+	unsigned long long* d_tags2[2] = { nullptr, nullptr }; // tag tables of the carried slots (alternating windows)
 	uint64_t tag_slots = 0;
-	unsigned epoch = 0;
-	unsigned epoch2[2] = { 0, 0 };          // per tag table
-	cudaStream_t stream2 = nullptr;         // reservation pass of the next window
-	cudaEvent_t ev_res[2] = { nullptr, nullptr }, ev_done[2] = { nullptr, nullptr }, ev_in = nullptr;
-	unsigned* d_deferred = nullptr;          // two carry lists of uint64 slot ids
-	unsigned* d_ndef = nullptr;
-	unsigned long long* d_stats = nullptr; // [0] deferred [1] max rounds [2] serial [3..4] popcount scratch
+	uint64_t* d_carry = nullptr;    // two carry lists and the drain's sorted list, (window + kCarryLanes) slots each
+	unsigned* d_slotbits = nullptr; // presence bitmap of the drain
+	uint64_t slotbit_words = 0;
+	unsigned* d_ctl = nullptr;             // abb::InsertCtl
+	unsigned long long* d_stats = nullptr; // [0] deferred [1] drains [2] slots replayed by drains [3..4] popcount scratch
 
-	// per-call buffers
+	// per-call buffers (bases/offs keep the device copy of the last host batch: abb_filter_resident_reads)
+	uint64_t resident_reads = 0;
 	abb::DevBuf<uint8_t> bases;
 	abb::DevBuf<uint64_t> offs, slot_offs, h0, lit;
-	abb::DevBuf<uint8_t> valid, scan_tmp, out8;
+	abb::DevBuf<uint8_t> valid, scan_tmp, out8, sh_buf;
 
 	// statistics
 	abb_insert_stats st = {};
-	bool profile = false; // time every k_commit launch with CUDA events
+	bool profile = false; // time the k_window launches with CUDA events (every prof_stride-th window)
+	uint64_t prof_stride = 1, prof_slots = 0, sh_drains = 0;
 	std::vector<cudaEvent_t> prof_ev;
 	size_t prof_used = 0;
 };

@@ -10,76 +10,72 @@
 // equal to it, so the final array depends on the order in which k-mers that share a counter are
 // inserted; the unitig FASTA prints sums of raw counters (bloom-dbg.h:599-603) and thresholds
 // them, so "same FASTA as the reference at -j1" means "same counters as the sequential,
-// file-order insert".  The cascading filter has the same property.  The scheme (deterministic
-// reservations):
+// file-order insert".  The cascading filter has the same property.  The scheme (round 2):
 //   * k-mer windows ("slots") are numbered in file order; a batch is cut into ordered windows of
 //     W slots; windows run one after another, slots inside a window run in parallel.
-//   * reserve: every valid slot i writes (position, i) for each of its H filter positions into an
-//     L2-resident open-addressing tag table keyed by the exact position, keeping the minimum i.
-//   * commit: slot i owns position p iff the table says min == i.  A slot that owns all of its
-//     positions has no earlier unfinished slot touching any of them, and no later slot can commit
-//     before it (it does not own the shared position), so applying it now is what the sequential
-//     order would do; owners touch pairwise disjoint positions, so plain byte loads/stores are
-//     race free.  Slots that lost a reservation are appended to a deferred list.
-//     Owners "release" their table entries (priority field := all ones) after applying.
-//   * carry: the slots that lost a reservation are simply carried into the next window, where they
-//     are the oldest pending events: priority = slot - window_start + kAge * W, so pending slots of
-//     up to kAge earlier windows sort before every slot of the current window, in file order.  A
-//     tiny kernel adds their reservations to the next window's table, the next commit kernel
-//     gives them threads of their own.  Nothing serial remains on the per-window critical path.
-//   * drain: one CTA replays whatever is still pending with the same reserve/commit/release rule
-//     round by round (then strictly in order) -- every 8 windows, when the carry list grows large
-//     (one k-mer repeated thousands of times), and at the end of a call.
-// Table entries are [epoch:4 | position:36 | priority:24]; an entry from an older epoch is free, so
-// a table is cleared only once every 15 uses.
+//   * conflict map: every slot of window w marks its H filter positions in an L2-resident map of
+//     two-bit entries (entry = position mod E): "touched" / "touched again".  A slot none of whose
+//     entries was touched again shares no counter with any other pending event: it commutes with
+//     all of them, so it applies its min-increment at once with plain byte loads/stores.  That is
+//     ~97 % of the slots and costs one L2 atomic + one L2 load per position on top of the HBM
+//     accesses themselves (round 1: CAS + probe + release on an 8-byte tag per position).
+//     The marks of window w+1 are written by the kernel that applies window w.
+//   * carry: the slots that saw "touched again" (true sharing, or an alias in the map) are carried
+//     into the next window as its OLDEST events.  Carried slots are few, so they use an exact
+//     open-addressing tag table keyed by the position: reserve keeps the minimum priority
+//     (= file order), a carried slot that owns all its positions applies, the others are carried
+//     again.  Carried slots also mark their positions "touched again" in the next window's map, so
+//     every new slot that shares a counter with them waits.  One chain link resolves per window.
+//   * drain: when more than kCarryLanes slots are pending (dense filters: everything conflicts), a
+//     pending slot gets old, or the call ends, one CTA sorts the pending slots by file order
+//     (presence bitmap), stages the counters they touch in shared memory chunk by chunk (one HBM
+//     round trip per chunk) and replays them sequentially there -- about 20 ns per slot instead of
+//     a dependent HBM round trip.
+// Tag entries are [epoch:4 | position:36 | priority:24]; an entry from an older epoch is free, so
+// the table is cleared only once every 15 windows.
 #pragma once
 #include "abb_device.cuh"
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 namespace abb {
+namespace cg = cooperative_groups;
 
-constexpr unsigned kSlotBits = 24;                  // priority = slot - window start + kAge * W  <  (kAge + 1) * W
-constexpr unsigned kAge = 15;                       // a pending slot is drained before it is this many windows old
-constexpr unsigned kCarryLanes = 1u << 16;          // threads a commit launch reserves for carried slots
-constexpr unsigned kPosBits = 36;                   // filters up to 2^36 counters / bits
-constexpr unsigned kEpochBits = 64 - kSlotBits - kPosBits;
-constexpr uint64_t kSlotMask = (1ULL << kSlotBits) - 1;
-constexpr unsigned kMaxEpoch = (1u << kEpochBits) - 1; // epoch 0 = never written (memset 0)
+constexpr unsigned kPrioBits = 28;                  // priority of a carried slot = age_off - (window start - slot) < 2^28 - 1
+constexpr unsigned kMaxAgeWindows = 48;             // age_off = min(kMaxAgeWindows, 2^28 / W - 1) windows; drain at 2/3 of it
+constexpr unsigned kCarryLanes = 1u << 16;          // most carried slots a window serves = drain threshold
+constexpr unsigned kPosBits = 36;                   // filters up to 2^36 - 1 counters / bits
+constexpr uint64_t kPrioMask = (1ULL << kPrioBits) - 1;
 
+/** exact open-addressing table of the positions the carried slots want: entry = [position + 1 : 36 | priority : 28],
+ *  0 = empty.  `mask` selects the prefix of the allocation in use (sized to the number of carried slots), so that
+ *  clearing it costs almost nothing. */
 struct TagTable {
 	unsigned long long* e; // entries
-	uint64_t mask;         // slots - 1 (power of two)
+	uint64_t mask;         // slots in use - 1 (power of two)
 };
 
-ABB_D uint64_t tag_pack(unsigned epoch, uint64_t pos, uint64_t slot)
-{
-	return ((uint64_t)epoch << (kPosBits + kSlotBits)) | (pos << kSlotBits) | slot;
-}
+ABB_D uint64_t tag_pack(uint64_t pos, uint64_t prio) { return ((pos + 1) << kPrioBits) | prio; }
 ABB_D uint64_t tag_home(uint64_t pos, const TagTable& t)
 {
 	// Fibonacci hashing of the position
 	return ((pos * 0x9E3779B97F4A7C15ULL) >> 20) & t.mask;
 }
 
-/** record "slot wants pos" keeping the smallest slot for this epoch */
-ABB_D void tag_reserve(const TagTable& t, unsigned epoch, uint64_t pos, uint64_t slot)
+/** record "prio wants pos" keeping the smallest priority */
+ABB_D void tag_reserve(const TagTable& t, uint64_t pos, uint64_t prio)
 {
-	const uint64_t mine = tag_pack(epoch, pos, slot);
-	const uint64_t key = mine >> kSlotBits;
+	const uint64_t mine = tag_pack(pos, prio);
+	const uint64_t key = mine >> kPrioBits;
 	uint64_t s = tag_home(pos, t);
 	for (;;) {
 		unsigned long long cur = __ldcg(&t.e[s]);
-		for (;;) {
-			if ((cur >> (kPosBits + kSlotBits)) != epoch) { // stale or empty: claim it
-				unsigned long long old = atomicCAS(&t.e[s], cur, (unsigned long long)mine);
-				if (old == cur)
-					return;
-				cur = old;
-				continue;
-			}
-			break;
+		if (cur == 0) {
+			cur = atomicCAS(&t.e[s], 0ULL, (unsigned long long)mine);
+			if (cur == 0)
+				return;
 		}
-		if ((cur >> kSlotBits) == key) {
+		if ((cur >> kPrioBits) == key) {
 			if (mine < cur)
 				atomicMin(&t.e[s], (unsigned long long)mine);
 			return;
@@ -88,48 +84,32 @@ ABB_D void tag_reserve(const TagTable& t, unsigned epoch, uint64_t pos, uint64_t
 	}
 }
 
-/** smallest slot that reserved pos in this epoch (pos must have been reserved) */
-ABB_D uint64_t tag_owner(const TagTable& t, unsigned epoch, uint64_t pos)
+/** smallest priority that reserved pos (pos must have been reserved); *where = its entry */
+ABB_D uint64_t tag_owner_at(const TagTable& t, uint64_t pos, uint64_t* where)
 {
-	const uint64_t key = tag_pack(epoch, pos, 0) >> kSlotBits;
+	const uint64_t key = pos + 1;
 	uint64_t s = tag_home(pos, t);
 	for (;;) {
 		unsigned long long cur = __ldcg(&t.e[s]);
-		if ((cur >> kSlotBits) == key)
-			return cur & kSlotMask;
-		s = (s + 1) & t.mask;
-	}
-}
-
-/** like tag_owner, also reporting where the entry lives so that the release needs no second probe */
-ABB_D uint64_t tag_owner_at(const TagTable& t, unsigned epoch, uint64_t pos, uint64_t* where)
-{
-	const uint64_t key = tag_pack(epoch, pos, 0) >> kSlotBits;
-	uint64_t s = tag_home(pos, t);
-	for (;;) {
-		unsigned long long cur = __ldcg(&t.e[s]);
-		if ((cur >> kSlotBits) == key) {
+		if ((cur >> kPrioBits) == key) {
 			*where = s;
-			return cur & kSlotMask;
+			return cur & kPrioMask;
 		}
 		s = (s + 1) & t.mask;
 	}
 }
-
-/** the owner is done with pos: later slots may now win it (slot field := kSlotMask) */
-ABB_D void tag_release(const TagTable& t, unsigned epoch, uint64_t pos)
+ABB_D uint64_t tag_owner(const TagTable& t, uint64_t pos)
 {
-	const uint64_t rel = tag_pack(epoch, pos, kSlotMask);
-	const uint64_t key = rel >> kSlotBits;
-	uint64_t s = tag_home(pos, t);
-	for (;;) {
-		unsigned long long cur = __ldcg(&t.e[s]);
-		if ((cur >> kSlotBits) == key) {
-			__stcg(&t.e[s], (unsigned long long)rel);
-			return;
-		}
-		s = (s + 1) & t.mask;
-	}
+	uint64_t where;
+	return tag_owner_at(t, pos, &where);
+}
+/** the owner is done with pos: younger slots may now win it (priority field := all ones) */
+ABB_D void tag_release_at(const TagTable& t, uint64_t pos, uint64_t where) { __stcg(&t.e[where], (unsigned long long)tag_pack(pos, kPrioMask)); }
+ABB_D void tag_release(const TagTable& t, uint64_t pos)
+{
+	uint64_t where;
+	tag_owner_at(t, pos, &where);
+	tag_release_at(t, pos, where);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -371,7 +351,6 @@ static __global__ void k_window_counts(const uint64_t* __restrict__ offs, uint64
 // ------------------------------------------------------------------------------------------
 // K2: ordered insert over one window of slots [w0, w0 + n)
 // ------------------------------------------------------------------------------------------
-constexpr unsigned kMaxRounds = 48;
 
 /** positions of slot s: either derived from h0 (stride 1) or read from the literal
  *  H-per-k-mer array of the reference interface */
@@ -391,21 +370,61 @@ ABB_D void slot_positions(const uint64_t* __restrict__ hashes, uint64_t s, const
 				pos[i] = nth_pos(h0, cfg, i);
 	}
 }
+/** one position of slot s */
+template <bool LITERAL>
+ABB_D uint64_t slot_position(const uint64_t* __restrict__ hashes, uint64_t s, const HashCfg& cfg, unsigned i)
+{
+	return LITERAL ? fastmod_u64(hashes[s * cfg.H + i], cfg.mod) : nth_pos(hashes[s], cfg, i);
+}
 
-/** CountingBloomFilter::incrementMin / HashAgnosticCascadingBloom::insert by the single owner */
+/** conflict map: E two-bit entries, 16 per word, entry = position mod E (E a power of two; exact when the
+ *  filter has at most E positions).  bit 0: touched by a slot of the window; bit 1: touched again (by a second
+ *  slot, by a second hash of the same slot, or by a carried slot). */
+struct ConflictMap {
+	unsigned* w;
+	uint64_t mask; // E - 1
+};
+ABB_D void map_mark(const ConflictMap& m, uint64_t pos)
+{
+	const uint64_t e = pos & m.mask;
+	const unsigned sh = (unsigned)(e & 15) * 2;
+	const unsigned old = atomicOr(&m.w[e >> 4], 1u << sh);
+	if (((old >> sh) & 3u) == 1u)
+		atomicOr(&m.w[e >> 4], 2u << sh);
+}
+ABB_D void map_mark_carried(const ConflictMap& m, uint64_t pos)
+{
+	const uint64_t e = pos & m.mask;
+	atomicOr(&m.w[e >> 4], 3u << ((unsigned)(e & 15) * 2));
+}
+ABB_D unsigned map_get(const ConflictMap& m, uint64_t pos)
+{
+	const uint64_t e = pos & m.mask;
+	return (__ldcg(&m.w[e >> 4]) >> ((unsigned)(e & 15) * 2)) & 3u;
+}
+
+/** device-resident control block of the insert pipeline */
+struct InsertCtl {
+	unsigned n_carry[2];  // lengths of the two carry lists
+	unsigned old_flag;    // a slot carried again is older than the drain age
+	unsigned resume;      // first window the kernel has NOT processed (it stops early when a drain is due)
+	unsigned tag_mask[2]; // prefix of each tag table that is in use (to be cleared before its next use)
+	unsigned pad[2];
+};
+
+/** CountingBloomFilter::incrementMin / HashAgnosticCascadingBloom::insert by a thread that is the
+ *  only pending event on all of its positions */
 template <int KIND, int MAXH>
-ABB_D void apply_owner(const FilterView& f, const uint64_t* pos, unsigned H)
+ABB_D void apply_alone(const FilterView& f, const uint64_t* pos, const unsigned* v, unsigned H)
 {
 	if (KIND == 0) {
-		unsigned v[MAXH];
+		// CountingBloomFilter.hpp:138-162; "if (minVal > newVal) return" = saturated at 255
 		unsigned mn = 255;
 #pragma unroll
 		for (int i = 0; i < MAXH; ++i)
-			if (i < (int)H) {
-				v[i] = __ldcg(f.data + pos[i]);
+			if (i < (int)H)
 				mn = min(mn, v[i]);
-			}
-		if (mn == 255) // "if (minVal > newVal) return": saturated (CountingBloomFilter.hpp:146-149)
+		if (mn == 255)
 			return;
 #pragma unroll
 		for (int i = 0; i < MAXH; ++i)
@@ -415,217 +434,366 @@ ABB_D void apply_owner(const FilterView& f, const uint64_t* pos, unsigned H)
 		apply_cascading(f, pos, H);
 }
 
-/** K2a: reserve */
-template <bool LITERAL, int MAXH>
-__global__ void __launch_bounds__(256)
-k_reserve(const uint64_t* __restrict__ hashes, const uint8_t* __restrict__ valid, uint64_t w0,
-          unsigned n, HashCfg cfg, TagTable tab, unsigned epoch, unsigned age_off)
+struct InsertArgs {
+	const uint64_t* hashes;
+	const uint8_t* valid;   // may be NULL (all slots valid)
+	uint64_t n_slots;
+	unsigned window;        // W
+	unsigned w_begin, n_windows;
+	HashCfg cfg;
+	ConflictMap map[2];
+	unsigned long long* tags[2];
+	unsigned tag_cap;       // entries allocated per tag table (power of two)
+	FilterView f;
+	unsigned age_off, drain_age;
+	uint64_t* carry[2];
+	InsertCtl* ctl;
+	unsigned long long* stats;
+};
+
+ABB_D unsigned tag_mask_for(unsigned n_carried, unsigned H, unsigned cap)
 {
-	const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
-	if (t >= n)
-		return;
-	const uint64_t s = w0 + t;
-	if (valid && !valid[s])
-		return;
-	uint64_t pos[MAXH];
-	slot_positions<LITERAL, MAXH>(hashes, s, cfg, pos);
-#pragma unroll
-	for (int i = 0; i < MAXH; ++i)
-		if (i < (int)cfg.H)
-			tag_reserve(tab, epoch, pos[i], age_off + t);
+	unsigned want = 4096;
+	while (want < 8u * n_carried * H && want < cap)
+		want <<= 1;
+	return min(want, cap) - 1;
 }
 
-/** reservations of the slots carried over from earlier windows (they precede every slot of this one) */
-template <bool LITERAL, int MAXH>
-__global__ void __launch_bounds__(256)
-k_reserve_carry(const uint64_t* __restrict__ hashes, const uint64_t* __restrict__ carry, const unsigned* __restrict__ n_carry,
-                uint64_t w0, HashCfg cfg, TagTable tab, unsigned epoch, unsigned age_off)
-{
-	const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= *n_carry)
-		return;
-	const uint64_t s = carry[i];
-	uint64_t pos[MAXH];
-	slot_positions<LITERAL, MAXH>(hashes, s, cfg, pos);
-	const uint64_t prio = s + age_off - w0;
-#pragma unroll
-	for (int j = 0; j < MAXH; ++j)
-		if (j < (int)cfg.H)
-			tag_reserve(tab, epoch, pos[j], prio);
-}
-
-/** K2b: owners apply and release, everybody else is carried into the next window.
- *  Threads [0, kCarryLanes) serve the slots carried in from earlier windows, the rest the n slots
- *  of this window.  The counter loads are issued before the ownership probes (wasted only for the
- *  <1 % of slots that lose a reservation) so that the HBM round trip overlaps the L2 round trip. */
+/**
+ * K2: the persistent window kernel (cooperative launch, one CTA set resident for a whole chunk of windows).
+ * Window w, phase A: the carried slots (exact ownership through tags[w & 1]) and the new slots [w0, w0 + n)
+ * (independent unless one of their entries in map[w & 1] was touched again) apply or are put on the other carry
+ * list; the same threads mark the slots of window w + 1 in map[(w+1) & 1] and clear the tag table of window w - 1.
+ * Grid barrier.  Phase B: map[w & 1] is cleared, the slots just carried reserve their positions in tags[(w+1) & 1]
+ * and mark them "touched again" in map[(w+1) & 1].  Grid barrier.  The counter loads are issued before the map / tag
+ * probes so that the HBM round trip overlaps the L2 round trip.  The kernel returns early (ctl->resume) when the
+ * pending slots need the serial drain.
+ */
 template <int KIND, bool LITERAL, int MAXH>
 __global__ void __launch_bounds__(256)
-k_commit(const uint64_t* __restrict__ hashes, const uint8_t* __restrict__ valid, uint64_t w0,
-         unsigned n, HashCfg cfg, TagTable tab, unsigned epoch, FilterView f, unsigned age_off,
-         const uint64_t* __restrict__ carry_in, const unsigned* __restrict__ n_in,
-         uint64_t* __restrict__ carry_out, unsigned* __restrict__ n_out, unsigned long long* __restrict__ stats)
+k_insert_windows(const InsertArgs a)
 {
-	const unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
-	uint64_t s;
-	if (id < kCarryLanes) {
-		if (id >= *n_in)
-			return;
-		s = carry_in[id];
-	} else {
-		const unsigned t = id - kCarryLanes;
-		if (t >= n)
-			return;
-		s = w0 + t;
-		if (valid && !valid[s])
-			return;
-	}
-	const uint64_t prio = s + age_off - w0;
+	cg::grid_group grid = cg::this_grid();
+	const uint64_t T = (uint64_t)gridDim.x * blockDim.x;
+	const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const unsigned H = a.cfg.H;
+	const uint64_t W = a.window;
 	uint64_t pos[MAXH];
-	slot_positions<LITERAL, MAXH>(hashes, s, cfg, pos);
 	unsigned v[MAXH];
-	if (KIND == 0) {
-#pragma unroll
-		for (int i = 0; i < MAXH; ++i)
-			if (i < (int)cfg.H)
-				v[i] = __ldcg(f.data + pos[i]);
-	}
-	bool owner = true;
-	uint64_t where[MAXH];
-#pragma unroll
-	for (int i = 0; i < MAXH; ++i)
-		if (i < (int)cfg.H)
-			owner &= tag_owner_at(tab, epoch, pos[i], &where[i]) == prio;
-	if (owner) {
-		if (KIND == 0) {
-			// CountingBloomFilter::incrementMin by the single owner (CountingBloomFilter.hpp:138-162)
-			unsigned mn = 255;
-#pragma unroll
-			for (int i = 0; i < MAXH; ++i)
-				if (i < (int)cfg.H)
-					mn = min(mn, v[i]);
-			if (mn != 255) {
+	if (a.w_begin == 0) { // the marks of window 0
+		const unsigned n0 = (unsigned)min((uint64_t)W, a.n_slots);
+		for (uint64_t t = gtid; t < n0; t += T)
+			if (!a.valid || a.valid[t]) {
+				slot_positions<LITERAL, MAXH>(a.hashes, t, a.cfg, pos);
 #pragma unroll
 				for (int i = 0; i < MAXH; ++i)
-					if (i < (int)cfg.H && v[i] == mn)
-						__stcg(f.data + pos[i], (uint8_t)(mn + 1));
+					if (i < (int)H)
+						map_mark(a.map[0], pos[i]);
 			}
-		} else
-			apply_owner<KIND, MAXH>(f, pos, cfg.H);
+		grid.sync();
+	}
+	for (unsigned w = a.w_begin; w < a.n_windows; ++w) {
+		const int in = (int)(w & 1), out = 1 - in;
+		const uint64_t w0 = (uint64_t)w * W, w1 = w0 + W;
+		const unsigned n = (unsigned)min(W, a.n_slots - w0);
+		const unsigned n_next = w + 1 < a.n_windows ? (unsigned)min(W, a.n_slots - w1) : 0u;
+		const unsigned n_in = a.ctl->n_carry[in];
+		const TagTable tcur = { a.tags[in], a.ctl->tag_mask[in] };
+		const unsigned old_mask_out = a.ctl->tag_mask[out];
+		// ---- phase A
+		for (uint64_t id = gtid; id < (uint64_t)n_in + max(n, n_next); id += T) {
+			if (id < n_in) {
+				const uint64_t s = a.carry[in][id];
+				const uint64_t prio = s + a.age_off - w0;
+				slot_positions<LITERAL, MAXH>(a.hashes, s, a.cfg, pos);
+				if (KIND == 0) {
 #pragma unroll
-		for (int i = 0; i < MAXH; ++i)
-			if (i < (int)cfg.H)
-				__stcg(&tab.e[where[i]], (unsigned long long)tag_pack(epoch, pos[i], kSlotMask));
-	} else {
-		carry_out[atomicAdd(n_out, 1u)] = s;
-		if (id >= kCarryLanes)
-			atomicAdd(&stats[0], 1ULL); // slots that did not commit in their own window
+					for (int i = 0; i < MAXH; ++i)
+						if (i < (int)H)
+							v[i] = __ldcg(a.f.data + pos[i]);
+				}
+				bool owner = true;
+				uint64_t where[MAXH];
+#pragma unroll
+				for (int i = 0; i < MAXH; ++i)
+					if (i < (int)H)
+						owner &= tag_owner_at(tcur, pos[i], &where[i]) == prio;
+				if (owner) {
+					apply_alone<KIND, MAXH>(a.f, pos, v, H);
+#pragma unroll
+					for (int i = 0; i < MAXH; ++i)
+						if (i < (int)H)
+							tag_release_at(tcur, pos[i], where[i]);
+				} else {
+					a.carry[out][atomicAdd(&a.ctl->n_carry[out], 1u)] = s;
+					if (w0 - s > a.drain_age)
+						a.ctl->old_flag = 1;
+				}
+				continue;
+			}
+			const uint64_t t = id - n_in;
+			if (t < n) {
+				const uint64_t s = w0 + t;
+				if (!a.valid || a.valid[s]) {
+					slot_positions<LITERAL, MAXH>(a.hashes, s, a.cfg, pos);
+					if (KIND == 0) {
+#pragma unroll
+						for (int i = 0; i < MAXH; ++i)
+							if (i < (int)H)
+								v[i] = __ldcg(a.f.data + pos[i]);
+					}
+					unsigned again = 0;
+#pragma unroll
+					for (int i = 0; i < MAXH; ++i)
+						if (i < (int)H)
+							again |= map_get(a.map[in], pos[i]);
+					if (!(again & 2u))
+						apply_alone<KIND, MAXH>(a.f, pos, v, H);
+					else {
+						a.carry[out][atomicAdd(&a.ctl->n_carry[out], 1u)] = s;
+						atomicAdd(&a.stats[0], 1ULL); // slots that did not commit in their own window
+					}
+				}
+			}
+			if (t < n_next) {
+				const uint64_t s = w1 + t;
+				if (!a.valid || a.valid[s]) {
+					slot_positions<LITERAL, MAXH>(a.hashes, s, a.cfg, pos);
+#pragma unroll
+					for (int i = 0; i < MAXH; ++i)
+						if (i < (int)H)
+							map_mark(a.map[out], pos[i]);
+				}
+			}
+		}
+		for (uint64_t i = gtid; i <= old_mask_out; i += T) // the tag table of window w - 1
+			a.tags[out][i] = 0;
+		__threadfence();
+		grid.sync();
+		// ---- phase B
+		const unsigned n_out = a.ctl->n_carry[out];
+		const bool stop = n_out > kCarryLanes || a.ctl->old_flag != 0;
+		const bool last = w + 1 == a.n_windows;
+		{
+			uint4* mw = reinterpret_cast<uint4*>(a.map[in].w);
+			const uint64_t words4 = (a.map[in].mask + 1) / 64; // 16 entries per word, 4 words per uint4
+			for (uint64_t i = gtid; i < words4; i += T)
+				mw[i] = make_uint4(0, 0, 0, 0);
+		}
+		const unsigned new_mask = tag_mask_for(n_out, H, a.tag_cap);
+		if (!stop && !last) {
+			const TagTable tnext = { a.tags[out], new_mask };
+			for (uint64_t i = gtid; i < n_out; i += T) {
+				const uint64_t s = a.carry[out][i];
+				slot_positions<LITERAL, MAXH>(a.hashes, s, a.cfg, pos);
+				const uint64_t prio = s + a.age_off - w1;
+#pragma unroll
+				for (int j = 0; j < MAXH; ++j)
+					if (j < (int)H) {
+						tag_reserve(tnext, pos[j], prio);
+						map_mark_carried(a.map[out], pos[j]);
+					}
+			}
+		}
+		if (gtid == 0) {
+			a.ctl->n_carry[in] = 0;
+			a.ctl->tag_mask[out] = (!stop && !last) ? new_mask : 0u;
+			a.ctl->resume = w + 1;
+		}
+		__threadfence();
+		grid.sync();
+		if (stop)
+			return;
 	}
 }
 
-/** K2c: one CTA applies every pending slot of `list` in dependency order (see the header comment).
- *  Does nothing when fewer than min_count slots are pending.  Clears *n_consumed (the list the
- *  preceding commit launch has just read) so that it can collect the next window's carries.
- *  stats[1] = max rounds seen, stats[2] += slots replayed strictly in order. */
+// ---- drain: one CTA replays the pending slots in file order on counters staged in shared memory ----
+constexpr unsigned kDrainThreads = 1024;
+constexpr unsigned kDrainPos = 2048;   // filter positions staged per chunk
+constexpr unsigned kDrainMap = 4096;   // shared-memory map entries (load <= 0.5)
+
+/** exclusive prefix sum of one value per thread over the CTA (kDrainThreads threads); total in *total */
+ABB_D unsigned block_exclusive_scan(unsigned x, unsigned* warp_sums /* [32] shared */, unsigned* total)
+{
+	const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	unsigned incl = x;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		unsigned y = __shfl_up_sync(0xffffffffu, incl, d);
+		if (lane >= (unsigned)d)
+			incl += y;
+	}
+	if (lane == 31)
+		warp_sums[warp] = incl;
+	__syncthreads();
+	if (warp == 0) {
+		unsigned wsum = warp_sums[lane];
+		unsigned winc = wsum;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			unsigned y = __shfl_up_sync(0xffffffffu, winc, d);
+			if (lane >= (unsigned)d)
+				winc += y;
+		}
+		warp_sums[lane] = winc - wsum; // exclusive
+		if (lane == 31)
+			*total = winc;
+	}
+	__syncthreads();
+	return warp_sums[warp] + incl - x;
+}
+
+/** the set bits of bw[0, words) in ascending order: out[i] = first_slot + bit index; clears the words.
+ *  Called by all threads of a kDrainThreads CTA; returns the number of slots written. */
+ABB_D unsigned enumerate_presence(unsigned* __restrict__ bw, unsigned words, uint64_t first_slot, uint64_t* __restrict__ out,
+                                  unsigned* warp_sums, unsigned* total)
+{
+	const unsigned per = (words + blockDim.x - 1) / blockDim.x;
+	const unsigned wb = min(words, threadIdx.x * per), we = min(words, wb + per);
+	unsigned cnt = 0;
+	for (unsigned wd = wb; wd < we; ++wd)
+		cnt += __popc(__ldcg(&bw[wd]));
+	unsigned at = block_exclusive_scan(cnt, warp_sums, total);
+	for (unsigned wd = wb; wd < we; ++wd) {
+		unsigned m = __ldcg(&bw[wd]);
+		if (m)
+			bw[wd] = 0;
+		while (m) {
+			const unsigned b = __ffs(m) - 1;
+			m &= m - 1;
+			out[at++] = first_slot + (uint64_t)wd * 32 + b;
+		}
+	}
+	__threadfence();
+	__syncthreads();
+	return *total;
+}
+
+/** K2c.  Does nothing unless forced, more than min_count slots are pending or a pending slot is old.
+ *  Clears ctl->n_carry[other] (the list the preceding window launch has just consumed) so that it can collect
+ *  the next window's carries.  `bits` is a zeroed presence bitmap for slots [lo_slot, lo_slot + 32 * bit_words)
+ *  (left zeroed), `sorted` holds as many slots as the list.  stats[2] += slots replayed. */
 template <int KIND, bool LITERAL, int MAXH>
-__global__ void __launch_bounds__(1024)
-k_drain(const uint64_t* __restrict__ hashes, uint64_t w0, HashCfg cfg, TagTable tab, unsigned epoch, FilterView f, unsigned age_off,
-        uint64_t* __restrict__ list, unsigned* __restrict__ n_list, unsigned* __restrict__ n_consumed, unsigned min_count,
+__global__ void __launch_bounds__(kDrainThreads)
+k_drain(const uint64_t* __restrict__ hashes, HashCfg cfg, FilterView f, const uint64_t* __restrict__ list, InsertCtl* __restrict__ ctl,
+        int which, unsigned min_count, int force, unsigned* __restrict__ bits, uint64_t lo_slot, uint64_t* __restrict__ sorted,
         unsigned long long* __restrict__ stats)
 {
-	__shared__ unsigned s_left;
-	__shared__ unsigned long long s_key[32];
-	if (threadIdx.x == 0)
-		*n_consumed = 0;
-	const unsigned n = *n_list;
-	if (n < min_count || n == 0)
-		return;
-	constexpr uint64_t kDone = ~0ULL;
-	unsigned left = n, round = 0;
-	while (left > 0 && round < kMaxRounds) {
-		for (unsigned x = threadIdx.x; x < n; x += blockDim.x) {
-			const uint64_t s = list[x];
-			if (s == kDone)
-				continue;
-			uint64_t pos[MAXH];
-			slot_positions<LITERAL, MAXH>(hashes, s, cfg, pos);
-#pragma unroll
-			for (int i = 0; i < MAXH; ++i)
-				if (i < (int)cfg.H)
-					tag_reserve(tab, epoch, pos[i], s + age_off - w0);
-		}
-		if (threadIdx.x == 0)
-			s_left = 0;
-		__threadfence();
-		__syncthreads();
-		for (unsigned x = threadIdx.x; x < n; x += blockDim.x) {
-			const uint64_t s = list[x];
-			if (s == kDone)
-				continue;
-			uint64_t pos[MAXH];
-			slot_positions<LITERAL, MAXH>(hashes, s, cfg, pos);
-			bool owner = true;
-#pragma unroll
-			for (int i = 0; i < MAXH; ++i)
-				if (i < (int)cfg.H)
-					owner &= tag_owner(tab, epoch, pos[i]) == s + age_off - w0;
-			if (owner) {
-				apply_owner<KIND, MAXH>(f, pos, cfg.H);
-#pragma unroll
-				for (int i = 0; i < MAXH; ++i)
-					if (i < (int)cfg.H)
-						tag_release(tab, epoch, pos[i]);
-				list[x] = kDone;
-			} else
-				atomicAdd(&s_left, 1u);
-		}
-		__threadfence();
-		__syncthreads();
-		left = s_left;
-		++round;
-		__syncthreads();
+	__shared__ unsigned long long s_key[kDrainMap];
+	__shared__ unsigned short s_val[kDrainMap]; // bit 8 = dirty
+	__shared__ unsigned short s_idx[kDrainPos];
+	__shared__ unsigned s_warp[32];
+	__shared__ unsigned s_total;
+	__shared__ unsigned long long s_lo, s_hi;
+	if (threadIdx.x == 0) {
+		ctl->n_carry[1 - which] = 0;
+		s_lo = ~0ULL;
+		s_hi = 0;
 	}
-	const unsigned serial = left;
-	// strict in-order replay of whatever is left (only reachable through very long chains)
-	while (left > 0) {
-		unsigned long long best = ~0ULL;
-		unsigned bestx = 0;
-		for (unsigned x = threadIdx.x; x < n; x += blockDim.x) {
-			const uint64_t s = list[x];
-			if (s < best) {
-				best = s;
-				bestx = x;
+	const unsigned n = ctl->n_carry[which];
+	const bool go = n > 0 && (force || n > min_count || ctl->old_flag);
+	__syncthreads();
+	if (!go)
+		return;
+	// 1. file order: presence bitmap over [min slot, max slot], enumerated in order
+	unsigned long long lo = ~0ULL, hi = 0;
+	for (unsigned x = threadIdx.x; x < n; x += blockDim.x) {
+		const unsigned long long s = list[x];
+		lo = s < lo ? s : lo;
+		hi = s > hi ? s : hi;
+	}
+	for (int d = 16; d; d >>= 1) {
+		unsigned long long a = __shfl_down_sync(0xffffffffu, lo, d), b = __shfl_down_sync(0xffffffffu, hi, d);
+		lo = a < lo ? a : lo;
+		hi = b > hi ? b : hi;
+	}
+	if ((threadIdx.x & 31) == 0) {
+		atomicMin(&s_lo, lo);
+		atomicMax(&s_hi, hi);
+	}
+	__syncthreads();
+	const uint64_t base = (s_lo - lo_slot) & ~31ULL; // bit index of the first word
+	const unsigned words = (unsigned)(((s_hi - lo_slot) - base) / 32 + 1);
+	unsigned* const bw = bits + base / 32;
+	for (unsigned x = threadIdx.x; x < n; x += blockDim.x) {
+		const uint64_t b = list[x] - lo_slot - base;
+		atomicOr(&bw[b >> 5], 1u << (b & 31));
+	}
+	__threadfence();
+	__syncthreads();
+	enumerate_presence(bw, words, lo_slot + base, sorted, s_warp, &s_total);
+	// 2. replay
+	if (KIND == 0) {
+		const unsigned H = cfg.H;
+		const unsigned per_chunk = kDrainPos / H; // slots per chunk
+		for (unsigned c0 = 0; c0 < n; c0 += per_chunk) {
+			const unsigned cn = min(per_chunk, n - c0);
+			for (unsigned e = threadIdx.x; e < kDrainMap; e += blockDim.x)
+				s_key[e] = 0;
+			__syncthreads();
+			for (unsigned x = threadIdx.x; x < cn * H; x += blockDim.x) {
+				const unsigned j = x / H, i = x - j * H;
+				const uint64_t p = slot_position<LITERAL>(hashes, sorted[c0 + j], cfg, i);
+				const unsigned long long key = p + 1;
+				unsigned e = (unsigned)((p * 0x9E3779B97F4A7C15ULL) >> 52) & (kDrainMap - 1);
+				for (;;) {
+					const unsigned long long old = atomicCAS(&s_key[e], 0ULL, key);
+					if (old == 0) {
+						s_val[e] = __ldcg(f.data + p);
+						break;
+					}
+					if (old == key)
+						break;
+					e = (e + 1) & (kDrainMap - 1);
+				}
+				s_idx[x] = (unsigned short)e;
+			}
+			__syncthreads();
+			if (threadIdx.x == 0) {
+				unsigned a[MAXH], v[MAXH];
+				for (unsigned j = 0; j < cn; ++j) {
+					unsigned mn = 255;
+#pragma unroll
+					for (int i = 0; i < MAXH; ++i)
+						if (i < (int)H) {
+							a[i] = s_idx[j * H + i];
+							v[i] = s_val[a[i]] & 0xffu;
+							mn = min(mn, v[i]);
+						}
+					if (mn != 255) {
+#pragma unroll
+						for (int i = 0; i < MAXH; ++i)
+							if (i < (int)H && v[i] == mn)
+								s_val[a[i]] = (unsigned short)((mn + 1) | 0x100u);
+					}
+				}
+			}
+			__syncthreads();
+			for (unsigned e = threadIdx.x; e < kDrainMap; e += blockDim.x)
+				if (s_key[e] && (s_val[e] & 0x100u))
+					__stcg(f.data + (s_key[e] - 1), (uint8_t)(s_val[e] & 0xffu));
+			__threadfence();
+			__syncthreads();
+		}
+	} else {
+		if (threadIdx.x == 0) {
+			uint64_t pos[MAXH];
+			for (unsigned j = 0; j < n; ++j) {
+				slot_positions<LITERAL, MAXH>(hashes, sorted[j], cfg, pos);
+				apply_cascading(f, pos, cfg.H);
+				__threadfence();
 			}
 		}
-		// block-wide argmin on (slot, x): slots fit in 40 bits
-		unsigned long long key = best == ~0ULL ? ~0ULL : ((best << 24) | bestx);
-		for (int d = 16; d; d >>= 1) {
-			unsigned long long o = __shfl_down_sync(0xffffffffu, key, d);
-			key = o < key ? o : key;
-		}
-		if ((threadIdx.x & 31) == 0)
-			s_key[threadIdx.x >> 5] = key;
 		__syncthreads();
-		if (threadIdx.x == 0) {
-			unsigned long long m = s_key[0];
-			for (unsigned w = 1; w < (blockDim.x >> 5); ++w)
-				m = s_key[w] < m ? s_key[w] : m;
-			const uint64_t s = m >> 24;
-			const unsigned x = (unsigned)(m & 0xffffff);
-			uint64_t pos[MAXH];
-			slot_positions<LITERAL, MAXH>(hashes, s, cfg, pos);
-			apply_owner<KIND, MAXH>(f, pos, cfg.H);
-			list[x] = kDone;
-		}
-		__threadfence();
-		__syncthreads();
-		--left;
 	}
 	if (threadIdx.x == 0) {
-		*n_list = 0;
-		atomicMax(&stats[1], (unsigned long long)round);
-		atomicAdd(&stats[2], (unsigned long long)serial);
+		ctl->n_carry[which] = 0;
+		ctl->old_flag = 0;
+		atomicAdd(&stats[2], (unsigned long long)n);
+		atomicAdd(&stats[1], 1ULL); // drains that did work
 	}
 }
+
 
 /** BloomFilter::insert for every valid slot (order free: OR commutes) -- the assembled-k-mer
  *  filter and plain `abyss-bloom build` bit filters */

@@ -12,14 +12,22 @@ paired reads (187.5 Mbp uniform-random genome, 40x, 0.5 % substitutions), k=64, 
 k-mers/s = (sum over reads of len-k+1) / step time, counted once per input k-mer.
 
 `value`  : reads resident in HBM when the timed region starts (abb_*_dev entry points).
-`e2e`    : same job through the host-buffer C-ABI calls (abb_insert_reads +
-           abb_assembler_process_reads): pinned host reads are copied to the device inside the
-           timed region in both passes, the unitigs come back to the host.
-`roofline`: the Bloom-insert commit kernel (k_commit): algorithmic bytes (64*H B of 32-byte
-           sectors per inserted k-mer + L/(L-k+1) B of read bases) / its summed
-           CUDA-event launch time, against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
-`cpu_baseline`: the UNMODIFIED reference (oracle/_ref/abyss-bloom-dbg-ref, built by
-           oracle/Makefile) on a bounded sample of the same reads with all host threads.
+`e2e`    : same job through the host-buffer C-ABI calls (abb_insert_reads[_sharded], then
+           abb_assembler_process_reads_dev on the copy that insert left on the device): pinned host reads are
+           copied to the device inside the timed region (once: the copy stays resident for pass 2), the unitigs and
+           per-read codes come back to the host.  Both arms, and every N, must give the same FASTA (`fasta_md5`,
+           checked here: a mismatch between the e2e and the device-resident arm, or between ranks, fails the run).
+`roofline`: the Bloom-insert kernel (k_insert_windows, the persistent window kernel): algorithmic bytes (64*H B of
+           32-byte sectors per inserted k-mer + L/(L-k+1) B of read bases) x the slots its timed
+           launches applied / their summed CUDA-event time, against the measured HBM copy bandwidth in
+           MEASURED_PEAKS.json.  `insert_phase` is the same over the whole insert phase (hash + insert + drains).
+`cpu_baseline`: the UNMODIFIED reference (oracle/_ref/abyss-bloom-dbg-ref, built by oracle/Makefile) with all host
+           threads.  The reference pays a fixed start-up cost that depends on -b, not on the reads (zero-filling the
+           8 GiB of filters, contigEndKmers.rehash(2^28), bloom-dbg.h:993): it is measured with a 1-read input
+           (`fixed_s`) and reported next to the as-run rate of the bounded sample, the marginal rate
+           (k-mers / (t - fixed_s)) and the full-job estimate fixed_s + N_kmers / marginal -- `value` of the reference
+           arm is that full-job estimate (what the reference would deliver on this config), not the sample's
+           as-run rate, so the ratio does not depend on the sample size.
 `--impl reference` times that reference binary as the step (bounded sample per step).
 """
 from __future__ import annotations
@@ -44,9 +52,9 @@ ERR = 0.005
 SEED = 2
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "abyss-bloom-dbg-ref")
 ALG_BYTES_PER_KMER = 64 * H + L / (L - K + 1)  # 257.7 B
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_commit launch over a 2^19-slot window of this filter
-# (ncu --set full, cold caches; profiles/r01_k_commit_w19_full_raw.csv): 387.9 MB + 87.0 MB
-NCU_TRAFFIC_PER_COMMIT_LAUNCH = 474.9e6
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_insert_windows launch (ncu --set full; profiles/README.md), per
+# k-mer slot applied; None until a capture of this round's kernel exists
+NCU_TRAFFIC_PER_SLOT = None
 
 
 def peaks():
@@ -95,7 +103,18 @@ class ClockSampler:
 
 
 def write_sample_fastq(rs, n, path):
-    rs.write_fastq(path, 0, n)
+    """first n reads of the workload as FASTQ; generated on the GPU when there is one (the numpy generator needs ~8 us/read)"""
+    from abyss_b200.synth import write_fastq_fast
+    ascii_fn = None
+    try:
+        import torch
+        if torch.cuda.is_available():
+            from abyss_b200.synth_torch import TorchReadSet
+            trs = TorchReadSet(rs, torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))))
+            ascii_fn = lambda lo, hi: trs.ascii(lo, hi).cpu().numpy()
+    except Exception:
+        ascii_fn = None
+    write_fastq_fast(rs, path, 0, n, ascii_fn=ascii_fn)
 
 
 def run_reference(fq, threads, out_fa):
@@ -109,6 +128,42 @@ def run_reference(fq, threads, out_fa):
     return dt
 
 
+def reference_measurement(rs, sample, cores, n_runs, warmup=0):
+    """fixed start-up cost (1-read input, same -b) and `n_runs` timed runs of the first `sample` reads"""
+    tmp = tempfile.mkdtemp(prefix="abyss_ref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    fq1, fq = os.path.join(tmp, "one.fq"), os.path.join(tmp, "sample.fq")
+    write_sample_fastq(rs, 1, fq1)
+    write_sample_fastq(rs, sample, fq)
+    out = os.path.join(tmp, "ref.fa")
+    fixed = min(run_reference(fq1, cores, out) for _ in range(2))
+    times = []
+    for i in range(warmup + n_runs):
+        dt = run_reference(fq, cores, out)
+        if i >= warmup:
+            times.append(dt)
+    import hashlib
+    md5 = hashlib.md5(open(out, "rb").read()).hexdigest()
+    for f in (fq1, fq, out):
+        os.remove(f)
+    os.rmdir(tmp)
+    t = sum(times) / len(times)
+    kmers = sample * (L - K + 1)
+    full = N_READS * (L - K + 1)
+    marginal = kmers / max(t - fixed, 1e-3)
+    est_full_s = fixed + full / marginal
+    return {"t": t, "fixed_s": fixed, "as_run": kmers / t, "marginal": marginal, "full_job_estimate_s": est_full_s,
+            "full_job_value": full / est_full_s, "sample_fasta_md5": md5, "kmers": kmers}
+
+
+def cpu_baseline_dict(m, cores, sample):
+    return {"value": m["full_job_value"], "unit": "k-mers/s", "cores": cores, "kind": "reference",
+            "as_run_value": m["as_run"], "marginal_value": m["marginal"], "fixed_s": m["fixed_s"], "sample_s": m["t"],
+            "full_job_estimate_s": m["full_job_estimate_s"],
+            "sample": f"first {sample} reads of the workload, abyss-bloom-dbg -j{cores} (unmodified reference), files on tmpfs; "
+                      f"{m['t']:.1f} s per run of which {m['fixed_s']:.1f} s do not depend on the reads (1-read run, same -b); value = "
+                      f"{N_READS} reads at the marginal rate + the fixed cost"}
+
+
 def reference_arm(args, rank, world):
     """--impl reference: the reference's own CPU implementation on this box's host cores"""
     if rank != 0:
@@ -118,27 +173,18 @@ def reference_arm(args, rank, world):
     if not os.path.exists(REF_BIN):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/abyss-bloom-dbg-ref not built (make -C oracle ref)"}))
         return
-    sample = args.ref_reads
+    # bounded: the whole call stays within a few minutes whatever --steps / --warmup say
+    runs = args.warmup + args.steps
+    sample = args.ref_reads if args.ref_reads else (4_000_000 if runs <= 6 else 2_000_000 if runs <= 12 else 1_000_000)
     rs = ReadSet(SEED, GENOME, N_READS, L, ERR, paired=True)
-    tmp = tempfile.mkdtemp(prefix="abyss_ref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
-    fq = os.path.join(tmp, "sample.fq")
-    write_sample_fastq(rs, sample, fq)
-    kmers = sample * (L - K + 1)
-    times = []
-    for i in range(args.warmup + args.steps):
-        dt = run_reference(fq, cores, os.path.join(tmp, "ref.fa"))
-        if i >= args.warmup:
-            times.append(dt)
-    ms = 1e3 * sum(times) / len(times)
-    val = kmers / (ms * 1e-3)
+    m = reference_measurement(rs, sample, cores, args.steps, args.warmup)
     line = {
-        "impl": "reference", "metric": "k-mers/sec (Bloom insert + unitig extend)", "value": val, "unit": "k-mers/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "impl": "reference", "metric": "k-mers/sec (Bloom insert + unitig extend)", "value": m["full_job_value"], "unit": "k-mers/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * m["t"], "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": workload_config(args, extra={"sample_reads": sample}),
-        "cpu_baseline": {"value": val, "unit": "k-mers/s", "cores": cores, "kind": "reference",
-                         "sample": f"first {sample} reads of the workload, abyss-bloom-dbg -j{cores}, files on tmpfs"},
-        "e2e": {"value": val, "unit": "k-mers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "cpu_baseline": cpu_baseline_dict(m, cores, sample),
+        "e2e": {"value": m["full_job_value"], "unit": "k-mers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
@@ -149,8 +195,9 @@ def workload_config(args, extra=None):
                      "(BASELINE.json configs[1])",
          "reads": args.reads, "read_len": L, "k": K, "kc": KC, "num_hashes": H, "bloom_bytes": BLOOM_BYTES,
          "l2_policy": "inputs (7.5 GB reads) and filters (8.6 GB) far exceed the 126 MB L2; no flush needed",
-         "parallelism": (f"pass 1 sharded by k-mer hash range over {args.gpus} GPUs (NCCL all-to-all + all-reduce max), read classification "
-                         "sharded by reads (all-gather), rest of pass 2 replicated"
+         "parallelism": (f"pass 1: counters sharded by position range over {args.gpus} GPUs, one ncclAllReduce(min) per file-order "
+                         "window, all-gather of the shards (exact: same counters as 1 GPU); pass 2: read classification sharded by "
+                         "reads (all-gather), the rest replicated"
                          if args.gpus > 1 else "1 GPU")}
     if extra:
         c.update(extra)
@@ -164,7 +211,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reads", type=int, default=N_READS, help="number of reads of the workload (default: the BASELINE config)")
-    ap.add_argument("--ref-reads", type=int, default=2_000_000, help="bounded CPU sample (reads)")
+    ap.add_argument("--ref-reads", type=int, default=0, help="bounded CPU sample (reads); 0 = sized from --steps")
     ap.add_argument("--window", type=int, default=0, help="ordered-insert window in k-mer slots (0 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -215,37 +262,49 @@ def main():
         filt.set_window(args.window)
     ext = torch.cuda.ExternalStream(filt.stream(), device=dev)
 
-    # N > 1: pass 1 is sharded by k-mer hash range (all-to-all of hashes, ordered insert of the owned
-    # k-mers, all-reduce(max) union over NVLink); pass 2 runs replicated on every rank
+    # N > 1: the NCCL communicator lives behind the C ABI; torch.distributed only ships its id and the timings
+    comm = None
+    if world > 1:
+        def bcast(b):
+            box = [b]
+            dist.broadcast_object_list(box, src=0)
+            return box[0]
+        comm = capi.Comm(rank, world, local_rank, bcast)
     lo, up = rank * rs.n // world, (rank + 1) * rs.n // world
     offs_slice = torch.arange(up - lo + 1, dtype=torch.int64, device=dev) * L
 
     asm = capi.Assembler(filt)  # one handle for all steps: device buffers are allocated once, state is reset per step
     asm.raw_results = True      # the unitig sequences are copied to the host by the library; no Python string per unitig
 
+    def pass2(d_bases, d_offs):
+        if world > 1:
+            from abyss_b200 import multigpu
+            codes = multigpu.sharded_classify(asm, comm, d_bases + lo * L, offs_slice.data_ptr(), up - lo, rs.n, dev)
+            out = asm.process_reads_dev(d_bases, d_offs, rs.n)
+            del codes
+            return out
+        return asm.process_reads_dev(d_bases, d_offs, rs.n)
+
     def one_step(host=None):
-        """returns (n_kmers, contigs, assembler stats, insert stats)"""
+        """returns (n_kmers, contigs, assembler stats, insert stats, counters)"""
         filt.clear()
         filt.stats(reset=True)
         asm.reset()
         p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         p0.record(ext)
-        if world > 1:
-            from abyss_b200 import multigpu
-            multigpu.sharded_insert(filt, bases[lo * L:up * L], offs_slice, up - lo)
-            nk = n_kmers_expected
+        if host is None:
+            if world > 1:
+                nk = filt.insert_reads_sharded_dev(comm, bases.data_ptr(), offs.data_ptr(), rs.n)
+            else:
+                nk = filt.insert_reads_dev(bases.data_ptr(), offs.data_ptr(), rs.n, bases.numel())
             p1.record(ext)
-            codes = multigpu.sharded_classify(asm, bases[lo * L:up * L], offs_slice, up - lo, rs.n)
-            contigs = asm.process_reads_dev(bases.data_ptr(), offs.data_ptr(), rs.n)
-            del codes
-        elif host is None:
-            nk = filt.insert_reads_dev(bases.data_ptr(), offs.data_ptr(), rs.n, bases.numel())
-            p1.record(ext)
-            contigs = asm.process_reads_dev(bases.data_ptr(), offs.data_ptr(), rs.n)
+            contigs = pass2(bases.data_ptr(), offs.data_ptr())
         else:
-            nk = filt.insert_reads(host)
+            nk = filt.insert_reads_sharded(comm, host) if world > 1 else filt.insert_reads(host)
             p1.record(ext)
-            contigs = asm.process_reads(host)
+            d_b, d_o, n_res = filt.resident_reads()  # the copy pass 1 made stays on the device for pass 2
+            assert n_res == rs.n
+            contigs = pass2(d_b, d_o)
         torch.cuda.synchronize()
         ast, ist, cnt = asm.stats(), filt.stats(), asm.counters()
         ist.ms_pass1 = p0.elapsed_time(p1)
@@ -279,22 +338,30 @@ def main():
     assert nk == n_kmers_expected, (nk, n_kmers_expected)
     total_kmers = nk  # one job, counted once (strong scaling)
     value = total_kmers / (ms_step * 1e-3)
+    digest = asm.last_digests(rs.read_id)
 
     # ---- e2e through host buffers
     e2e = None
-    if not args.no_e2e and world == 1:
+    if not args.no_e2e:
         hb = torch.empty(bases.numel(), dtype=torch.uint8, pin_memory=True)
         hb.copy_(bases)
         ho = offs.cpu().numpy().astype(np.uint64)
         host = (hb.numpy(), ho)
         timed(1, host)
-        eruns = timed(max(1, args.steps), host)
+        eruns = timed(max(1, min(args.steps, 3)), host)
         ems = sum(r[0] for r in eruns) / len(eruns)
         econt = eruns[-1][1][1]
+        edigest = asm.last_digests(rs.read_id)
+        assert edigest == digest, ("e2e output differs from the device-resident arm", edigest, digest)
         d2h = sum(c[1] for c in econt) + 24 * len(econt) + rs.n  # unitig bases + records + per-read codes
         e2e = {"value": total_kmers / (ems * 1e-3), "unit": "k-mers/s", "ms_per_step": ems,
-               "h2d_bytes_per_step": 2 * (int(hb.numel()) + int(ho.nbytes)), "d2h_bytes_per_step": int(d2h)}
+               "h2d_bytes_per_step": int(hb.numel()) + int(ho.nbytes), "d2h_bytes_per_step": int(d2h),
+               "note": "per rank" if world > 1 else "", "fasta_md5": edigest["fasta_md5"]}
         del hb
+    if world > 1:  # every rank must have produced the same FASTA
+        box = [None] * world
+        dist.all_gather_object(box, digest)
+        assert all(d == box[0] for d in box), ("ranks disagree on the output", box)
 
     if rank != 0:
         if world > 1:
@@ -303,28 +370,27 @@ def main():
         return
 
     peak, peak_src = peaks()
-    commit_ms = ist.ms_commit / max(1, ist.commit_launches)
-    kmers_per_launch = ist.kmers / max(1, ist.commit_launches)  # k-mers this rank inserted per k_commit launch
-    achieved = ALG_BYTES_PER_KMER * kmers_per_launch / (commit_ms * 1e-3) / 1e9 if commit_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "k_commit (ordered counting-Bloom min-increment)", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak,
-                "traffic": NCU_TRAFFIC_PER_COMMIT_LAUNCH if (args.window in (0, 1 << 19) and args.reads == N_READS) else None,
-                "traffic_note": "bytes per launch, ncu cold-cache capture profiles/r01_k_commit_w19_full_raw.csv; algorithmic bytes per launch = "
-                                f"{ALG_BYTES_PER_KMER * kmers_per_launch:.3e}",
-                "peak_source": peak_src,
-                "alg_bytes_per_kmer": ALG_BYTES_PER_KMER, "launches": int(ist.commit_launches),
-                "avg_launch_ms": commit_ms, "share_of_step": ist.ms_commit / ms_step}
+    launch_ms = ist.ms_commit / max(1, ist.commit_launches)
+    slots_per_launch = ist.commit_slots / max(1, ist.commit_launches)
+    # at N > 1 each rank moves 1/N of the counter sectors of every slot it evaluates
+    alg_per_slot = (64 * H) / world + L / (L - K + 1)
+    achieved = alg_per_slot * slots_per_launch / (launch_ms * 1e-3) / 1e9 if launch_ms > 0 else 0.0
+    phase_ms = ist.ms_pass1
+    phase_achieved = alg_per_slot * nk / (phase_ms * 1e-3) / 1e9
+    kernel = "k_insert_windows (persistent ordered counting-Bloom min-increment)" if world == 1 else \
+        "k_sh_gather + ncclAllReduce(min) + k_sh_apply (one file-order window, counters sharded by position)"
+    roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": NCU_TRAFFIC_PER_SLOT * slots_per_launch if NCU_TRAFFIC_PER_SLOT else None,
+                "peak_source": peak_src, "alg_bytes_per_kmer": alg_per_slot, "launches": int(ist.commit_launches),
+                "slots_per_launch": slots_per_launch, "avg_launch_ms": launch_ms, "share_of_step": ist.ms_commit / ms_step,
+                "insert_phase": {"ms": phase_ms, "achieved": phase_achieved, "frac": phase_achieved / peak,
+                                 "what": "hash + ordered insert + drains" + (" + all-gather of the shards" if world > 1 else "")}}
 
     cpu = None
-    if not args.no_cpu_baseline and os.path.exists(REF_BIN):
+    if not args.no_cpu_baseline and os.path.exists(REF_BIN) and world == 1:
         cores = os.cpu_count() or 1
-        tmp = tempfile.mkdtemp(prefix="abyss_ref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
-        fq = os.path.join(tmp, "sample.fq")
-        write_sample_fastq(rs, min(args.ref_reads, rs.n), fq)
-        dt = run_reference(fq, cores, os.path.join(tmp, "ref.fa"))
-        sample = min(args.ref_reads, rs.n)
-        cpu = {"value": sample * (L - K + 1) / dt, "unit": "k-mers/s", "cores": cores, "kind": "reference",
-               "sample": f"first {sample} reads of the workload, abyss-bloom-dbg -j{cores} (unmodified reference), {dt:.1f} s wall"}
+        sample = args.ref_reads or 4_000_000
+        cpu = cpu_baseline_dict(reference_measurement(rs, min(sample, rs.n), cores, 1), cores, min(sample, rs.n))
 
     line = {
         "metric": "k-mers/sec (Bloom insert + unitig extend)", "value": value, "unit": "k-mers/s", "n_gpus": world,
@@ -339,6 +405,8 @@ def main():
         "pass1_ms": ist.ms_pass1, "insert_kmers_per_s": nk / (ist.ms_pass1 * 1e-3),
         "extend_kmers_per_s": nk / ((ast.ms_classify + ast.ms_tiles + ast.ms_visited + ast.ms_extend + ast.ms_replay) * 1e-3),
         "unitigs": int(cnt.contig_id), "bases_assembled": int(cnt.bases_assembled),
+        "fasta_md5": digest["fasta_md5"], "unitig_multiset_md5": digest["unitig_multiset_md5"],
+        "drains": int(ist.drains), "drained_slots": int(ist.drained_slots),
         "speculation": {"rounds": int(ast.rounds), "speculated": int(ast.speculated_reads), "wasted": int(ast.wasted_reads),
                         "markers": int(ast.markers), "tiles": int(ast.tiles), "serial_fallbacks": int(ast.serial_fallbacks)},
         "deferred_inserts": int(ist.deferred),

@@ -109,10 +109,40 @@ int abb_hash_reads(unsigned k, const char* mask, const char* bases, const uint64
 int abb_hash_reads_dev(abb_filter* f, const char* d_bases, const uint64_t* d_offsets, uint64_t n_reads,
                        uint64_t* d_h0, uint8_t* d_valid, uint64_t capacity, uint64_t* n_slots_out);
 int abb_insert_h0_dev(abb_filter* f, const uint64_t* d_h0, uint64_t n);
-/* stable partition of the valid hashes by owning rank (world contiguous hash ranges over the top 16 bits):
- * d_send = [owned by 0 | owned by 1 | ...], each part in slot order; counts_out[world] on the host. */
-int abb_route_h0_dev(abb_filter* f, const uint64_t* d_h0, const uint8_t* d_valid, uint64_t n, unsigned world,
-                     uint64_t* d_send, uint64_t* counts_out);
+
+/* ---- multi-GPU exact insert (Bloom/bloom.cc:556-580 `-w M/N` windows are the precedent) -----
+ * One process (or host thread) per GPU.  The counter array is sharded by POSITION RANGE: rank r owns counters
+ * [r*chunk, (r+1)*chunk), chunk = ceil(size / world) rounded up to 16.  All ranks walk the same file-order windows
+ * of all reads, touch only the counters they own, and exchange one ncclAllReduce(min, uint8) per window (partial
+ * minima + veto flags); the result is the sequential -j1 counter array, bit for bit, for every world size
+ * (abb_shard.cuh).  The NCCL communicator lives behind the C ABI; NCCL is dlopen()ed (libnccl.so.2), so a host
+ * that never calls abb_comm_* does not need it.
+ * abb_comm_unique_id: rank 0 creates the 128-byte NCCL id, the caller ships it to the other ranks (MPI, TCP, a
+ *                     file, torch.distributed ...).
+ * abb_comm_create:    ncclCommInitRank on `device`.
+ * abb_insert_reads_sharded_dev: EVERY rank passes the same reads (device resident).  finalize != 0 all-gathers the
+ *                     shards afterwards so that each rank holds the whole filter (what the extension stage needs);
+ *                     with finalize == 0 only the own range of f is meaningful until abb_filter_allgather.
+ * abb_comm_allgather_bytes / abb_comm_allreduce_max_u8: the collectives pass 2 needs (read codes, tile stores). */
+typedef struct abb_comm abb_comm;
+int abb_comm_unique_id(uint8_t id_out[128]);
+int abb_comm_create(abb_comm** out, int rank, int world, const uint8_t id[128], int device);
+int abb_comm_destroy(abb_comm* c);
+int abb_comm_rank(const abb_comm* c);
+int abb_comm_world(const abb_comm* c);
+int abb_insert_reads_sharded_dev(abb_filter* f, abb_comm* c, const char* d_bases, const uint64_t* d_offsets, uint64_t n_reads,
+                                 int finalize, uint64_t* n_kmers_out);
+int abb_insert_reads_sharded(abb_filter* f, abb_comm* c, const char* bases, const uint64_t* offsets, uint64_t n_reads, int finalize,
+                             uint64_t* n_kmers_out); /* host buffers: copies the batch to the device first */
+int abb_filter_allgather(abb_filter* f, abb_comm* c);
+/* the device copy of the batch the last host-buffer insert (abb_insert_reads / abb_insert_reads_sharded) made: a host
+ * that inserts all reads in one batch hands these to abb_assembler_process_reads_dev instead of copying the reads a
+ * second time for pass 2 (the reference reads its input files twice, BloomDBG/bloom-dbg.h:1011-1046) */
+int abb_filter_resident_reads(abb_filter* f, const char** d_bases, const uint64_t** d_offsets, uint64_t* n_reads);
+/* d_buf holds world * bytes_per_rank bytes, this rank's part already in place at rank * bytes_per_rank */
+int abb_comm_allgather_bytes(abb_comm* c, void* d_buf, uint64_t bytes_per_rank, void* cuda_stream);
+int abb_comm_allreduce_max_u8(abb_comm* c, void* d_buf, uint64_t n, void* cuda_stream);
+
 void* abb_filter_device_ptr(abb_filter* f, int level);
 
 /* ---- raw array <-> host (operator<< / loadFilter: CountingBloomFilter.hpp:262-379,
@@ -208,11 +238,14 @@ typedef struct abb_insert_stats {
 	uint64_t deferred;        /* events that lost a reservation and went through the ordered pass */
 	uint64_t launches;        /* kernels launched by this library since the last reset */
 	float ms_hash, ms_insert; /* CUDA-event time on the library stream since the last reset */
-	float ms_commit;          /* with profiling on: summed CUDA-event time of the k_commit launches */
-	uint64_t commit_launches; /* number of k_commit launches timed */
+	float ms_commit;          /* with profiling on: summed CUDA-event time of the timed k_window launches */
+	uint64_t commit_launches; /* number of k_window launches timed */
+	uint64_t commit_slots;    /* k-mer slots those launches applied */
+	uint64_t drains;          /* serial drains that did work, and the slots they replayed */
+	uint64_t drained_slots;
 } abb_insert_stats;
 int abb_filter_insert_stats(abb_filter* f, abb_insert_stats* out, int reset);
-/* time each launch of the Bloom-insert commit kernel with CUDA events (bench.py roofline) */
+/* time launches of the Bloom-insert window kernel with CUDA events (bench.py roofline) */
 int abb_filter_set_profiling(abb_filter* f, int on);
 /* the cudaStream_t all work of this filter (and of an assembler created on it) is issued to */
 void* abb_filter_stream(abb_filter* f);

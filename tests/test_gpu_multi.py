@@ -1,4 +1,7 @@
-"""2-GPU test of the hash-range sharded pass 1 (run under `gpurun --gpus 2`; skipped with < 2 devices)."""
+"""Multi-GPU tests of the exact position-sharded pass 1 (run under `gpurun --gpus 2` or more; skipped with one device).
+At every world size the counters must be the sequential -j1 array bit for bit (sha256 of the reference's
+`abyss-bloom build -t counting` output, tests/golden/e2e_cases.json) and the unitig FASTA byte-identical to the
+reference's (tests/golden/*.fa) -- the same goldens the single-GPU tests use."""
 import os
 import subprocess
 import sys
@@ -9,7 +12,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 WORKER = r'''
-import os, sys, json, numpy as np, torch, torch.distributed as dist
+import os, sys, json, hashlib, numpy as np, torch, torch.distributed as dist
 sys.path.insert(0, %(root)r)
 from abyss_b200 import capi, multigpu
 from abyss_b200.synth import ReadSet
@@ -17,64 +20,56 @@ rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(rank)
 dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
 dev = torch.device("cuda", rank)
-rs = ReadSet.from_coverage(21, 20000, 30, 150, 0.005)
-k, kc, H, m, L = 32, 2, 4, 932096, 150
-asc = rs.ascii(0, rs.n)
-lo, up = rank * rs.n // world, (rank + 1) * rs.n // world
-bases = torch.from_numpy(asc[lo:up].reshape(-1).copy()).to(dev)
-offs = torch.arange(up - lo + 1, dtype=torch.int64, device=dev) * L
-f = capi.Filter.counting(m, H, k, kc, device=rank)
-owned = multigpu.sharded_insert(f, bases, offs, up - lo)
-merged = f.download()
-# sharded classification: codes gathered from both ranks == codes of an unsharded run on the merged filter
-all_bases = torch.from_numpy(asc.reshape(-1).copy()).to(dev)
-all_offs = torch.arange(rs.n + 1, dtype=torch.int64, device=dev) * L
-a1 = capi.Assembler(f)
-codes = multigpu.sharded_classify(a1, bases, offs, up - lo, rs.n)
-out_sharded = a1.process_reads_dev(all_bases.data_ptr(), all_offs.data_ptr(), rs.n)
-res_sharded = a1.read_results().copy()
-a1.close()
-a2 = capi.Assembler(f)
-out_plain = a2.process_reads_dev(all_bases.data_ptr(), all_offs.data_ptr(), rs.n)
-res_plain = a2.read_results().copy()
-a2.close()
-assert out_sharded == out_plain and (res_sharded == res_plain).all()
-tot = torch.tensor([owned], device=dev); dist.all_reduce(tot)
-assert int(tot.item()) == rs.n * (L - k + 1), (int(tot.item()), rs.n * (L - k + 1))
-# every rank holds the same merged filter
-chk = torch.tensor([int(merged.astype(np.uint64).sum())], device=dev)
-mx = chk.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX); assert int(mx.item()) == int(chk.item())
+def bcast(b):
+    box = [b]; dist.broadcast_object_list(box, src=0); return box[0]
+comm = capi.Comm(rank, world, rank, bcast)
+gd = os.path.join(%(root)r, "tests", "golden")
+cases = {c["name"]: c for c in json.load(open(os.path.join(gd, "e2e_cases.json")))}
+for name, window in (("e2e_g20k_k32", 0), ("e2e_g30k_k64", 4096), ("e2e_g10k_k25_small", 1000)):
+    c = cases[name]
+    rs = ReadSet.from_coverage(c["seed"], c["genome"], c["cov"], c["L"], c["err"])
+    L = c["L"]
+    asc = rs.ascii(0, rs.n)
+    bases = torch.from_numpy(asc.reshape(-1).copy()).to(dev)
+    offs = torch.arange(rs.n + 1, dtype=torch.int64, device=dev) * L
+    f = capi.Filter.counting(c["counters"], c["H"], c["k"], c["kc"], device=rank)
+    if window:
+        f.set_window(window)
+    nk = f.insert_reads_sharded_dev(comm, bases.data_ptr(), offs.data_ptr(), rs.n)
+    assert nk == rs.n * (L - c["k"] + 1), (nk, rs.n)
+    got = f.download()
+    assert hashlib.sha256(got.tobytes()).hexdigest() == c["counters_sha256"], f"{name}: rank {rank} counters differ from the -j1 reference"
+    # host-buffer entry point gives the same
+    g = capi.Filter.counting(c["counters"], c["H"], c["k"], c["kc"], device=rank)
+    g.insert_reads_sharded(comm, capi.fixed_length_reads(asc))
+    assert (g.download() == got).all()
+    g.close()
+    # pass 2 with the classification sharded over the ranks: FASTA and read log identical to the reference
+    lo, up = rank * rs.n // world, (rank + 1) * rs.n // world
+    offs_slice = torch.arange(up - lo + 1, dtype=torch.int64, device=dev) * L
+    a = capi.Assembler(f, read_log=True)
+    codes = multigpu.sharded_classify(a, comm, bases.data_ptr() + lo * L, offs_slice.data_ptr(), up - lo, rs.n, dev)
+    out = a.process_reads_dev(bases.data_ptr(), offs.data_ptr(), rs.n)
+    fasta = "".join(f">{i} {len(s)} {cov} read:{rs.read_id(r)}\n{s}\n" for i, (r, s, cov) in enumerate(out))
+    assert fasta == open(os.path.join(gd, name + ".fa")).read(), f"{name}: rank {rank} FASTA differs"
+    res = a.read_results()
+    log = open(os.path.join(gd, name + ".readlog.tsv")).read().split("\n")[1:-1]
+    assert [f"{rs.read_id(i)}\t{capi.READ_CODES[res[i]]}" for i in range(rs.n)] == log
+    a.close(); f.close()
+dist.barrier()
 if rank == 0:
-    # single-GPU filter of the same reads: the merged one never under-counts an inserted k-mer
-    g = capi.Filter.counting(m, H, k, kc, device=0)
-    g.insert_reads(capi.fixed_length_reads(asc))
-    h0, valid, _ = capi.hash_reads(k, capi.fixed_length_reads(asc[:400]))
-    mult = [np.uint64((i ^ ((k * 0x90b45d39fb6da1fa) & 0xFFFFFFFFFFFFFFFF)) & 0xFFFFFFFFFFFFFFFF) for i in range(H)]
-    hh = [h0]
-    with np.errstate(over="ignore"):
-        for j in range(1, H):
-            t = h0 * mult[j]; hh.append(t ^ (t >> np.uint64(27)))
-    hs = np.stack(hh, axis=1)
-    uniq, cnt = np.unique(h0, return_counts=True)
-    assert (f.minCount(hs) >= 1).all()
-    # unitigs from the merged filter equal the single-GPU ones as a set of canonical sequences
-    ids = [rs.read_id(i) for i in range(rs.n)]
-    def unitigs(filt):
-        a = capi.Assembler(filt); out = a.process_reads(capi.fixed_length_reads(asc)); a.close()
-        rc = lambda s: s.translate(str.maketrans("ACGT", "TGCA"))[::-1]
-        return sorted(min(s, rc(s)) for _, s, _ in out)
-    assert unitigs(f) == unitigs(g)
     print("MULTI_OK")
-dist.barrier(); dist.destroy_process_group()
+dist.destroy_process_group()
 '''
 
 
-def test_sharded_pass1_two_gpus(tmp_path):
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_insert_is_exact(tmp_path, world):
     import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
     w = tmp_path / "worker.py"
     w.write_text(WORKER % {"root": ROOT})
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-                        "--master-port", "29541", str(w)], capture_output=True, text=True, timeout=600)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+                        "--master-port", str(29541 + world), str(w)], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "MULTI_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]

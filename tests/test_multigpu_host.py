@@ -1,9 +1,12 @@
-"""CPU (gloo, world_size 2, 3 and 4): the host logic of the hash-range sharded pass 1 -- ownership, stable
-routing, the all-to-all, and the file-order property of the receive buffer.  No GPU needed."""
+"""CPU (gloo, world_size 1, 2, 3 and 4): the protocol of the position-sharded exact insert -- partial minima and veto
+flags, ONE all-reduce(min) per step, identical file-order carry lists on every rank -- reproduces the sequential
+oracle's counters bit for bit at every world size.  The CUDA implementation (abb_shard.cuh) follows the same steps;
+tests/shard_model.py is its numpy statement.  No GPU needed."""
 import os
 import socket
 
 import numpy as np
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -17,46 +20,59 @@ def _free_port():
     return p
 
 
+def _case(seed, n_reads, L, k, H, m):
+    import oracle_py
+    from abyss_b200.synth import ReadSet
+    orc = oracle_py.load()
+    rs = ReadSet(seed, 3000, n_reads, L, 0.01)
+    seqs = [a.tobytes() for a in rs.ascii(0, rs.n)]
+    seqs[3] = seqs[3][:20] + b"N" + seqs[3][21:]          # a window with a non-ACGT base yields no k-mer
+    seqs += [b"T" * 60, b"T" * 60]                          # one k-mer repeated: long dependency chain
+    hs = np.concatenate([orc.hash_seq(s, k, H)[0] for s in seqs])
+    exp = np.zeros(m, dtype=np.uint8)
+    orc.cbf_insert_hashes(exp, hs)
+    return (hs % np.uint64(m)).astype(np.int64), exp
+
+
 def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from shard_model import shard_range, sharded_insert_model
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from abyss_b200.multigpu import exchange, owner_of, route_by_owner
-    # global stream of "k-mers" in file order: value i carries its own index in the low bits
-    n = 10000
-    rng = np.random.default_rng(1)
-    hi = rng.integers(0, 1 << 16, size=n, dtype=np.int64)
-    allh = torch.from_numpy((hi << 48) | np.arange(n, dtype=np.int64))
-    allv = torch.from_numpy((rng.random(n) > 0.1).astype(np.uint8))
-    lo, up = rank * n // world, (rank + 1) * n // world  # contiguous file-order slices
-    send, counts = route_by_owner(allh[lo:up], allv[lo:up], world)
-    assert int(counts.sum()) == int(allv[lo:up].sum())
-    recv = exchange(send, counts)
-    # everything received is owned by this rank, valid, and in global file order
-    assert bool((owner_of(recv, world) == rank).all())
-    idx = recv & 0xFFFFFFFF
-    assert bool((idx[1:] > idx[:-1]).all())
-    expect = allh[(owner_of(allh, world) == rank) & allv.bool()]
-    assert torch.equal(recv, expect)
-    out[rank] = int(recv.numel())
+
+    def allreduce_min(buf):
+        t = torch.from_numpy(buf.copy())
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return t.numpy()
+
+    ok = True
+    # tiny filter (everything conflicts, saturation), a medium one, and one with H = 3
+    for (seed, n_reads, L, k, H, m, window, ent, lanes) in [(5, 60, 60, 20, 4, 512, 64, 1 << 8, 16), (6, 120, 80, 25, 4, 40000, 256, 1 << 10, 32),
+                                                             (7, 80, 60, 21, 3, 3001 * 8, 100, 1 << 9, 8)]:
+        pos, exp = _case(seed, n_reads, L, k, H, m)
+        got, steps = sharded_insert_model(pos, m, rank, world, allreduce_min, window, ent, lanes)
+        lo, hi = shard_range(m, rank, world)
+        ok &= bool((got[lo:hi] == exp[lo:hi]).all())
+        # all-gather of the shards = the whole sequential array
+        parts = [torch.zeros(m, dtype=torch.uint8) for _ in range(world)]
+        mine = torch.zeros(m, dtype=torch.uint8)
+        mine[lo:hi] = torch.from_numpy(got[lo:hi])
+        if world > 1:
+            dist.all_gather(parts, mine)
+            full = torch.stack(parts).max(dim=0).values.numpy()
+        else:
+            full = mine.numpy()
+        ok &= bool((full == exp).all())
+    out[rank] = ok
     dist.barrier()
     dist.destroy_process_group()
 
 
-import pytest
-
-
-@pytest.mark.parametrize("world", [2, 3, 4])
-def test_sharded_routing(world):
+@pytest.mark.parametrize("world", [1, 2, 3, 4])
+def test_sharded_insert_protocol_is_exact(world):
     mgr = mp.Manager()
     out = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
-    assert sum(out.values()) > 0 and len(out) == world
-
-
-def test_owner_ranges():
-    from abyss_b200.multigpu import owner_of
-    h = torch.tensor([0, (1 << 62), -1, -(1 << 63)], dtype=torch.int64)  # int64 views of uint64 0, 2^62, 2^64-1, 2^63
-    for world in (1, 2, 4, 8):
-        o = owner_of(h, world)
-        assert o.min() >= 0 and o.max() < world
-        assert int(o[0]) == 0 and int(o[2]) == world - 1
+    assert len(out) == world and all(out.values())
