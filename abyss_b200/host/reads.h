@@ -82,22 +82,51 @@ struct ReadBatch {
 	std::string id(size_t i) const { return std::string(id_chars.data() + id_offsets[i], id_chars.data() + id_offsets[i + 1]); }
 };
 
+/** the shell command that decompresses `path` to stdout ("" = plain file).  The name goes through /bin/sh (popen),
+ *  so a single quote inside it is escaped as '\'' (Common/Uncompress.cpp of the reference builds its commands the
+ *  same way and has the same exposure). */
+inline std::string decompress_command(const std::string& path)
+{
+	auto ends = [&](const char* suf) {
+		size_t n = strlen(suf);
+		return path.size() >= n && path.compare(path.size() - n, n, suf) == 0;
+	};
+	const char* tool = (ends(".gz") || ends(".z") || ends(".Z")) ? "gunzip -c" : ends(".bz2") ? "bunzip2 -c" : ends(".xz") ? "xzdec -c" : nullptr;
+	if (!tool)
+		return "";
+	std::string q = "'";
+	for (char c : path) {
+		if (c == '\'')
+			q += "'\\''";
+		else
+			q += c;
+	}
+	q += "'";
+	return std::string(tool) + " " + q;
+}
+/** close an input opened with fopen / popen; a decompressor that failed (missing tool, corrupt file) is an error, not an
+ *  empty input */
+inline void close_input(FILE* f, bool is_pipe, const std::string& path)
+{
+	if (!f || f == stdin)
+		return;
+	if (!is_pipe) {
+		fclose(f);
+		return;
+	}
+	const int st = pclose(f);
+	if (st != 0) {
+		fprintf(stderr, "error: `%s': the decompressor exited with status %d\n", path.c_str(), st);
+		exit(EXIT_FAILURE);
+	}
+}
+
 class SeqReader {
   public:
 	SeqReader(const std::string& path, const ReadOpts& o) : m_path(path), m_opt(o)
 	{
 		const char* p = path.c_str();
-		auto ends = [&](const char* suf) {
-			size_t n = strlen(suf);
-			return path.size() >= n && path.compare(path.size() - n, n, suf) == 0;
-		};
-		std::string cmd;
-		if (ends(".gz") || ends(".z") || ends(".Z"))
-			cmd = "gunzip -c '" + path + "'";
-		else if (ends(".bz2"))
-			cmd = "bunzip2 -c '" + path + "'";
-		else if (ends(".xz"))
-			cmd = "xzdec -c '" + path + "'";
+		const std::string cmd = decompress_command(path);
 		if (!cmd.empty()) {
 			m_f = popen(cmd.c_str(), "r");
 			m_pipe = true;
@@ -121,8 +150,7 @@ class SeqReader {
 	RawBuf release() { return std::move(m_buf); }
 	~SeqReader()
 	{
-		if (m_f && m_f != stdin)
-			m_pipe ? pclose(m_f) : fclose(m_f);
+		close_input(m_f, m_pipe, m_path);
 	}
 
 	/** next record; false at end of file */
@@ -223,7 +251,7 @@ class SeqReader {
 			for (auto& ch : seq) // FOLD_CASE
 				if (ch >= 'a' && ch <= 'z')
 					ch = (char)(ch - 32);
-			const int qoff = m_opt.qualityOffset > 0 ? m_opt.qualityOffset : 33;
+			const int qoff = 33; // FastaReader.cpp: `qualityOffset = 33` for '>' / '@' records; --illumina-quality only applies to qseq/export
 			if (m_opt.qualityThreshold > 0 && !q.empty()) { // FastaReader.cpp:376-394
 				const int good = qoff + m_opt.qualityThreshold;
 				size_t front = 0, back = q.size();
@@ -406,7 +434,7 @@ class BatchStream {
 				out.reset(new ReadBatch());
 			out->clear();
 			m_outp = out.get();
-			while (out->size() < m_batchReads) {
+			while (out->size() < m_batchReads && out->bases.size() < kBatchBaseBudget) {
 				if (!m_cur || m_curPos == m_cur->size()) {
 					std::unique_lock<std::mutex> l(m_mu);
 					m_cv.wait(l, [&] { return m_stop || m_done.count(m_nextOut) || (m_readerDone && m_nextOut == m_nextSeq); });
@@ -425,14 +453,18 @@ class BatchStream {
 					m_cv.notify_all();
 					continue;
 				}
-				const size_t take = (size_t)std::min<uint64_t>(m_batchReads - out->size(), m_cur->size() - m_curPos);
-				if (out->bases.capacity() == 0 && m_cur->size()) { // size a new output batch from the piece's average read
+				size_t take = (size_t)std::min<uint64_t>(m_batchReads - out->size(), m_cur->size() - m_curPos);
+				// long records (contigs, genomes): stop at the base budget, but always take at least one record
+				while (take > 1 && out->bases.size() + (m_cur->offsets[m_curPos + take] - m_cur->offsets[m_curPos]) > kBatchBaseBudget)
+					take = (take + 1) / 2;
+				if (out->bases.capacity() == 0 && m_cur->size()) { // size a new output batch from the piece's average read: a hint, capped
 					const double n = (double)m_cur->size();
 					const uint64_t want = m_batchReads;
-					out->bases.reserve((size_t)(1.05 * want * (m_cur->bases.size() / n)) + 4096);
-					out->id_chars.reserve((size_t)(1.25 * want * (m_cur->id_chars.size() / n)) + 4096);
-					out->offsets.reserve(want + 1);
-					out->id_offsets.reserve(want + 1);
+					const size_t cap = (size_t)1 << 30;
+					out->bases.reserve(std::min(cap, (size_t)(1.05 * want * (m_cur->bases.size() / n)) + 4096));
+					out->id_chars.reserve(std::min(cap, (size_t)(1.25 * want * (m_cur->id_chars.size() / n)) + 4096));
+					out->offsets.reserve(std::min<size_t>(want + 1, cap / 8));
+					out->id_offsets.reserve(std::min<size_t>(want + 1, cap / 8));
 				}
 				const auto a0 = std::chrono::steady_clock::now();
 				append(*m_cur, m_curPos, take);
@@ -579,17 +611,7 @@ class BatchStream {
 	}
 	static FILE* open_input(const std::string& path, bool* is_pipe)
 	{
-		auto ends = [&](const char* suf) {
-			size_t n = strlen(suf);
-			return path.size() >= n && path.compare(path.size() - n, n, suf) == 0;
-		};
-		std::string cmd;
-		if (ends(".gz") || ends(".z") || ends(".Z"))
-			cmd = "gunzip -c '" + path + "'";
-		else if (ends(".bz2"))
-			cmd = "bunzip2 -c '" + path + "'";
-		else if (ends(".xz"))
-			cmd = "xzdec -c '" + path + "'";
+		const std::string cmd = decompress_command(path);
 		*is_pipe = !cmd.empty();
 		FILE* f = !cmd.empty() ? popen(cmd.c_str(), "r") : path == "-" ? stdin : fopen(path.c_str(), "r");
 		if (!f) {
@@ -665,12 +687,12 @@ class BatchStream {
 			}
 			m_cv.notify_all();
 		}
-		if (f != stdin)
-			is_pipe ? pclose(f) : fclose(f);
+		close_input(f, is_pipe, path);
 		m_tRead += std::chrono::duration<double>(std::chrono::steady_clock::now() - r0).count();
 		return ok;
 	}
 
+	static constexpr size_t kBatchBaseBudget = (size_t)3 << 29; // 1.5 G bases per batch at most
 	std::vector<std::string> m_files;
 	ReadOpts m_opt;
 	uint64_t m_batchReads;

@@ -19,7 +19,7 @@ bases = torch.cat(chunks); del chunks
 offs = torch.arange(rs.n + 1, dtype=torch.int64, device="cuda") * L
 torch.cuda.synchronize()
 print(f"generated {rs.n} reads in {time.time()-t0:.1f}s")
-windows = [int(sys.argv[3])] if len(sys.argv) > 3 else [1 << 17, 1 << 18, 1 << 19, (1 << 20) - 64]
+windows = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [1 << 16, 1 << 17, 1 << 18, 1 << 19]
 for window in windows:
     f = capi.Filter.counting(counters, H, k, 3)
     f.set_window(window)
@@ -30,5 +30,6 @@ for window in windows:
     dt = time.time() - t0
     st = f.stats()
     print(f"window {window:8d}: {n/dt/1e9:6.3f} G kmers/s wall | hash {st.ms_hash:8.1f} ms insert {st.ms_insert:8.1f} ms "
-          f"-> insert-only {n/st.ms_insert/1e6:6.3f} G/s | windows {st.windows} deferred {st.deferred} ({100*st.deferred/n:.2f}%) launches {st.launches}")
+          f"-> insert-only {n/st.ms_insert/1e6:6.3f} G/s | windows {st.windows} deferred {st.deferred} ({100*st.deferred/n:.2f}%) launches {st.launches} drains {st.drains} "
+          f"drained {st.drained_slots} | map 2^{__import__('os').environ.get('ABB_MAP_LOG2', '25')}")
     f.close()

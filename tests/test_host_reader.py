@@ -123,3 +123,32 @@ def test_long_records(exe, tmp_path):
     assert len(lines[0]) == 4 + len(big) and len(lines[1]) == 7 + 3_000_060 and lines[2] == "tail\tACGT"
     got, batches = run(exe, "stream", 2, 2, 1 << 20, p)
     assert got == want and batches == [2, 1]
+
+
+def test_default_batch_size_with_long_record(exe, tmp_path):
+    # the CLIs' default --batch-reads (4 000 000) with a multi-Mbp record: the batch buffers are sized as a hint with a
+    # ceiling (the first version asked for 1.05 * 4e6 * 5 Mbp and died with std::bad_alloc)
+    rng = random.Random(5)
+    genome = "".join(rng.choice("ACGT") for _ in range(1 << 16)) * 80       # 5.2 Mbp
+    p = tmp_path / "genome.fa"
+    p.write_text(">chr1\n" + genome + "\n>chr2\n" + genome[:1000] + "\n")
+    want, _ = run(exe, "serial", p)
+    got, batches = run(exe, "stream", 2, 4_000_000, 1 << 24, p)
+    assert got == want and sum(batches) == 2
+
+
+def test_compressed_input_and_quoting(exe, tmp_path):
+    import gzip
+    # a file name with a single quote and a space goes through popen's shell unharmed
+    d = tmp_path / "it's a dir"
+    d.mkdir()
+    p = d / "r.fa.gz"
+    with gzip.open(p, "wt") as f:
+        f.write(">a\nACGTACGT\n>b\nTTTT\n")
+    got, _ = run(exe, "serial", p)
+    assert got == "a\tACGTACGT\nb\tTTTT\n"
+    # a decompressor that fails is an error, not an empty input
+    bad = d / "broken.fa.gz"
+    bad.write_bytes(b"this is not gzip")
+    r = subprocess.run([exe, "serial", str(bad)], capture_output=True, text=True)
+    assert r.returncode != 0 and "decompressor" in r.stderr
