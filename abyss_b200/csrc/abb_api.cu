@@ -71,12 +71,12 @@ static FilterView view_of(const abb_filter* f)
 	return v;
 }
 
-/** conflict-map size: 2^25 two-bit entries (8 MiB per map: with the small default window both maps, the tag prefix
- *  and the carry lists stay resident in the 126 MB L2 next to the streaming counter sectors); exact (no aliases)
- *  for filters of up to 2^25 positions.  ABB_MAP_LOG2 overrides (tuning). */
+/** conflict-map size: 2^26 two-bit entries (16 MiB per map; both maps are pinned in L2 while the insert runs,
+ *  set_l2_policy); with the default window of 2^17 slots 3.2 % of the slots see an alias and are carried.  Exact (no
+ *  aliases) for filters of up to 2^26 positions.  ABB_MAP_LOG2 overrides (tuning). */
 static uint64_t map_entries_for(uint64_t filter_size)
 {
-	unsigned lg = 25;
+	unsigned lg = 26;
 	if (const char* e = getenv("ABB_MAP_LOG2")) {
 		const int v = atoi(e);
 		if (v >= 10 && v <= 32)
@@ -97,8 +97,8 @@ static int ensure_workspace(abb_filter* f)
 {
 	if (f->d_carry && f->ws_window == f->window && f->ws_H == f->H)
 		return ABB_OK;
+	cudaFree(f->d_map[0]); // one allocation holds both maps (one L2 access-policy window covers them)
 	for (int i = 0; i < 2; ++i) {
-		cudaFree(f->d_map[i]);
 		cudaFree(f->d_tags2[i]);
 		f->d_map[i] = nullptr;
 		f->d_tags2[i] = nullptr;
@@ -112,9 +112,10 @@ static int ensure_workspace(abb_filter* f)
 	// at most kCarryLanes carried slots reserve H positions each; load factor <= 1/8.  Only a prefix sized to the
 	// carried slots of a window is in use (tag_mask_for)
 	f->tag_slots = next_pow2(8ULL * kCarryLanes * f->H);
+	ABB_CUDA(cudaMalloc((void**)&f->d_map[0], 2 * map_bytes));
+	ABB_CUDA(cudaMemsetAsync(f->d_map[0], 0, 2 * map_bytes, f->stream));
+	f->d_map[1] = f->d_map[0] + map_bytes / sizeof(unsigned);
 	for (int i = 0; i < 2; ++i) {
-		ABB_CUDA(cudaMalloc((void**)&f->d_map[i], map_bytes));
-		ABB_CUDA(cudaMemsetAsync(f->d_map[i], 0, map_bytes, f->stream));
 		ABB_CUDA(cudaMalloc((void**)&f->d_tags2[i], f->tag_slots * sizeof(unsigned long long)));
 		ABB_CUDA(cudaMemsetAsync(f->d_tags2[i], 0, f->tag_slots * sizeof(unsigned long long), f->stream));
 	}
@@ -142,6 +143,45 @@ static int ensure_workspace(abb_filter* f)
 			__VA_ARGS__;                  \
 		}                                 \
 	} while (0)
+
+/** While the insert runs, the two conflict maps are pinned in L2 (persisting access-policy window on the filter's stream)
+ *  and everything else -- the random counter sectors, the hashes -- is treated as streaming, so that 30-60 MB of counter
+ *  lines per window cannot push the maps out (ncu, round 2: without this 57 % of the map atomics missed L2 and the kernel
+ *  moved 3x the algorithmic DRAM bytes).  ABB_L2_PERSIST=0 switches it off (tuning). */
+static void set_l2_policy(abb_filter* f, bool on)
+{
+	static int enabled = -1;
+	if (enabled < 0) {
+		const char* e = getenv("ABB_L2_PERSIST");
+		enabled = e ? atoi(e) : 1;
+	}
+	if (!enabled)
+		return;
+	cudaStreamAttrValue attr;
+	memset(&attr, 0, sizeof attr);
+	if (on) {
+		int max_persist = 0, max_window = 0;
+		cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, f->device);
+		cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, f->device);
+		const size_t bytes = 2 * std::max<size_t>(f->map_entries / 4, 256);
+		if (max_persist <= 0 || max_window <= 0)
+			return;
+		cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>(bytes, (size_t)max_persist));
+		attr.accessPolicyWindow.base_ptr = f->d_map[0];
+		attr.accessPolicyWindow.num_bytes = std::min<size_t>(bytes, (size_t)max_window);
+		attr.accessPolicyWindow.hitRatio = std::min(1.0f, (float)max_persist / (float)bytes);
+		attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+		attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+	} else {
+		attr.accessPolicyWindow.num_bytes = 0; // no window
+		attr.accessPolicyWindow.hitProp = cudaAccessPropertyNormal;
+		attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+	}
+	cudaStreamSetAttribute(f->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+	if (!on)
+		cudaCtxResetPersistingL2Cache(); // hand the carve-out back to pass 2
+	cudaGetLastError(); // best effort: a device without the feature runs without the hint
+}
 
 /** cooperative launch of the persistent window kernel with as many CTAs as fit on the device */
 template <int KIND, bool LITERAL, int MAXH>
@@ -199,12 +239,18 @@ static int ordered_insert(abb_filter* f, const uint64_t* d_hashes, const uint8_t
 	a.drain_age = a.age_off / 3 * 2;
 	a.ctl = reinterpret_cast<InsertCtl*>(f->d_ctl);
 	a.stats = f->d_stats;
+	a.dbg = getenv("ABB_DBG") ? (unsigned)atoi(getenv("ABB_DBG")) : 0u;
 	uint64_t* sorted = f->d_carry + 2 * cap;
 	// both tag tables and the control block start clean (the maps are left clean by every call)
 	ABB_CUDA(cudaMemsetAsync(f->d_ctl, 0, sizeof(InsertCtl), st));
 	for (int i = 0; i < 2; ++i)
 		ABB_CUDA(cudaMemsetAsync(f->d_tags2[i], 0, f->tag_slots * sizeof(unsigned long long), st));
 	const bool counting = f->kind == ABB_COUNTING;
+	set_l2_policy(f, true);
+	struct PolicyGuard {
+		abb_filter* f;
+		~PolicyGuard() { set_l2_policy(f, false); }
+	} policy_guard{ f };
 	while (a.w_begin < a.n_windows) {
 		const bool timed = f->profile && f->prof_used + 2 <= f->prof_ev.size();
 		if (timed)
@@ -760,8 +806,7 @@ int abb_filter_destroy(abb_filter* f)
 	cudaFree(f->d_care);
 	cudaFree(f->d_tags2[0]);
 	cudaFree(f->d_tags2[1]);
-	cudaFree(f->d_map[0]);
-	cudaFree(f->d_map[1]);
+	cudaFree(f->d_map[0]); // holds both maps
 	cudaFree(f->d_carry);
 	cudaFree(f->d_slotbits);
 	cudaFree(f->d_ctl);

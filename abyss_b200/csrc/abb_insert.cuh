@@ -449,6 +449,8 @@ struct InsertArgs {
 	uint64_t* carry[2];
 	InsertCtl* ctl;
 	unsigned long long* stats;
+	unsigned dbg; // ABB_DBG what-if switches for timing experiments (results are WRONG when set): 1 no marks, 2 no counter traffic,
+	              // 4 no map clear, 8 no carried reservations, 16 no grid barriers
 };
 
 ABB_D unsigned tag_mask_for(unsigned n_carried, unsigned H, unsigned cap)
@@ -470,7 +472,7 @@ ABB_D unsigned tag_mask_for(unsigned n_carried, unsigned H, unsigned cap)
  * pending slots need the serial drain.
  */
 template <int KIND, bool LITERAL, int MAXH>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 k_insert_windows(const InsertArgs a)
 {
 	cg::grid_group grid = cg::this_grid();
@@ -532,44 +534,48 @@ k_insert_windows(const InsertArgs a)
 				continue;
 			}
 			const uint64_t t = id - n_in;
-			if (t < n) {
-				const uint64_t s = w0 + t;
-				if (!a.valid || a.valid[s]) {
-					slot_positions<LITERAL, MAXH>(a.hashes, s, a.cfg, pos);
-					if (KIND == 0) {
-#pragma unroll
-						for (int i = 0; i < MAXH; ++i)
-							if (i < (int)H)
-								v[i] = __ldcg(a.f.data + pos[i]);
-					}
-					unsigned again = 0;
+			// slot w0 + t is applied, slot w1 + t is marked for the next window.  Order of issue: both hashes, the counter
+			// loads and map probes of the first, then the marks of the second (they run in the shadow of the HBM round
+			// trip), then the decision and the stores.
+			const bool do_apply = t < n && (!a.valid || a.valid[w0 + t]);
+			const bool do_mark = t < n_next && (!a.valid || a.valid[w1 + t]);
+			uint64_t pos2[MAXH];
+			if (do_apply)
+				slot_positions<LITERAL, MAXH>(a.hashes, w0 + t, a.cfg, pos);
+			if (do_mark)
+				slot_positions<LITERAL, MAXH>(a.hashes, w1 + t, a.cfg, pos2);
+			unsigned again = 0;
+			if (do_apply) {
+				if (KIND == 0) {
 #pragma unroll
 					for (int i = 0; i < MAXH; ++i)
 						if (i < (int)H)
-							again |= map_get(a.map[in], pos[i]);
-					if (!(again & 2u))
-						apply_alone<KIND, MAXH>(a.f, pos, v, H);
-					else {
-						a.carry[out][atomicAdd(&a.ctl->n_carry[out], 1u)] = s;
-						atomicAdd(&a.stats[0], 1ULL); // slots that did not commit in their own window
-					}
+							v[i] = (a.dbg & 2u) ? 255u : __ldcg(a.f.data + pos[i]);
 				}
-			}
-			if (t < n_next) {
-				const uint64_t s = w1 + t;
-				if (!a.valid || a.valid[s]) {
-					slot_positions<LITERAL, MAXH>(a.hashes, s, a.cfg, pos);
 #pragma unroll
-					for (int i = 0; i < MAXH; ++i)
-						if (i < (int)H)
-							map_mark(a.map[out], pos[i]);
+				for (int i = 0; i < MAXH; ++i)
+					if (i < (int)H)
+						again |= map_get(a.map[in], pos[i]);
+			}
+			if (do_mark && !(a.dbg & 1u)) {
+#pragma unroll
+				for (int i = 0; i < MAXH; ++i)
+					if (i < (int)H)
+						map_mark(a.map[out], pos2[i]);
+			}
+			if (do_apply) {
+				if (!(again & 2u))
+					apply_alone<KIND, MAXH>(a.f, pos, v, H);
+				else {
+					a.carry[out][atomicAdd(&a.ctl->n_carry[out], 1u)] = w0 + t;
+					atomicAdd(&a.stats[0], 1ULL); // slots that did not commit in their own window
 				}
 			}
 		}
 		for (uint64_t i = gtid; i <= old_mask_out; i += T) // the tag table of window w - 1
 			a.tags[out][i] = 0;
-		__threadfence();
-		grid.sync();
+		if (!(a.dbg & 16u))
+			grid.sync(); // (a grid barrier orders memory itself)
 		// ---- phase B
 		const unsigned n_out = a.ctl->n_carry[out];
 		const bool stop = n_out > kCarryLanes || a.ctl->old_flag != 0;
@@ -577,11 +583,12 @@ k_insert_windows(const InsertArgs a)
 		{
 			uint4* mw = reinterpret_cast<uint4*>(a.map[in].w);
 			const uint64_t words4 = (a.map[in].mask + 1) / 64; // 16 entries per word, 4 words per uint4
-			for (uint64_t i = gtid; i < words4; i += T)
-				mw[i] = make_uint4(0, 0, 0, 0);
+			if (!(a.dbg & 4u))
+				for (uint64_t i = gtid; i < words4; i += T)
+					mw[i] = make_uint4(0, 0, 0, 0);
 		}
 		const unsigned new_mask = tag_mask_for(n_out, H, a.tag_cap);
-		if (!stop && !last) {
+		if (!stop && !last && !(a.dbg & 8u)) {
 			const TagTable tnext = { a.tags[out], new_mask };
 			for (uint64_t i = gtid; i < n_out; i += T) {
 				const uint64_t s = a.carry[out][i];
@@ -600,8 +607,8 @@ k_insert_windows(const InsertArgs a)
 			a.ctl->tag_mask[out] = (!stop && !last) ? new_mask : 0u;
 			a.ctl->resume = w + 1;
 		}
-		__threadfence();
-		grid.sync();
+		if (!(a.dbg & 16u))
+			grid.sync();
 		if (stop)
 			return;
 	}
