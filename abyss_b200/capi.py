@@ -41,6 +41,12 @@ class AssemblyParams(C.Structure):
     _fields_ = [("trim", C.c_uint), ("verbose", C.c_uint), ("read_log", C.c_uint), ("reserved", C.c_uint)]
 
 
+class TraceRow(C.Structure):
+    _fields_ = [("contig_id", C.c_uint64), ("seed_read", C.c_uint64), ("length", C.c_uint32), ("seed_pos", C.c_uint32),
+                ("left_n", C.c_uint32), ("right_n", C.c_uint32), ("left_code", C.c_uint8), ("right_code", C.c_uint8),
+                ("redundant", C.c_uint8), ("pad", C.c_uint8)]
+
+
 class AssemblyStats(C.Structure):
     _fields_ = [("rounds", C.c_uint64), ("speculated_reads", C.c_uint64), ("wasted_reads", C.c_uint64),
                 ("candidates", C.c_uint64), ("contigs_tried", C.c_uint64), ("launches", C.c_uint64),
@@ -91,6 +97,7 @@ SIGNATURES = {
     "abb_filter_allgather": (C.c_int, [_vp, _vp]),
     "abb_comm_allgather_bytes": (C.c_int, [_vp, _vp, C.c_uint64, _vp]),
     "abb_comm_allreduce_max_u8": (C.c_int, [_vp, _vp, C.c_uint64, _vp]),
+    "abb_comm_exchange_bytes": (C.c_int, [_vp, _vp, C.c_uint64, _vp, _u64p, _u64p, _vp]),
     "abb_filter_device_ptr": (_vp, [_vp, C.c_int]),
     "abb_filter_download": (C.c_int, [_vp, C.c_int, _vp, C.c_uint64]),
     "abb_filter_upload": (C.c_int, [_vp, C.c_int, _vp, C.c_uint64]),
@@ -106,6 +113,8 @@ SIGNATURES = {
     "abb_assembler_set_codes": (C.c_int, [_vp, _vp, C.c_uint64]),
     "abb_assembler_counters": (C.c_int, [_vp, C.POINTER(AssemblyCounters)]),
     "abb_assembler_read_results": (C.c_int, [_vp, C.POINTER(_u8p), _u64p]),
+    "abb_assembler_set_comm": (C.c_int, [_vp, _vp]),
+    "abb_assembler_trace": (C.c_int, [_vp, C.POINTER(C.POINTER(TraceRow)), _u64p]),
     "abb_assembler_assembled_filter": (_vp, [_vp]),
     "abb_filter_insert_stats": (C.c_int, [_vp, C.POINTER(InsertStats), C.c_int]),
     "abb_filter_set_window": (C.c_int, [_vp, C.c_uint64]),
@@ -396,6 +405,11 @@ class Assembler:
 
     def reset(self):
         check(self._lib.abb_assembler_reset(self._h))
+
+    def set_comm(self, comm):
+        """multi-GPU pass 2: shard classification, candidate scans and tile production over the ranks of `comm`"""
+        self._comm = comm
+        check(self._lib.abb_assembler_set_comm(self._h, comm.handle if comm is not None else None))
 
     def classify_dev(self, d_bases_ptr: int, d_offs_ptr: int, n_reads: int, d_codes_ptr: int):
         check(self._lib.abb_assembler_classify_dev(self._h, _vp(d_bases_ptr), _vp(d_offs_ptr), n_reads, _vp(d_codes_ptr)))

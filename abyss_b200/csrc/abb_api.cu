@@ -74,9 +74,8 @@ static FilterView view_of(const abb_filter* f)
 /** conflict-map size: 2^26 two-bit entries (16 MiB per map; both maps are pinned in L2 while the insert runs,
  *  set_l2_policy); with the default window of 2^17 slots 3.2 % of the slots see an alias and are carried.  Exact (no
  *  aliases) for filters of up to 2^26 positions.  ABB_MAP_LOG2 overrides (tuning). */
-static uint64_t map_entries_for(uint64_t filter_size)
+static uint64_t map_entries_for(uint64_t filter_size, unsigned lg = 26)
 {
-	unsigned lg = 26;
 	if (const char* e = getenv("ABB_MAP_LOG2")) {
 		const int v = atoi(e);
 		if (v >= 10 && v <= 32)
@@ -95,7 +94,8 @@ static unsigned age_windows_for(uint64_t window)
 /** make sure the ordered-insert workspace exists for the current window size and hash count */
 static int ensure_workspace(abb_filter* f)
 {
-	if (f->d_carry && f->ws_window == f->window && f->ws_H == f->H)
+	const uint64_t want_entries = map_entries_for(f->size, f->map_log2 ? f->map_log2 : 26);
+	if (f->d_carry && f->ws_window == f->window && f->ws_H == f->H && f->map_entries == want_entries)
 		return ABB_OK;
 	cudaFree(f->d_map[0]); // one allocation holds both maps (one L2 access-policy window covers them)
 	for (int i = 0; i < 2; ++i) {
@@ -107,7 +107,7 @@ static int ensure_workspace(abb_filter* f)
 	cudaFree(f->d_slotbits);
 	f->d_carry = nullptr;
 	f->d_slotbits = nullptr;
-	f->map_entries = map_entries_for(f->size);
+	f->map_entries = want_entries;
 	const size_t map_bytes = std::max<size_t>(f->map_entries / 4, 256);
 	// at most kCarryLanes carried slots reserve H positions each; load factor <= 1/8.  Only a prefix sized to the
 	// carried slots of a window is in use (tag_mask_for)
@@ -489,6 +489,10 @@ struct NcclApi {
 	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
 	ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
 	ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*GroupStart)() = nullptr;
+	ncclResult_t (*GroupEnd)() = nullptr;
 	const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 static NcclApi g_nccl;
@@ -519,6 +523,10 @@ static int load_nccl()
 	ABB_NCCL_SYM(CommDestroy, "ncclCommDestroy");
 	ABB_NCCL_SYM(AllReduce, "ncclAllReduce");
 	ABB_NCCL_SYM(AllGather, "ncclAllGather");
+	ABB_NCCL_SYM(Send, "ncclSend");
+	ABB_NCCL_SYM(Recv, "ncclRecv");
+	ABB_NCCL_SYM(GroupStart, "ncclGroupStart");
+	ABB_NCCL_SYM(GroupEnd, "ncclGroupEnd");
 	ABB_NCCL_SYM(GetErrorString, "ncclGetErrorString");
 #undef ABB_NCCL_SYM
 	g_nccl.h = h;
@@ -548,7 +556,7 @@ static uint64_t shard_chunk(uint64_t size, unsigned world) { return ((size + wor
 /** the window of the sharded pipeline: per-rank conflict-map load like the single-GPU window */
 static uint64_t sharded_window(const abb_filter* f, unsigned world)
 {
-	uint64_t w = f->window * world;
+	uint64_t w = 2 * f->window * world; // 2^18 slots per rank: the per-rank conflict-map load of the single-GPU window, twice
 	if (const char* e = getenv("ABB_SHARD_WINDOW"))
 		w = strtoull(e, nullptr, 10);
 	return std::min<uint64_t>(std::max<uint64_t>(w, 32), 1ULL << 21);
@@ -560,9 +568,11 @@ static int sharded_ordered_insert(abb_filter* f, abb_comm* c, const uint64_t* d_
 		return ABB_OK;
 	const uint64_t user_window = f->window;
 	f->window = sharded_window(f, (unsigned)c->world);
+	f->map_log2 = 27; // each rank marks window * H / world positions: 2^20 at the default window
 	int rc = ensure_workspace(f);
 	const uint64_t W = f->window;
 	f->window = user_window;
+	f->map_log2 = 0;
 	ABB_CHECK(rc);
 	ABB_CHECK(f->sh_buf.reserve(2 * (W + kCarryLanes) + 64));
 	cudaStream_t st = f->stream;
@@ -648,6 +658,11 @@ static int sharded_ordered_insert(abb_filter* f, abb_comm* c, const uint64_t* d_
 		return ABB_OK;
 	};
 	f->prof_stride = f->prof_ev.empty() ? 1 : std::max<uint64_t>(1, (2 * n_windows + f->prof_ev.size() - 1) / f->prof_ev.size());
+	set_l2_policy(f, true);
+	struct PolicyGuard {
+		abb_filter* f;
+		~PolicyGuard() { set_l2_policy(f, false); }
+	} policy_guard{ f };
 	ABB_CHECK(step(0, 0, 0, (unsigned)std::min<uint64_t>(W, n_slots))); // marks of window 0
 	p = 1 - p; // the marks went to maps[1 - p]
 	for (uint64_t w = 0; w < n_windows; ++w) {
@@ -1059,6 +1074,27 @@ int abb_comm_allgather_bytes(abb_comm* c, void* d_buf, uint64_t bytes_per_rank, 
 	ABB_CUDA(cudaSetDevice(c->device));
 	ABB_NCCL(g_nccl.AllGather((const uint8_t*)d_buf + (uint64_t)c->rank * bytes_per_rank, d_buf, bytes_per_rank, ncclUint8, c->comm,
 	                          (cudaStream_t)cuda_stream));
+	return ABB_OK;
+}
+
+int abb_comm_exchange_bytes(abb_comm* c, const void* d_send, uint64_t send_bytes, void* d_recv_base, const uint64_t* recv_offsets,
+                            const uint64_t* recv_bytes, void* cuda_stream)
+{
+	ABB_REQUIRE(c && recv_offsets && recv_bytes, "NULL argument");
+	if (c->world == 1)
+		return ABB_OK;
+	ABB_CUDA(cudaSetDevice(c->device));
+	cudaStream_t st = (cudaStream_t)cuda_stream;
+	ABB_NCCL(g_nccl.GroupStart());
+	for (int r = 0; r < c->world; ++r) {
+		if (r == c->rank)
+			continue;
+		if (send_bytes)
+			ABB_NCCL(g_nccl.Send(d_send, send_bytes, ncclUint8, r, c->comm, st));
+		if (recv_bytes[r])
+			ABB_NCCL(g_nccl.Recv((uint8_t*)d_recv_base + recv_offsets[r], recv_bytes[r], ncclUint8, r, c->comm, st));
+	}
+	ABB_NCCL(g_nccl.GroupEnd());
 	return ABB_OK;
 }
 

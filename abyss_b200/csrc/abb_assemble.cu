@@ -336,6 +336,7 @@ struct ContigRec {
 	unsigned psize;
 	unsigned char left, right, flags, pad1; // flags: 1 pushed_front, 2 pushed_back, 4 popped_front, 8 popped_back
 	unsigned long long front_h, back_h;     // canonical hashes of trimmed-off end vertices (flags 4 / 8)
+	unsigned left_n, right_n;               // vertices added by the two extensions (-T trace)
 };
 
 struct DevEmit {
@@ -361,6 +362,8 @@ struct DevEmit {
 				r.pad1 = 0;
 				r.front_h = o.front_h;
 				r.back_h = o.back_h;
+				r.left_n = o.left_n;
+				r.right_n = o.right_n;
 				recs[idx] = r;
 			}
 		}
@@ -543,11 +546,13 @@ __global__ void __launch_bounds__(256)
 k_find_markers(const uint64_t* __restrict__ h0, const uint8_t* __restrict__ valid, const uint64_t* __restrict__ slot_offs,
                uint64_t n_reads, uint64_t n_slots, WalkCfg w, const __grid_constant__ HashCfg cfg, unsigned long long* mset,
                unsigned mset_mask, unsigned long long* __restrict__ out /* packed (read << 24 | pos) */, unsigned* n_out,
-               unsigned out_cap)
+               unsigned out_cap, unsigned world, unsigned rank)
 {
 	for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n_slots; s += (uint64_t)gridDim.x * blockDim.x) {
 		const uint64_t h = h0[s];
 		if (!is_marker(h) || !valid[s])
+			continue;
+		if (world > 1 && (unsigned)((h >> 8) % world) != rank) // several GPUs: each marker is tiled by exactly one rank
 			continue;
 		bool solid = true;
 		for (unsigned i = 0; i < cfg.H; ++i)
@@ -656,6 +661,43 @@ k_make_tiles(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ off
 					break; // palindromic marker: the same (key, class) twice, keep the first
 			}
 		}
+	}
+}
+
+/** tiles [first, first + n) as produced by THIS rank -> a copy whose pool pointers are offsets from pool_base (what
+ *  travels to the other ranks) */
+__global__ void __launch_bounds__(256)
+k_export_tiles(const TileRec* __restrict__ recs, unsigned first, unsigned n, const uint8_t* pool_base, TileRec* __restrict__ out)
+{
+	const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n)
+		return;
+	TileRec t = recs[first + i];
+	t.bases = reinterpret_cast<uint8_t*>(reinterpret_cast<const uint8_t*>(t.bases) - pool_base);
+	t.hashes = reinterpret_cast<uint64_t*>(reinterpret_cast<const uint8_t*>(t.hashes) - pool_base);
+	t.next = 0;
+	out[i] = t;
+}
+
+/** received tiles [first, first + n) (pool offsets relative to the sender's segment, which now lives at seg_base):
+ *  rebase the pointers and enter them into the (marker, class) table */
+__global__ void __launch_bounds__(256)
+k_import_tiles(TileRec* __restrict__ recs, unsigned first, unsigned n, uint8_t* seg_base, unsigned* __restrict__ tab, unsigned mask)
+{
+	const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n)
+		return;
+	TileRec* t = recs + first + i;
+	t->bases = seg_base + reinterpret_cast<uintptr_t>(t->bases);
+	t->hashes = reinterpret_cast<uint64_t*>(seg_base + reinterpret_cast<uintptr_t>(t->hashes));
+	t->next = 0;
+	for (uint64_t s = tile_slot(t->key, t->cls, mask);; s = (s + 1) & mask) {
+		const unsigned old = atomicCAS(tab + s, 0u, first + i + 1);
+		if (old == 0u)
+			break;
+		const TileRec* o = recs + (old - 1);
+		if (o->key == t->key && o->cls == t->cls)
+			break;
 	}
 }
 
@@ -1058,6 +1100,8 @@ struct abb_assembler {
 	uint8_t* d_mpos = nullptr;
 	const uint8_t* ext_codes = nullptr; // classification supplied by the caller for the next batch (device)
 	uint64_t ext_n = 0;
+	abb_comm* comm = nullptr;           // multi-GPU: classification, candidate scans and tile production are sharded over it
+	DevBuf<uint8_t> gather;             // all-gather staging (world x padded slice)
 	const uint8_t* cur_bases = nullptr; // device reads of the batch being processed
 	const uint64_t* cur_offs = nullptr;
 
@@ -1093,6 +1137,7 @@ struct abb_assembler {
 	unsigned long long* d_marker_set = nullptr;
 	unsigned marker_set_mask = 0;
 	DevBuf<unsigned long long> new_markers, rep_tab;
+	DevBuf<TileRec> tile_export;
 	DevBuf<uint8_t> stage_bases, rep_flag;
 	DevBuf<uint64_t> stage_hashes;
 	uint64_t st_markers = 0, st_tiles = 0, st_fallbacks = 0;
@@ -1105,6 +1150,7 @@ struct abb_assembler {
 	std::vector<abb_contig> out_contigs;
 	std::vector<char> out_seqs;
 	std::vector<uint8_t> out_codes;
+	std::vector<abb_trace_row> out_trace; // one row per contig handed to outputContig (params.reserved & 1)
 	// statistics
 	uint64_t st_iterations = 0, st_speculated = 0, st_wasted = 0, st_launches = 0, st_candidates = 0, st_contigs_tried = 0;
 	float ms_classify = 0, ms_visited = 0, ms_extend = 0, ms_replay = 0;
@@ -1210,6 +1256,29 @@ int h2d(DevBuf<T>& d, const std::vector<T>& h, cudaStream_t s)
 	return ABB_OK;
 }
 
+/** rank r holds `mine` = n_r bytes (n_r = its slice of n_total split as [r*n/w, (r+1)*n/w)); afterwards `all` holds the
+ *  n_total bytes of every rank's slice in rank order.  One ncclAllGather over slices padded to the longest. */
+int allgather_slices(abb_assembler* a, const uint8_t* mine, uint64_t n_total, uint8_t* all)
+{
+	const unsigned world = (unsigned)abb_comm_world(a->comm), rank = (unsigned)abb_comm_rank(a->comm);
+	cudaStream_t st = a->stream;
+	uint64_t mx = 0;
+	for (unsigned r = 0; r < world; ++r)
+		mx = std::max<uint64_t>(mx, (r + 1) * n_total / world - r * n_total / world);
+	mx = (mx + 15) & ~15ULL;
+	ABB_CHECK(a->gather.reserve(world * mx));
+	const uint64_t lo = rank * n_total / world, up = (rank + 1) * n_total / world;
+	if (up > lo)
+		ABB_CUDA(cudaMemcpyAsync(a->gather.p + rank * mx, mine, up - lo, cudaMemcpyDeviceToDevice, st));
+	ABB_CHECK(abb_comm_allgather_bytes(a->comm, a->gather.p, mx, st));
+	for (unsigned r = 0; r < world; ++r) {
+		const uint64_t l = r * n_total / world, u = (r + 1) * n_total / world;
+		if (u > l)
+			ABB_CUDA(cudaMemcpyAsync(all + l, a->gather.p + r * mx, u - l, cudaMemcpyDeviceToDevice, st));
+	}
+	return ABB_OK;
+}
+
 TileView tile_view(const abb_assembler* a, bool on)
 {
 	TileView v = { nullptr, nullptr, 0 };
@@ -1256,6 +1325,56 @@ int ensure_tile_store(abb_assembler* a)
 	return ABB_OK;
 }
 
+/** several GPUs: the tiles this rank has just produced ([n0, n1) of the store, pool bytes [p0, p1)) go to every other
+ *  rank and theirs are appended here; afterwards every rank holds all tiles (indices differ between ranks, content not) */
+int exchange_tiles(abb_assembler* a, unsigned n0, unsigned n1, unsigned long long p0, unsigned long long p1)
+{
+	cudaStream_t st = a->stream;
+	const unsigned world = (unsigned)abb_comm_world(a->comm), rank = (unsigned)abb_comm_rank(a->comm);
+	// 1. how much does everybody have?
+	ABB_CHECK(a->gather.reserve(world * 16 + 16));
+	unsigned long long mine[2] = { n1 - n0, p1 - p0 };
+	ABB_CUDA(cudaMemcpyAsync(a->gather.p + rank * 16, mine, 16, cudaMemcpyHostToDevice, st));
+	ABB_CHECK(abb_comm_allgather_bytes(a->comm, a->gather.p, 16, st));
+	std::vector<unsigned long long> all(2 * world);
+	ABB_CUDA(cudaMemcpyAsync(all.data(), a->gather.p, world * 16, cudaMemcpyDeviceToHost, st));
+	ABB_CUDA(cudaStreamSynchronize(st));
+	// 2. where the others' tiles and pool segments land in my store
+	std::vector<uint64_t> rec_off(world, 0), rec_bytes(world, 0), pool_off(world, 0), pool_bytes(world, 0);
+	unsigned long long nt = n1, pt = (p1 + 15) & ~15ULL;
+	for (unsigned r = 0; r < world; ++r) {
+		if (r == rank)
+			continue;
+		rec_off[r] = (uint64_t)nt * sizeof(TileRec);
+		rec_bytes[r] = all[2 * r] * sizeof(TileRec);
+		pool_off[r] = pt;
+		pool_bytes[r] = all[2 * r + 1];
+		nt += all[2 * r];
+		pt += (all[2 * r + 1] + 15) & ~15ULL;
+	}
+	ABB_REQUIRE(nt <= a->tile_cap && pt <= a->tile_pool_size, "tile store too small for the merged tiles (%llu tiles, %llu pool bytes)", nt, pt);
+	// 3. my records with pool-relative pointers, then the two exchanges
+	ABB_CHECK(a->tile_export.reserve((size_t)(n1 - n0) + 1));
+	if (n1 > n0)
+		k_export_tiles<<<blocks_for(n1 - n0, 256), 256, 0, st>>>(a->d_tiles, n0, n1 - n0, a->d_tile_pool + p0, a->tile_export.p);
+	ABB_CUDA(cudaGetLastError());
+	ABB_CHECK(abb_comm_exchange_bytes(a->comm, a->tile_export.p, (uint64_t)(n1 - n0) * sizeof(TileRec), a->d_tiles, rec_off.data(), rec_bytes.data(), st));
+	ABB_CHECK(abb_comm_exchange_bytes(a->comm, a->d_tile_pool + p0, p1 - p0, a->d_tile_pool, pool_off.data(), pool_bytes.data(), st));
+	for (unsigned r = 0; r < world; ++r) {
+		if (r == rank || all[2 * r] == 0)
+			continue;
+		const unsigned first = (unsigned)(rec_off[r] / sizeof(TileRec)), n = (unsigned)all[2 * r];
+		k_import_tiles<<<blocks_for(n, 256), 256, 0, st>>>(a->d_tiles, first, n, a->d_tile_pool + pool_off[r], a->d_tile_tab, a->tile_tab_mask);
+	}
+	ABB_CUDA(cudaGetLastError());
+	const unsigned nt32 = (unsigned)nt;
+	ABB_CUDA(cudaMemcpyAsync(a->d_tile_n, &nt32, sizeof nt32, cudaMemcpyHostToDevice, st));
+	ABB_CUDA(cudaMemcpyAsync(a->d_tile_pool_top, &pt, sizeof pt, cudaMemcpyHostToDevice, st));
+	ABB_CUDA(cudaStreamSynchronize(st));
+	a->st_launches += 2 + world;
+	return ABB_OK;
+}
+
 /** markers among this batch's k-mers that have no tiles yet get their four tiles */
 int produce_tiles(abb_assembler* a, uint64_t n_reads, uint64_t n_slots)
 {
@@ -1266,40 +1385,57 @@ int produce_tiles(abb_assembler* a, uint64_t n_reads, uint64_t n_slots)
 	abb_filter* f = a->solid;
 	cudaStream_t st = a->stream;
 	const WalkCfg w = walk_cfg(a);
+	const unsigned world = a->comm ? (unsigned)abb_comm_world(a->comm) : 1u, rank = a->comm ? (unsigned)abb_comm_rank(a->comm) : 0u;
 	const unsigned out_cap = (unsigned)std::min<uint64_t>(n_slots / (kMarkerMask + 1) * 2 + 4096, a->marker_set_mask / 2 + 1);
 	ABB_CHECK(a->new_markers.reserve(out_cap));
 	ABB_CUDA(cudaMemsetAsync(a->d_tile_n + 1, 0, 2 * sizeof(unsigned), st));
 	k_find_markers<<<148 * 16, 256, 0, st>>>(a->h0.p, a->valid.p, a->slot_offs.p, n_reads, n_slots, w, f->cfg, a->d_marker_set,
-	                                         a->marker_set_mask, a->new_markers.p, a->d_tile_n + 2, out_cap);
+	                                         a->marker_set_mask, a->new_markers.p, a->d_tile_n + 2, out_cap, world, rank);
 	ABB_CUDA(cudaGetLastError());
-	unsigned nm = 0;
+	unsigned nm = 0, n0 = 0;
+	unsigned long long p0 = 0;
 	ABB_CUDA(cudaMemcpyAsync(&nm, a->d_tile_n + 2, sizeof nm, cudaMemcpyDeviceToHost, st));
+	ABB_CUDA(cudaMemcpyAsync(&n0, a->d_tile_n, sizeof n0, cudaMemcpyDeviceToHost, st));
+	ABB_CUDA(cudaMemcpyAsync(&p0, a->d_tile_pool_top, sizeof p0, cudaMemcpyDeviceToHost, st));
 	ABB_CUDA(cudaStreamSynchronize(st));
 	nm = std::min(nm, out_cap);
+	n0 = std::min(n0, a->tile_cap);
 	a->st_launches += 1;
-	if (nm == 0) {
+	if (nm == 0 && world == 1) {
 		tt.stop();
 		return ABB_OK;
 	}
-	int sms = 148;
-	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, f->device);
-	const unsigned grid = (unsigned)std::min<uint64_t>(blocks_for((uint64_t)nm * 4, kWalkWarps), (uint64_t)sms * 4);
-	const unsigned warps = grid * kWalkWarps;
-	ABB_CHECK(ensure_scratch(a, warps));
-	ABB_CHECK(a->stage_bases.reserve((size_t)warps * kTileCap));
-	ABB_CHECK(a->stage_hashes.reserve((size_t)warps * kTileCap));
-	TileStore ts = { a->d_tiles, a->d_tile_tab, a->tile_tab_mask, a->tile_cap, a->d_tile_n, a->d_tile_pool, a->tile_pool_size,
-		             a->d_tile_pool_top };
-	ABB_DISPATCH_KW(a->kw, (k_make_tiles<KW><<<grid, kWalkWarps * 32, 0, st>>>(a->cur_bases, a->cur_offs, a->new_markers.p, nm,
-	                                                                          a->d_tile_n + 1, w, f->cfg, a->frames.p, a->look.p,
-	                                                                          a->stage_bases.p, a->stage_hashes.p, ts)));
-	ABB_CUDA(cudaGetLastError());
-	a->st_launches += 1;
+	if (nm) {
+		int sms = 148;
+		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, f->device);
+		const unsigned grid = (unsigned)std::min<uint64_t>(blocks_for((uint64_t)nm * 4, kWalkWarps), (uint64_t)sms * 4);
+		const unsigned warps = grid * kWalkWarps;
+		ABB_CHECK(ensure_scratch(a, warps));
+		ABB_CHECK(a->stage_bases.reserve((size_t)warps * kTileCap));
+		ABB_CHECK(a->stage_hashes.reserve((size_t)warps * kTileCap));
+		TileStore ts = { a->d_tiles, a->d_tile_tab, a->tile_tab_mask, a->tile_cap, a->d_tile_n, a->d_tile_pool, a->tile_pool_size,
+			             a->d_tile_pool_top };
+		ABB_DISPATCH_KW(a->kw, (k_make_tiles<KW><<<grid, kWalkWarps * 32, 0, st>>>(a->cur_bases, a->cur_offs, a->new_markers.p, nm,
+		                                                                          a->d_tile_n + 1, w, f->cfg, a->frames.p, a->look.p,
+		                                                                          a->stage_bases.p, a->stage_hashes.p, ts)));
+		ABB_CUDA(cudaGetLastError());
+		a->st_launches += 1;
+	}
 	unsigned nt = 0;
+	unsigned long long p1 = 0;
 	ABB_CUDA(cudaMemcpyAsync(&nt, a->d_tile_n, sizeof nt, cudaMemcpyDeviceToHost, st));
+	ABB_CUDA(cudaMemcpyAsync(&p1, a->d_tile_pool_top, sizeof p1, cudaMemcpyDeviceToHost, st));
 	ABB_CUDA(cudaStreamSynchronize(st));
+	nt = std::min(nt, a->tile_cap);
+	p1 = std::min(p1, a->tile_pool_size);
 	a->st_markers += nm;
-	a->st_tiles = std::min(nt, a->tile_cap);
+	a->st_tiles = nt;
+	if (world > 1) {
+		ABB_CHECK(exchange_tiles(a, n0, nt, p0, p1));
+		ABB_CUDA(cudaMemcpyAsync(&nt, a->d_tile_n, sizeof nt, cudaMemcpyDeviceToHost, st));
+		ABB_CUDA(cudaStreamSynchronize(st));
+		a->st_tiles = nt;
+	}
 	k_link_tiles<<<148 * 8, 256, 0, st>>>(a->d_tiles, (unsigned)a->st_tiles, a->d_tile_tab, a->tile_tab_mask);
 	ABB_CUDA(cudaGetLastError());
 	a->st_launches += 1;
@@ -1462,10 +1598,18 @@ int speculate_round(abb_assembler* a, const std::vector<unsigned>& cand, size_t*
 	while (pos < ncand && spec.size() < a->spec_target) {
 		const unsigned n = (unsigned)std::min(chunk, ncand - pos);
 		ABB_CHECK(a->vis.reserve(n));
-		k_visited<<<blocks_for((uint64_t)n * 32, 256), 256, 0, st>>>(a->cand.p, (unsigned)pos, n, a->slot_offs.p, a->h0.p, f->cfg,
-		                                                            a->assembled->d_data, a->vis.p);
-		ABB_CUDA(cudaGetLastError());
-		++a->st_launches;
+		{
+			// pure per candidate against the CURRENT assembled filter (identical on every rank: the replay is replicated)
+			const unsigned world = a->comm ? (unsigned)abb_comm_world(a->comm) : 1u, rank = a->comm ? (unsigned)abb_comm_rank(a->comm) : 0u;
+			const unsigned vlo = (unsigned)((uint64_t)rank * n / world), vup = (unsigned)((uint64_t)(rank + 1) * n / world);
+			if (vup > vlo)
+				k_visited<<<blocks_for((uint64_t)(vup - vlo) * 32, 256), 256, 0, st>>>(a->cand.p, (unsigned)pos + vlo, vup - vlo, a->slot_offs.p, a->h0.p,
+				                                                                      f->cfg, a->assembled->d_data, a->vis.p + vlo);
+			ABB_CUDA(cudaGetLastError());
+			++a->st_launches;
+			if (world > 1)
+				ABB_CHECK(allgather_slices(a, a->vis.p + vlo, n, a->vis.p));
+		}
 		std::vector<uint8_t> vis(n);
 		ABB_CUDA(cudaMemcpyAsync(vis.data(), a->vis.p, n, cudaMemcpyDeviceToHost, st));
 		ABB_CUDA(cudaStreamSynchronize(st));
@@ -1691,6 +1835,20 @@ int speculate_round(abb_assembler* a, const std::vector<unsigned>& cand, size_t*
 			continue;
 		}
 		for (unsigned c = spec_cbeg[s]; c < spec_cbeg[s + 1]; ++c) {
+			if (a->params.reserved & 1u) { // ContigRecord (bloom-dbg.h:186-254): every contig that reached outputContig
+				abb_trace_row tr;
+				tr.contig_id = caccept[c] ? a->counters.contig_id : ~0ULL;
+				tr.seed_read = a->reads_seen + spec[s];
+				tr.length = clen[c];
+				tr.seed_pos = recs[c].seed_pos;
+				tr.left_n = recs[c].left_n;
+				tr.right_n = recs[c].right_n;
+				tr.left_code = recs[c].left;
+				tr.right_code = recs[c].right;
+				tr.redundant = caccept[c] ? 0 : 1;
+				tr.pad = 0;
+				a->out_trace.push_back(tr);
+			}
 			if (!caccept[c])
 				continue;
 			abb_contig oc;
@@ -1816,6 +1974,8 @@ int abb_assembler_destroy(abb_assembler* a)
 	cudaFree(a->d_tile_pool_top);
 	cudaFree(a->d_marker_set);
 	a->rep_off.release();
+	a->gather.release();
+	a->tile_export.release();
 	a->seg_contig.release(); a->seg_len.release(); a->seg_beg.release(); a->seg_slot.release();
 	a->new_markers.release(); a->rep_tab.release(); a->stage_bases.release(); a->rep_flag.release(); a->stage_hashes.release();
 	cudaFree(a->d_arena);
@@ -1850,13 +2010,21 @@ static int hash_and_classify(abb_assembler* a, const uint8_t* d_bases, const uin
 		return ABB_OK;
 	int sms = 148;
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, f->device);
-	const unsigned grid = (unsigned)std::min<uint64_t>(blocks_for(n_reads, kWalkWarps), (uint64_t)sms * 8);
+	// K3a is pure per read: with a communicator every rank classifies its contiguous slice of the batch and the codes
+	// are all-gathered
+	const unsigned world = a->comm ? (unsigned)abb_comm_world(a->comm) : 1u, rank = a->comm ? (unsigned)abb_comm_rank(a->comm) : 0u;
+	const uint64_t lo = rank * n_reads / world, up = (rank + 1) * n_reads / world;
+	const unsigned grid = (unsigned)std::min<uint64_t>(blocks_for(std::max<uint64_t>(up - lo, 1), kWalkWarps), (uint64_t)sms * 8);
 	ABB_CHECK(ensure_scratch(a, grid * kWalkWarps));
 	const WalkCfg w = walk_cfg(a);
-	ABB_DISPATCH_KW(a->kw, (k_classify<KW><<<grid, kWalkWarps * 32, 0, st>>>(d_bases, d_offs, a->slot_offs.p, a->h0.p, a->valid.p, n_reads, w,
-	                                                                        f->cfg, a->look.p, (int)a->params.read_log, a->codes.p)));
+	if (up > lo)
+		ABB_DISPATCH_KW(a->kw, (k_classify<KW><<<grid, kWalkWarps * 32, 0, st>>>(d_bases, d_offs + lo, a->slot_offs.p + lo, a->h0.p, a->valid.p,
+		                                                                        up - lo, w, f->cfg, a->look.p, (int)a->params.read_log,
+		                                                                        a->codes.p + lo)));
 	ABB_CUDA(cudaGetLastError());
 	++a->st_launches;
+	if (world > 1)
+		ABB_CHECK(allgather_slices(a, a->codes.p + lo, n_reads, a->codes.p));
 	return ABB_OK;
 }
 
@@ -1929,6 +2097,7 @@ static int begin_batch(abb_assembler* a, uint64_t n_reads, const abb_contig** co
 	ABB_REQUIRE(a, "NULL assembler");
 	a->out_contigs.clear();
 	a->out_seqs.clear();
+	a->out_trace.clear();
 	a->out_codes.assign(n_reads, RC_SHORTER_THAN_K);
 	if (contigs) *contigs = nullptr;
 	if (n_contigs) *n_contigs = 0;
@@ -2051,6 +2220,21 @@ int abb_assembler_counters(const abb_assembler* a, abb_assembly_counters* out)
 {
 	ABB_REQUIRE(a && out, "NULL argument");
 	*out = a->counters;
+	return ABB_OK;
+}
+
+int abb_assembler_set_comm(abb_assembler* a, abb_comm* comm)
+{
+	ABB_REQUIRE(a, "NULL assembler");
+	a->comm = comm && abb_comm_world(comm) > 1 ? comm : nullptr;
+	return ABB_OK;
+}
+
+int abb_assembler_trace(const abb_assembler* a, const abb_trace_row** rows, uint64_t* n)
+{
+	ABB_REQUIRE(a && rows && n, "NULL argument");
+	*rows = a->out_trace.data();
+	*n = a->out_trace.size();
 	return ABB_OK;
 }
 

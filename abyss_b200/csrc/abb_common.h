@@ -104,6 +104,7 @@ struct abb_filter {
 	uint64_t ws_window = 0;   // window the workspace below was sized for
 	unsigned ws_H = 0;
 	uint64_t map_entries = 0; // two-bit entries per conflict map (power of two)
+	unsigned map_log2 = 0;    // 0 = default size
 	unsigned* d_map[2] = { nullptr, nullptr };
 	unsigned long long* d_tags2[2] = { nullptr, nullptr }; // tag tables of the carried slots (alternating windows)
 	uint64_t tag_slots = 0;

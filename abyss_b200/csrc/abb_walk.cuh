@@ -998,6 +998,7 @@ struct ContigOut {
 	unsigned len;    // bases
 	unsigned psize;  // vertices before trimming (contigPath.size() as isTip sees it)
 	ExtCode left, right;
+	unsigned left_n, right_n; // vertices the two extendPath calls added (ContigRecord left/rightExtensionResult.first)
 	bool tip;        // isTip: not output, but its k-mers still count as assembled for this read
 	bool popped_front, popped_back; // a real path vertex (not a pushed duplicate) was trimmed off that end
 	uint64_t front_h, back_h;       // canonical hashes of the trimmed-off vertices
@@ -1028,6 +1029,8 @@ ABB_HD bool extend_seed(Ctx& c, const Vtx<KW>& seed, PathSet& ps, ContigOut* o)
 	if (!ok || c.failed())
 		return false;
 	o->psize = psize;
+	o->left_n = left.n;
+	o->right_n = right.n;
 	o->tip = is_tip(psize, o->left, o->right, c.trim);
 	o->popped_front = o->popped_back = false;
 	o->front_h = o->back_h = 0;

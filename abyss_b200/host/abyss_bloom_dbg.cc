@@ -19,6 +19,7 @@
 #include <iomanip>
 #include <iostream>
 #include <sstream>
+#include <thread>
 
 #define PROGRAM "abyss-bloom-dbg"
 #define MAX_KMER 192
@@ -45,6 +46,7 @@ struct AssemblyParams {
 	int verbose = 0;
 	std::string outputPath, tracePath;
 	int device = 0; // B200 extension: --device=N
+	std::string devices; // B200 extension: --devices=LIST, several GPUs (one host thread per GPU)
 	uint64_t batchReads = 4000000; // B200 extension: --batch-reads=N
 	bool initialized() const { return bloomSize > 0 && k > 0 && trim != UINT_MAX; }
 	void resetSpacedSeedParams()
@@ -87,6 +89,9 @@ static const char USAGE_MESSAGE[] =
     "      --version                output version information and exit\n"
     "      --read-log=FILE          write outcome of processing each read to FILE\n"
     "      --device=N               CUDA device to use [0]\n"
+    "      --devices=LIST           several GPUs, e.g. 0-7 or 0,2,4: the counting Bloom\n"
+    "                               filter is sharded by position range over them (same\n"
+    "                               output as one GPU), one host thread per GPU\n"
     "      --batch-reads=N          reads per GPU batch [4000000]\n"
     "\n"
     "Spaced seeds (-K, --qr-seed, -s) are accepted by the hashing/insert stage only; -g, -C, -R, -T\n"
@@ -95,7 +100,7 @@ static const char USAGE_MESSAGE[] =
 static AssemblyParams params;
 static ReadOpts ropt;
 
-enum { OPT_HELP = 1, OPT_VERSION, QR_SEED, MIN_KMER_COV, CHECKPOINT, KEEP_CHECKPOINT, CHECKPOINT_PREFIX, READ_LOG, OPT_DEVICE, OPT_BATCH };
+enum { OPT_HELP = 1, OPT_VERSION, QR_SEED, MIN_KMER_COV, CHECKPOINT, KEEP_CHECKPOINT, CHECKPOINT_PREFIX, READ_LOG, OPT_DEVICE, OPT_DEVICES, OPT_BATCH };
 
 static int chastity = 1, trimMasked = 1, illuminaQ = 0;
 static const char shortopts[] = "b:C:g:H:i:j:k:K:o:q:Q:R:s:t:T:v";
@@ -132,6 +137,7 @@ static const struct option longopts[] = {
 	{ "checkpoint-prefix", required_argument, NULL, CHECKPOINT_PREFIX },
 	{ "read-log", required_argument, NULL, READ_LOG },
 	{ "device", required_argument, NULL, OPT_DEVICE },
+	{ "devices", required_argument, NULL, OPT_DEVICES },
 	{ "batch-reads", required_argument, NULL, OPT_BATCH },
 	{ NULL, 0, NULL, 0 }
 };
@@ -167,6 +173,38 @@ static void for_each_batch(const std::vector<std::string>& files, Fn fn)
 	host::BatchStream stream(files, ropt, params.batchReads, params.threads > 1 ? params.threads : 0, params.verbose != 0);
 	while (const ReadBatch* batch = stream.next())
 		fn(*batch);
+}
+
+/** --devices: "0-3", "0,2,5" or a mix */
+static std::vector<int> parse_devices(const std::string& spec)
+{
+	std::vector<int> out;
+	std::istringstream in(spec);
+	std::string item;
+	while (std::getline(in, item, ',')) {
+		const size_t dash = item.find('-');
+		const int a = atoi(item.substr(0, dash).c_str());
+		const int b = dash == std::string::npos ? a : atoi(item.substr(dash + 1).c_str());
+		for (int d = a; d <= b; ++d)
+			out.push_back(d);
+	}
+	if (out.empty()) {
+		std::cerr << PROGRAM ": invalid option: `--devices=" << spec << "'\n";
+		exit(EXIT_FAILURE);
+	}
+	return out;
+}
+
+/** one host thread per GPU: run fn(rank) on every rank at once (the library's collectives meet inside) */
+template <typename Fn>
+static void on_all_ranks(size_t n, Fn fn)
+{
+	std::vector<std::thread> th;
+	for (size_t r = 1; r < n; ++r)
+		th.emplace_back([&fn, r] { fn(r); });
+	fn((size_t)0);
+	for (auto& t : th)
+		t.join();
 }
 
 int main(int argc, char** argv)
@@ -208,6 +246,7 @@ int main(int argc, char** argv)
 		case CHECKPOINT_PREFIX: arg >> params.checkpointPathPrefix; break;
 		case READ_LOG: arg >> params.readLogPath; break;
 		case OPT_DEVICE: arg >> params.device; break;
+		case OPT_DEVICES: arg >> params.devices; break;
 		case OPT_BATCH: arg >> params.batchReads; break;
 		}
 		if (optarg != NULL && (!arg.eof() || arg.fail())) {
@@ -257,9 +296,8 @@ int main(int argc, char** argv)
 		std::cerr << "Try `" << PROGRAM << " --help' for more information.\n";
 		exit(EXIT_FAILURE);
 	}
-	if (!params.graphPath.empty() || !params.covTrackPath.empty() || !params.tracePath.empty() ||
-	    params.readsPerCheckpoint != UINT64_MAX) {
-		std::cerr << PROGRAM ": -g, -C, -T and --checkpoint are not supported by the B200 implementation\n";
+	if (!params.graphPath.empty() || !params.covTrackPath.empty() || params.readsPerCheckpoint != UINT64_MAX) {
+		std::cerr << PROGRAM ": -g, -C and --checkpoint are not supported by the B200 implementation\n";
 		exit(EXIT_FAILURE);
 	}
 	/* initGlobals (bloom-dbg.cc:215-233) + MaskedKmer::setMask (BloomDBG/MaskedKmer.h:25-48), once k is known */
@@ -327,7 +365,16 @@ int main(int argc, char** argv)
 	}
 	std::ostream& out = params.outputPath.empty() ? std::cout : outputFile;
 
-	abb_filter* bloom = nullptr;
+	const std::vector<int> devs = params.devices.empty() ? std::vector<int>{ params.device } : parse_devices(params.devices);
+	const size_t nd = devs.size();
+	std::vector<abb_filter*> blooms(nd, nullptr);
+	std::vector<abb_comm*> comms(nd, nullptr);
+	if (nd > 1) { // the NCCL communicator of the sharded insert: rank r = r-th listed device
+		uint8_t id[128];
+		check(abb_comm_unique_id(id), "NCCL");
+		on_all_ranks(nd, [&](size_t r) { check(abb_comm_create(&comms[r], (int)r, (int)nd, id, devs[r]), "NCCL communicator"); });
+	}
+	abb_filter*& bloom = blooms[0];
 	if (!params.bloomPath.empty()) {
 		/* prebuiltBloomAssembly (bloom-dbg.cc:301-345) */
 		if (params.verbose)
@@ -343,8 +390,10 @@ int main(int argc, char** argv)
 		if (params.verbose)
 			std::cerr << "Assembling with k-mer size " << params.k << "\n";
 		const std::string mask = spacedSeedMask();
-		check(abb_filter_create(&bloom, ABB_COUNTING, h.size, h.hashNum, h.kmerSize, params.minCov, mask.c_str(), params.device), "filter");
-		check(abb_filter_upload(bloom, 0, raw.data(), raw.size()), "upload");
+		on_all_ranks(nd, [&](size_t r) {
+			check(abb_filter_create(&blooms[r], ABB_COUNTING, h.size, h.hashNum, h.kmerSize, params.minCov, mask.c_str(), devs[r]), "filter");
+			check(abb_filter_upload(blooms[r], 0, raw.data(), raw.size()), "upload");
+		});
 		printCountingBloomStats(bloom, std::cerr);
 	} else {
 		/* countingBloomAssembly (bloom-dbg.cc:347-386) */
@@ -355,14 +404,23 @@ int main(int argc, char** argv)
 		if (counters % 64)
 			counters += 64 - counters % 64;
 		const std::string mask = spacedSeedMask();
-		check(abb_filter_create(&bloom, ABB_COUNTING, counters, params.numHashes, params.k, params.minCov, mask.c_str(), params.device), "filter");
+		on_all_ranks(nd, [&](size_t r) {
+			check(abb_filter_create(&blooms[r], ABB_COUNTING, counters, params.numHashes, params.k, params.minCov, mask.c_str(), devs[r]), "filter");
+		});
 		uint64_t readCount = 0;
 		for_each_batch(loadFiles, [&](const ReadBatch& b) {
-			check(abb_insert_reads(bloom, b.bases.data(), b.offsets.data(), b.size(), nullptr), "insert");
+			if (nd > 1) // every rank sees every batch and keeps the counters of its own position range (abb_shard.cuh)
+				on_all_ranks(nd, [&](size_t r) {
+					check(abb_insert_reads_sharded(blooms[r], comms[r], b.bases.data(), b.offsets.data(), b.size(), 0, nullptr), "insert");
+				});
+			else
+				check(abb_insert_reads(bloom, b.bases.data(), b.offsets.data(), b.size(), nullptr), "insert");
 			readCount += b.size();
 			if (params.verbose)
 				std::cerr << "Loaded " << readCount << " reads into Bloom filter\n";
 		});
+		if (nd > 1) // union of the shards: every GPU gets the whole filter for the extension stage
+			on_all_ranks(nd, [&](size_t r) { check(abb_filter_allgather(blooms[r], comms[r]), "all-gather"); });
 		if (params.verbose) {
 			uint64_t nz = 0;
 			check(abb_filter_popcount(bloom, &nz, nullptr), "popcount");
@@ -375,27 +433,76 @@ int main(int argc, char** argv)
 	/* BloomDBG::assemble (bloom-dbg.h:900-1089) */
 	if (params.verbose)
 		std::cerr << "Trimming branches " << params.trim << " k-mers or shorter\n";
-	abb_assembly_params ap = { params.trim, (unsigned)params.verbose, params.readLogPath.empty() ? 0u : 1u, 0u };
-	abb_assembler* as = nullptr;
-	check(abb_assembler_create(&as, bloom, &ap), "assembler");
+	abb_assembly_params ap = { params.trim, (unsigned)params.verbose, params.readLogPath.empty() ? 0u : 1u, params.tracePath.empty() ? 0u : 1u };
+	std::vector<abb_assembler*> asms(nd, nullptr);
+	on_all_ranks(nd, [&](size_t r) {
+		check(abb_assembler_create(&asms[r], blooms[r], &ap), "assembler");
+		if (nd > 1)
+			check(abb_assembler_set_comm(asms[r], comms[r]), "assembler");
+	});
+	abb_assembler* as = asms[0];
 	std::ofstream readLog;
 	static const char* names[] = { "SHORTER_THAN_K", "NON_ACGT", "BLUNT_END", "NOT_SOLID", "ALL_KMERS_VISITED", "GENERATED_CONTIGS", "NA" };
 	if (!params.readLogPath.empty()) {
 		readLog.open(params.readLogPath.c_str());
 		readLog << "read_id\tresult\n";
 	}
+	/* -T FILE: ContigRecord::printHeaders / operator<< (bloom-dbg.h:219-253) */
+	std::ofstream traceOut;
+	static const char* extNames[] = { "AMBI_IN", "AMBI_OUT", "DEAD_END", "CYCLE", "LENGTH_LIMIT" };
+	if (!params.tracePath.empty()) {
+		traceOut.open(params.tracePath.c_str());
+		if (!traceOut) {
+			std::cerr << "error: `" << params.tracePath << "': " << strerror(errno) << "\n";
+			exit(EXIT_FAILURE);
+		}
+		traceOut << "contig_id\tlength\tredundant\tread_id\tleft_result\tleft_extension\tright_result\tright_extension\tseed_type\tseed_length\tseed\n";
+	}
 	uint64_t contigID = 0, readBase = 0;
 	for_each_batch(asmFiles, [&](const ReadBatch& b) {
 		const abb_contig* contigs = nullptr;
 		uint64_t n = 0;
 		const char* seqs = nullptr;
-		check(abb_assembler_process_reads(as, b.bases.data(), b.offsets.data(), b.size(), &contigs, &n, &seqs), "assemble");
+		if (nd > 1) // every rank runs the batch (sharded stages meet inside the library); rank 0's unitigs are printed
+			on_all_ranks(nd, [&](size_t r) {
+				if (r)
+					check(abb_assembler_process_reads(asms[r], b.bases.data(), b.offsets.data(), b.size(), nullptr, nullptr, nullptr), "assemble");
+				else
+					check(abb_assembler_process_reads(as, b.bases.data(), b.offsets.data(), b.size(), &contigs, &n, &seqs), "assemble");
+			});
+		else
+			check(abb_assembler_process_reads(as, b.bases.data(), b.offsets.data(), b.size(), &contigs, &n, &seqs), "assemble");
 		for (uint64_t i = 0; i < n; ++i) {
 			const abb_contig& c = contigs[i];
 			/* printContig (bloom-dbg.h:455-487) */
 			out << '>' << contigID++ << ' ' << c.length << ' ' << c.coverage << " read:" << b.id(c.seed_read - readBase) << '\n';
 			out.write(seqs + c.seq_offset, c.length);
 			out << '\n';
+		}
+		if (traceOut.is_open()) {
+			const abb_trace_row* rows = nullptr;
+			uint64_t nr = 0;
+			check(abb_assembler_trace(as, &rows, &nr), "trace");
+			for (uint64_t i = 0; i < nr; ++i) {
+				const abb_trace_row& t = rows[i];
+				const uint64_t r = t.seed_read - readBase;
+				if (t.redundant)
+					traceOut << "NA\t";
+				else
+					traceOut << t.contig_id << '\t';
+				traceOut << t.length << '\t' << (int)t.redundant << '\t' << b.id(r) << '\t';
+				if (t.left_n > 0)
+					traceOut << extNames[t.left_code > 4 ? 4 : t.left_code] << '\t' << t.left_n << '\t';
+				else
+					traceOut << "NA\tNA\t";
+				if (t.right_n > 0)
+					traceOut << extNames[t.right_code > 4 ? 4 : t.right_code] << '\t' << t.right_n << '\t';
+				else
+					traceOut << "NA\tNA\t";
+				traceOut << "READ\t" << params.k << '\t';
+				traceOut.write(b.bases.data() + b.offsets[r] + t.seed_pos, params.k);
+				traceOut << '\n';
+			}
 		}
 		if (readLog.is_open()) {
 			const uint8_t* codes = nullptr;
@@ -415,8 +522,11 @@ int main(int argc, char** argv)
 	});
 	if (params.verbose)
 		std::cerr << "Assembly complete\n";
-	abb_assembler_destroy(as);
-	abb_filter_destroy(bloom);
+	for (size_t r = 0; r < nd; ++r) {
+		abb_assembler_destroy(asms[r]);
+		abb_filter_destroy(blooms[r]);
+		abb_comm_destroy(comms[r]);
+	}
 	if (!params.outputPath.empty())
 		outputFile.close();
 	return EXIT_SUCCESS;

@@ -270,19 +270,13 @@ def main():
             dist.broadcast_object_list(box, src=0)
             return box[0]
         comm = capi.Comm(rank, world, local_rank, bcast)
-    lo, up = rank * rs.n // world, (rank + 1) * rs.n // world
-    offs_slice = torch.arange(up - lo + 1, dtype=torch.int64, device=dev) * L
-
     asm = capi.Assembler(filt)  # one handle for all steps: device buffers are allocated once, state is reset per step
     asm.raw_results = True      # the unitig sequences are copied to the host by the library; no Python string per unitig
 
+    if world > 1:
+        asm.set_comm(comm)      # classification, candidate scans and tile production are sharded inside the library
+
     def pass2(d_bases, d_offs):
-        if world > 1:
-            from abyss_b200 import multigpu
-            codes = multigpu.sharded_classify(asm, comm, d_bases + lo * L, offs_slice.data_ptr(), up - lo, rs.n, dev)
-            out = asm.process_reads_dev(d_bases, d_offs, rs.n)
-            del codes
-            return out
         return asm.process_reads_dev(d_bases, d_offs, rs.n)
 
     def one_step(host=None):

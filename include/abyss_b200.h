@@ -142,6 +142,10 @@ int abb_filter_resident_reads(abb_filter* f, const char** d_bases, const uint64_
 /* d_buf holds world * bytes_per_rank bytes, this rank's part already in place at rank * bytes_per_rank */
 int abb_comm_allgather_bytes(abb_comm* c, void* d_buf, uint64_t bytes_per_rank, void* cuda_stream);
 int abb_comm_allreduce_max_u8(abb_comm* c, void* d_buf, uint64_t n, void* cuda_stream);
+/* all-gather of unequal parts: this rank's send_bytes go to every other rank; rank r's recv_bytes[r] bytes land at
+ * d_recv_base + recv_offsets[r] (grouped ncclSend / ncclRecv; entries for the own rank are ignored) */
+int abb_comm_exchange_bytes(abb_comm* c, const void* d_send, uint64_t send_bytes, void* d_recv_base, const uint64_t* recv_offsets,
+                            const uint64_t* recv_bytes, void* cuda_stream);
 
 void* abb_filter_device_ptr(abb_filter* f, int level);
 
@@ -166,7 +170,7 @@ typedef struct abb_assembly_params {
 	unsigned verbose;
 	unsigned read_log;  /* 1: per-read outcome codes are exact (`--read-log`); 0: a read that fails the
 	                       solid test is reported NOT_SOLID without the (more expensive) blunt-end test */
-	unsigned reserved;
+	unsigned reserved;  /* flags: bit 0 = keep the `-T` trace rows of each batch (abb_assembler_trace) */
 } abb_assembly_params;
 
 typedef struct abb_contig {
@@ -211,6 +215,24 @@ int abb_assembler_counters(const abb_assembler* a, abb_assembly_counters* out);
  * codes: 0 SHORTER_THAN_K, 1 NON_ACGT, 2 BLUNT_END, 3 NOT_SOLID, 4 ALL_KMERS_VISITED,
  * 5 GENERATED_CONTIGS */
 int abb_assembler_read_results(const abb_assembler* a, const uint8_t** codes, uint64_t* n);
+/* multi-GPU pass 2 (one process per GPU, every rank holds the whole solid filter and is fed the same batches): the
+ * pure per-item stages -- read classification (K3a), the candidate scans against the assembled filter (K3b) and tile
+ * production -- are split over the ranks of `comm` and all-gathered; the walks and the file-order replay run
+ * replicated, so every rank returns the same unitigs.  NULL = single GPU. */
+int abb_assembler_set_comm(abb_assembler* a, abb_comm* comm);
+/* `-T FILE` (ContigRecord, bloom-dbg.h:186-254, written by outputContig :618-619): one row per contig that was
+ * handed to outputContig while the last batch was processed, in the reference's order.  contig_id = ~0 for a
+ * redundant contig ("NA"); codes: 0 AMBI_IN, 1 AMBI_OUT, 2 DEAD_END, 3 CYCLE, 4 LENGTH_LIMIT (Graph/ExtendPath.h:63-80);
+ * the seed is the k-mer at seed_pos of read seed_read.  Needs abb_assembly_params.reserved bit 0. */
+typedef struct abb_trace_row {
+	uint64_t contig_id;
+	uint64_t seed_read;
+	uint32_t length;    /* bases of the contig (the reference prints an uninitialised value here for redundant contigs) */
+	uint32_t seed_pos;
+	uint32_t left_n, right_n;
+	uint8_t left_code, right_code, redundant, pad;
+} abb_trace_row;
+int abb_assembler_trace(const abb_assembler* a, const abb_trace_row** rows, uint64_t* n);
 /* access to the assembled-k-mer bit filter (for checkpoints / tests) */
 abb_filter* abb_assembler_assembled_filter(abb_assembler* a);
 

@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 WORKER = r'''
 import os, sys, json, hashlib, numpy as np, torch, torch.distributed as dist
 sys.path.insert(0, %(root)r)
-from abyss_b200 import capi, multigpu
+from abyss_b200 import capi
 from abyss_b200.synth import ReadSet
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(rank)
@@ -44,11 +44,10 @@ for name, window in (("e2e_g20k_k32", 0), ("e2e_g30k_k64", 4096), ("e2e_g10k_k25
     g.insert_reads_sharded(comm, capi.fixed_length_reads(asc))
     assert (g.download() == got).all()
     g.close()
-    # pass 2 with the classification sharded over the ranks: FASTA and read log identical to the reference
-    lo, up = rank * rs.n // world, (rank + 1) * rs.n // world
-    offs_slice = torch.arange(up - lo + 1, dtype=torch.int64, device=dev) * L
+    # pass 2 with classification, candidate scans and tile production sharded over the ranks: FASTA and read log
+    # identical to the reference on every rank
     a = capi.Assembler(f, read_log=True)
-    codes = multigpu.sharded_classify(a, comm, bases.data_ptr() + lo * L, offs_slice.data_ptr(), up - lo, rs.n, dev)
+    a.set_comm(comm)
     out = a.process_reads_dev(bases.data_ptr(), offs.data_ptr(), rs.n)
     fasta = "".join(f">{i} {len(s)} {cov} read:{rs.read_id(r)}\n{s}\n" for i, (r, s, cov) in enumerate(out))
     assert fasta == open(os.path.join(gd, name + ".fa")).read(), f"{name}: rank {rank} FASTA differs"
@@ -73,3 +72,27 @@ def test_sharded_insert_is_exact(tmp_path, world):
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
                         "--master-port", str(29541 + world), str(w)], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "MULTI_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("ndev", [2, 8])
+def test_cli_devices_option(tmp_path, ndev):
+    # abyss-bloom-dbg --devices=0-(N-1): the C++ host drives N GPUs (one thread per GPU, NCCL behind the C ABI) and
+    # prints the same bytes as the reference / the single-GPU run
+    import json
+    import torch
+    from abyss_b200 import build
+    from abyss_b200.synth import ReadSet
+    if torch.cuda.device_count() < ndev:
+        pytest.skip(f"needs {ndev} GPUs")
+    build.build()
+    gd = os.path.join(ROOT, "tests", "golden")
+    c = {x["name"]: x for x in json.load(open(os.path.join(gd, "e2e_cases.json")))}["e2e_g20k_k32"]
+    rs = ReadSet.from_coverage(c["seed"], c["genome"], c["cov"], c["L"], c["err"])
+    fq = str(tmp_path / "r.fq")
+    rs.write_fastq(fq)
+    fa, log = str(tmp_path / "out.fa"), str(tmp_path / "read.log")
+    r = subprocess.run([os.path.join(ROOT, "abyss_b200", "lib", "abyss-bloom-dbg"), f"-k{c['k']}", f"--kc={c['kc']}", f"-b{c['b']}", f"-H{c['H']}",
+                        f"--devices=0-{ndev - 1}", "--batch-reads=1500", f"--read-log={log}", "-o", fa, fq], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    assert open(fa).read() == open(os.path.join(gd, "e2e_g20k_k32.fa")).read()
+    assert open(log).read() == open(os.path.join(gd, "e2e_g20k_k32.readlog.tsv")).read()
