@@ -112,6 +112,7 @@ SIGNATURES = {
     "abb_assembler_classify_dev": (C.c_int, [_vp, _vp, _vp, C.c_uint64, _vp]),
     "abb_assembler_set_codes": (C.c_int, [_vp, _vp, C.c_uint64]),
     "abb_assembler_counters": (C.c_int, [_vp, C.POINTER(AssemblyCounters)]),
+    "abb_assembler_set_counters": (C.c_int, [_vp, C.POINTER(AssemblyCounters)]),
     "abb_assembler_read_results": (C.c_int, [_vp, C.POINTER(_u8p), _u64p]),
     "abb_assembler_set_comm": (C.c_int, [_vp, _vp]),
     "abb_assembler_trace": (C.c_int, [_vp, C.POINTER(C.POINTER(TraceRow)), _u64p]),

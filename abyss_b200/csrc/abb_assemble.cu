@@ -2223,6 +2223,14 @@ int abb_assembler_counters(const abb_assembler* a, abb_assembly_counters* out)
 	return ABB_OK;
 }
 
+int abb_assembler_set_counters(abb_assembler* a, const abb_assembly_counters* in)
+{
+	ABB_REQUIRE(a && in, "NULL argument");
+	a->counters = *in;
+	a->reads_seen = in->reads_processed;
+	return ABB_OK;
+}
+
 int abb_assembler_set_comm(abb_assembler* a, abb_comm* comm)
 {
 	ABB_REQUIRE(a, "NULL assembler");

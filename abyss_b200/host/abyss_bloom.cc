@@ -10,6 +10,7 @@
 #include "bloom_file.h"
 #include "reads.h"
 #include <getopt.h>
+#include <cmath>
 #include <iomanip>
 
 #define PROGRAM "abyss-bloom"
@@ -29,10 +30,56 @@ static void usage()
 	exit(EXIT_FAILURE);
 }
 
+/** `abyss-bloom info FILE`: printBloomStats (Bloom/bloom.cc:433-441,823-846) for the two ntHash-family file formats.
+ *  (The reference's `info` reads the Konnector format only; the filters of this path are the BTL ones, so this command
+ *  prints the same three lines for them, with the population counted on the GPU.) */
+static int info(int argc, char** argv)
+{
+	int device = 0;
+	std::string path;
+	for (int i = 2; i < argc; ++i) {
+		const std::string a = argv[i];
+		if (a.rfind("--device=", 0) == 0)
+			device = atoi(a.c_str() + 9);
+		else if (a == "-v" || a == "--verbose")
+			;
+		else
+			path = a;
+	}
+	if (path.empty()) {
+		std::cerr << PROGRAM ": missing arguments\n";
+		usage();
+	}
+	std::ifstream probe(path, std::ios::binary);
+	std::string magic;
+	std::getline(probe, magic);
+	probe.close();
+	BloomHeader h;
+	std::vector<uint8_t> raw;
+	abb_filter* f = nullptr;
+	if (magic == "[BTLCountingBloomFilter_v1]") {
+		read_counting_bloom(path, h, raw);
+		check(abb_filter_create(&f, ABB_COUNTING, h.size, h.hashNum, h.kmerSize, 1, "", device), "filter");
+	} else {
+		read_bit_bloom(path, h, raw);
+		check(abb_filter_create(&f, ABB_BIT, h.size, h.hashNum, h.kmerSize, 0, "", device), "filter");
+	}
+	check(abb_filter_upload(f, 0, raw.data(), raw.size()), "upload");
+	uint64_t nz = 0;
+	check(abb_filter_popcount(f, &nz, nullptr), "popcount");
+	std::cerr << "Bloom size (bits): " << h.size << "\n"
+	          << "Bloom popcount (bits): " << nz << "\n"
+	          << "Bloom filter FPR: " << std::setprecision(3) << 100 * std::pow((double)nz / (double)h.size, (double)h.hashNum) << "%\n";
+	abb_filter_destroy(f);
+	return EXIT_SUCCESS;
+}
+
 int main(int argc, char** argv)
 {
+	if (argc >= 2 && std::string(argv[1]) == "info")
+		return info(argc, argv);
 	if (argc < 2 || std::string(argv[1]) != "build") {
-		std::cerr << PROGRAM ": only the `build' command (-t counting | rolling-hash) is implemented on the B200\n";
+		std::cerr << PROGRAM ": only the `build' (-t counting | rolling-hash) and `info' commands are implemented on the B200\n";
 		usage();
 	}
 	uint64_t bloomSize = 500ULL << 20; // [500M]

@@ -296,8 +296,8 @@ int main(int argc, char** argv)
 		std::cerr << "Try `" << PROGRAM << " --help' for more information.\n";
 		exit(EXIT_FAILURE);
 	}
-	if (!params.graphPath.empty() || !params.covTrackPath.empty() || params.readsPerCheckpoint != UINT64_MAX) {
-		std::cerr << PROGRAM ": -g, -C and --checkpoint are not supported by the B200 implementation\n";
+	if (!params.graphPath.empty() || !params.covTrackPath.empty()) {
+		std::cerr << PROGRAM ": -g and -C are not supported by the B200 implementation\n";
 		exit(EXIT_FAILURE);
 	}
 	/* initGlobals (bloom-dbg.cc:215-233) + MaskedKmer::setMask (BloomDBG/MaskedKmer.h:25-48), once k is known */
@@ -365,6 +365,23 @@ int main(int argc, char** argv)
 	}
 	std::ostream& out = params.outputPath.empty() ? std::cout : outputFile;
 
+	/* checkpoints (BloomDBG/Checkpoint.h): PREFIX.dbg.bloom, PREFIX.visited.bloom, PREFIX.counters.tsv, PREFIX.contigs.fa */
+	const bool ckptOn = params.readsPerCheckpoint != UINT64_MAX && params.readsPerCheckpoint != 0;
+	const std::string ckDbg = params.checkpointPathPrefix + ".dbg.bloom", ckVisited = params.checkpointPathPrefix + ".visited.bloom",
+	                  ckCounters = params.checkpointPathPrefix + ".counters.tsv", ckFasta = params.checkpointPathPrefix + ".contigs.fa";
+	auto readable = [](const std::string& p) { return std::ifstream(p.c_str()).good(); };
+	const bool resume = ckptOn && readable(ckDbg) && readable(ckVisited) && readable(ckCounters) && readable(ckFasta); // checkpointExists
+	if (resume) {
+		if (params.verbose)
+			std::cerr << "Resuming from last checkpoint...\n\tReading Bloom filter de Bruijn graph from `" << ckDbg << "'\n";
+		params.bloomPath = ckDbg; // the solid filter comes from the checkpoint; pass 1 is skipped
+	}
+	if (ckptOn) { // batches must end on checkpoint boundaries: the largest divisor of N that is a reasonable batch
+		uint64_t b = std::min<uint64_t>(params.readsPerCheckpoint, params.batchReads ? params.batchReads : 4000000);
+		while (params.readsPerCheckpoint % b)
+			--b;
+		params.batchReads = b;
+	}
 	const std::vector<int> devs = params.devices.empty() ? std::vector<int>{ params.device } : parse_devices(params.devices);
 	const size_t nd = devs.size();
 	std::vector<abb_filter*> blooms(nd, nullptr);
@@ -441,6 +458,88 @@ int main(int argc, char** argv)
 			check(abb_assembler_set_comm(asms[r], comms[r]), "assembler");
 	});
 	abb_assembler* as = asms[0];
+	uint64_t contigID = 0, readBase = 0, skipReads = 0, sinceCheckpoint = 0;
+	std::ofstream checkpointOut; // duplicate FASTA output (bloom-dbg.h:919-926)
+	if (resume) { // resumeFromCheckpoint (Checkpoint.h:158-226)
+		BloomHeader vh;
+		std::vector<uint8_t> vraw;
+		if (params.verbose)
+			std::cerr << "\tReading reading visited k-mers Bloom from `" << ckVisited << "'\n";
+		read_bit_bloom(ckVisited, vh, vraw);
+		abb_assembly_counters cn = {};
+		{
+			std::ifstream cin_(ckCounters.c_str());
+			std::string header;
+			std::getline(cin_, header);
+			unsigned long long a = 0, b = 0, c = 0, d = 0;
+			cin_ >> a >> b >> c >> d;
+			if (!cin_) {
+				std::cerr << "error: `" << ckCounters << "': malformed counters\n";
+				exit(EXIT_FAILURE);
+			}
+			cn.solid_reads = a;
+			cn.reads_processed = b;
+			cn.bases_assembled = c;
+			cn.contig_id = d;
+		}
+		on_all_ranks(nd, [&](size_t r) {
+			check(abb_filter_upload(abb_assembler_assembled_filter(asms[r]), 0, vraw.data(), vraw.size()), "visited filter");
+			check(abb_assembler_set_counters(asms[r], &cn), "counters");
+		});
+		contigID = cn.contig_id;
+		readBase = skipReads = cn.reads_processed;
+		if (params.verbose)
+			std::cerr << "\tAdvancing to read index " << cn.reads_processed << " in input reads...\n\tOutputting previously assembled contigs from `"
+			          << ckFasta << "'\n";
+		std::ifstream prev(ckFasta.c_str());
+		out << prev.rdbuf();
+		std::ifstream prev2(ckFasta.c_str());
+		checkpointOut.open((ckFasta + ".tmp").c_str());
+		checkpointOut << prev2.rdbuf();
+	} else if (ckptOn)
+		checkpointOut.open((ckFasta + ".tmp").c_str());
+	bool dbgWritten = resume;
+	auto createCheckpoint = [&]() { // createCheckpoint (Checkpoint.h:31-127); the solid filter does not change during pass 2
+		checkpointOut.flush();
+		if (params.verbose)
+			std::cerr << "Writing checkpoint data...\n";
+		if (!dbgWritten) {
+			BloomHeader h;
+			h.size = abb_filter_size(bloom);
+			h.sizeInBytes = abb_filter_size_in_bytes(bloom);
+			h.hashNum = abb_filter_hash_num(bloom);
+			h.kmerSize = abb_filter_kmer_size(bloom);
+			std::vector<uint8_t> raw(h.sizeInBytes);
+			check(abb_filter_download(bloom, 0, raw.data(), raw.size()), "download");
+			std::ofstream o((ckDbg + ".tmp").c_str(), std::ios::binary);
+			write_counting_bloom(o, h, raw);
+			o.close();
+			rename((ckDbg + ".tmp").c_str(), ckDbg.c_str());
+			dbgWritten = true;
+		}
+		{
+			abb_filter* vis = abb_assembler_assembled_filter(as);
+			std::vector<uint8_t> raw(abb_filter_size_in_bytes(vis));
+			check(abb_filter_download(vis, 0, raw.data(), raw.size()), "download");
+			std::ofstream o((ckVisited + ".tmp").c_str(), std::ios::binary);
+			write_bit_bloom(o, abb_filter_size(vis), abb_filter_hash_num(vis), abb_filter_kmer_size(vis), raw);
+			o.close();
+		}
+		{
+			abb_assembly_counters cn;
+			abb_assembler_counters(as, &cn);
+			std::ofstream o((ckCounters + ".tmp").c_str());
+			o << "solid_reads\tprocessed_reads\tbases_assembled\tnext_contig_id\n"
+			  << cn.solid_reads << '\t' << cn.reads_processed << '\t' << cn.bases_assembled << '\t' << cn.contig_id << '\n';
+		}
+		{
+			std::ifstream src((ckFasta + ".tmp").c_str(), std::ios::binary);
+			std::ofstream dst(ckFasta.c_str(), std::ios::binary);
+			dst << src.rdbuf();
+		}
+		rename((ckVisited + ".tmp").c_str(), ckVisited.c_str());
+		rename((ckCounters + ".tmp").c_str(), ckCounters.c_str());
+	};
 	std::ofstream readLog;
 	static const char* names[] = { "SHORTER_THAN_K", "NON_ACGT", "BLUNT_END", "NOT_SOLID", "ALL_KMERS_VISITED", "GENERATED_CONTIGS", "NA" };
 	if (!params.readLogPath.empty()) {
@@ -458,8 +557,11 @@ int main(int argc, char** argv)
 		}
 		traceOut << "contig_id\tlength\tredundant\tread_id\tleft_result\tleft_extension\tright_result\tright_extension\tseed_type\tseed_length\tseed\n";
 	}
-	uint64_t contigID = 0, readBase = 0;
 	for_each_batch(asmFiles, [&](const ReadBatch& b) {
+		if (skipReads) { // resumed: these reads were processed before the checkpoint
+			skipReads -= std::min<uint64_t>(skipReads, b.size());
+			return;
+		}
 		const abb_contig* contigs = nullptr;
 		uint64_t n = 0;
 		const char* seqs = nullptr;
@@ -475,9 +577,15 @@ int main(int argc, char** argv)
 		for (uint64_t i = 0; i < n; ++i) {
 			const abb_contig& c = contigs[i];
 			/* printContig (bloom-dbg.h:455-487) */
-			out << '>' << contigID++ << ' ' << c.length << ' ' << c.coverage << " read:" << b.id(c.seed_read - readBase) << '\n';
+			out << '>' << contigID << ' ' << c.length << ' ' << c.coverage << " read:" << b.id(c.seed_read - readBase) << '\n';
 			out.write(seqs + c.seq_offset, c.length);
 			out << '\n';
+			if (checkpointOut.is_open()) {
+				checkpointOut << '>' << contigID << ' ' << c.length << ' ' << c.coverage << " read:" << b.id(c.seed_read - readBase) << '\n';
+				checkpointOut.write(seqs + c.seq_offset, c.length);
+				checkpointOut << '\n';
+			}
+			++contigID;
 		}
 		if (traceOut.is_open()) {
 			const abb_trace_row* rows = nullptr;
@@ -512,6 +620,11 @@ int main(int argc, char** argv)
 				readLog << b.id(i) << '\t' << names[codes[i] > 6 ? 6 : codes[i]] << '\n';
 		}
 		readBase += b.size();
+		sinceCheckpoint += b.size();
+		if (ckptOn && sinceCheckpoint == params.readsPerCheckpoint) {
+			createCheckpoint();
+			sinceCheckpoint = 0;
+		}
 		if (params.verbose) {
 			abb_assembly_counters cn;
 			abb_assembler_counters(as, &cn);
@@ -522,6 +635,11 @@ int main(int argc, char** argv)
 	});
 	if (params.verbose)
 		std::cerr << "Assembly complete\n";
+	if (ckptOn && !params.keepCheckpoint) { // removeCheckpointData (Checkpoint.h:229-247)
+		checkpointOut.close();
+		for (const std::string& f : { ckDbg, ckVisited, ckCounters, ckFasta, ckFasta + ".tmp" })
+			remove(f.c_str());
+	}
 	for (size_t r = 0; r < nd; ++r) {
 		abb_assembler_destroy(asms[r]);
 		abb_filter_destroy(blooms[r]);

@@ -76,6 +76,28 @@ inline void read_counting_bloom(const std::string& path, BloomHeader& h, std::ve
 	}
 }
 
+/** BloomFilter::loadFilter (BloomFilter.hpp:104-163): header + raw bit array */
+inline void read_bit_bloom(const std::string& path, BloomHeader& h, std::vector<uint8_t>& raw)
+{
+	std::ifstream in(path, std::ios::binary);
+	if (!in) {
+		std::cerr << "error: `" << path << "': cannot open\n";
+		exit(EXIT_FAILURE);
+	}
+	auto kv = read_header(in, "BTLBloomFilter_v1", path);
+	h.size = strtoull(kv["BloomFilterSize"].c_str(), nullptr, 10);
+	h.hashNum = (unsigned)strtoul(kv["HashNum"].c_str(), nullptr, 10);
+	h.kmerSize = (unsigned)strtoul(kv["KmerSize"].c_str(), nullptr, 10);
+	h.sizeInBytes = strtoull(kv["BloomFilterSizeInBytes"].c_str(), nullptr, 10);
+	h.bitsPerCounter = 1;
+	raw.resize(h.sizeInBytes);
+	in.read(reinterpret_cast<char*>(raw.data()), (std::streamsize)raw.size());
+	if (!in) {
+		std::cerr << "error: `" << path << "': truncated filter\n";
+		exit(EXIT_FAILURE);
+	}
+}
+
 /** CountingBloomFilter::storeHeader + operator<< (CountingBloomFilter.hpp:341-379) */
 inline void write_counting_bloom(std::ostream& out, const BloomHeader& h, const std::vector<uint8_t>& raw)
 {

@@ -211,6 +211,9 @@ int abb_assembler_set_codes(abb_assembler* a, const uint8_t* d_codes, uint64_t n
  * filter, the contig-end table, the tile store, counters and statistics, keeps all device buffers. */
 int abb_assembler_reset(abb_assembler* a);
 int abb_assembler_counters(const abb_assembler* a, abb_assembly_counters* out);
+/* resume from a checkpoint (resumeFromCheckpoint, BloomDBG/Checkpoint.h:158-226): restores the counters (next contig id,
+ * index of the next input read); the caller uploads the two filters with abb_filter_upload */
+int abb_assembler_set_counters(abb_assembler* a, const abb_assembly_counters* in);
 /* optional per-read outcome log of the last batch (ReadResult, bloom-dbg.h:256-293);
  * codes: 0 SHORTER_THAN_K, 1 NON_ACGT, 2 BLUNT_END, 3 NOT_SOLID, 4 ALL_KMERS_VISITED,
  * 5 GENERATED_CONTIGS */

@@ -60,6 +60,40 @@ def test_trace_file_identical_to_reference(cases, name):
     assert got == want
 
 
+def test_checkpoints(cases):
+    # --checkpoint=N: PREFIX.dbg.bloom / .visited.bloom / .counters.tsv / .contigs.fa byte-identical to the files the
+    # reference's createCheckpoint writes (BloomDBG/Checkpoint.h:31-127; goldens from tests/golden/make_golden_checkpoint.py),
+    # and a run that finds them resumes there and ends with the FASTA of the uninterrupted run.  (The reference's own
+    # resume path is broken in 2.3.10 -- it emits 35 000 k-length contigs on this input -- so resume is checked against
+    # the uninterrupted output, which is what resumeFromCheckpoint is meant to reproduce.)
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "checkpoint_case.json")))
+    c, fq, d = cases[g["case"]]
+    pfx = str(d / "ck")
+    fa = str(d / "ck_out.fa")
+    cmd = [os.path.join(BIN, "abyss-bloom-dbg"), f"-k{c['k']}", f"--kc={c['kc']}", f"-b{c['b']}", f"-H{c['H']}",
+           f"--checkpoint={g['reads_per_checkpoint']}", "--keep-checkpoint", f"--checkpoint-prefix={pfx}", "-o", fa, fq]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    golden_fa = open(os.path.join(ROOT, "tests", "golden", g["case"] + ".fa")).read()
+    assert open(fa).read() == golden_fa
+    sha = lambda p: hashlib.sha256(open(p, "rb").read()).hexdigest()
+    assert open(pfx + ".counters.tsv").read() == g["counters_tsv"]
+    assert sha(pfx + ".dbg.bloom") == g["dbg_bloom_sha256"]
+    assert sha(pfx + ".visited.bloom") == g["visited_bloom_sha256"]
+    assert sha(pfx + ".contigs.fa") == g["contigs_fa_sha256"]
+    # resume from the state after 3000 of the 4000 reads
+    fa2 = str(d / "ck_resumed.fa")
+    r = subprocess.run(cmd[:-3] + ["-v", "-o", fa2, fq], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "Resuming from last checkpoint" in r.stderr and "Advancing to read index 3000" in r.stderr
+    assert open(fa2).read() == golden_fa
+    # without --keep-checkpoint the files are removed at the end (removeCheckpointData)
+    cmd3 = [x for x in cmd if x != "--keep-checkpoint"]
+    r = subprocess.run(cmd3, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert not os.path.exists(pfx + ".dbg.bloom") and not os.path.exists(pfx + ".counters.tsv")
+
+
 def test_abyss_bloom_build_and_prebuilt(cases):
     c, fq, d = cases["e2e_g20k_k32"]
     bf = str(d / "counting.bloom")
@@ -72,6 +106,10 @@ def test_abyss_bloom_build_and_prebuilt(cases):
     r = subprocess.run([os.path.join(BIN, "abyss-bloom-dbg"), f"--kc={c['kc']}", "-i", bf, "-o", fa, fq], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert open(fa).read() == open(os.path.join(ROOT, "tests", "golden", "e2e_g20k_k32.fa")).read()
+    # abyss-bloom info on both file formats: size / popcount / FPR lines (printBloomStats, bloom.cc:433-441)
+    r = subprocess.run([os.path.join(BIN, "abyss-bloom"), "info", bf], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert f"Bloom size (bits): {c['counters']}" in r.stderr and f"Bloom popcount (bits): {c['counters_nonzero']}" in r.stderr
     # rolling-hash cascading filter, 2 levels: file identical to the reference's
     rh = str(d / "rh.bloom")
     r = subprocess.run([os.path.join(BIN, "abyss-bloom"), "build", "-k", str(c["k"]), "-t", "rolling-hash", "-l", "2", f"-H{c['H']}",
