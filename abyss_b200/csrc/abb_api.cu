@@ -26,7 +26,7 @@ void set_error(const char* fmt, ...)
 }
 
 constexpr uint64_t kDefaultWindow = 1ULL << 17;
-constexpr uint64_t kChunkSlots = 1ULL << 25; // h0 staging: 32 Mi slots = 256 MiB + 32 MiB flags
+constexpr uint64_t kChunkSlots = 1ULL << 27; // h0 staging: 128 Mi slots = 1 GiB + 128 MiB flags (one persistent launch + one forced drain per chunk)
 
 static uint64_t next_pow2(uint64_t x)
 {

@@ -18,7 +18,8 @@
 // Vertex identity: the reference compares vertices by canonical hash AND canonical string
 // (RollingBloomDBG.h:92-100, RC-invariant).  Here identity is the 64-bit canonical ntHash alone;
 // two distinct k-mers colliding inside one local traversal has probability ~2^-64 per comparison.
-// Spaced seeds are not supported in pass 2 (the assembler refuses a masked filter).
+// With a spaced seed (MaskedKmer) a vertex carries the masked Bloom hash and a separate identity (see "Spaced seeds" in
+// DESIGN.md section 3); tiles are switched off then (equal hash no longer implies equal continuation).
 #pragma once
 #include "abb_device.cuh"
 

@@ -94,8 +94,8 @@ static const char USAGE_MESSAGE[] =
     "                               output as one GPU), one host thread per GPU\n"
     "      --batch-reads=N          reads per GPU batch [4000000]\n"
     "\n"
-    "Spaced seeds (-K, --qr-seed, -s) are accepted by the hashing/insert stage only; -g, -C, -R, -T\n"
-    "and --checkpoint are not supported by the B200 implementation.\n";
+    "Spaced seeds (-K, --qr-seed, -s), -T, --read-log and --checkpoint work as in the reference;\n"
+    "-g, -C and -R (GraphViz / coverage-track debug outputs) are not supported by the B200 implementation.\n";
 
 static AssemblyParams params;
 static ReadOpts ropt;

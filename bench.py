@@ -22,12 +22,13 @@ k-mers/s = (sum over reads of len-k+1) / step time, counted once per input k-mer
            launches applied / their summed CUDA-event time, against the measured HBM copy bandwidth in
            MEASURED_PEAKS.json.  `insert_phase` is the same over the whole insert phase (hash + insert + drains).
 `cpu_baseline`: the UNMODIFIED reference (oracle/_ref/abyss-bloom-dbg-ref, built by oracle/Makefile) with all host
-           threads.  The reference pays a fixed start-up cost that depends on -b, not on the reads (zero-filling the
-           8 GiB of filters, contigEndKmers.rehash(2^28), bloom-dbg.h:993): it is measured with a 1-read input
-           (`fixed_s`) and reported next to the as-run rate of the bounded sample, the marginal rate
-           (k-mers / (t - fixed_s)) and the full-job estimate fixed_s + N_kmers / marginal -- `value` of the reference
-           arm is that full-job estimate (what the reference would deliver on this config), not the sample's
-           as-run rate, so the ratio does not depend on the sample size.
+           threads, on a bounded job of the workload's SHAPE: S reads at the same 40x coverage (genome S*L/40), error
+           rate, k, kc, H and -b.  (The first S reads of the 50 M-read job would be a 3x-coverage job with nothing to
+           assemble: round 1's sample, 12 s, of which 9 s were start-up cost.)  Reported: the as-run rate (`value`),
+           the start-up cost that depends on -b only (`fixed_s`, 1-read input: zero-filling 8 GiB of filters,
+           contigEndKmers.rehash(2^28), bloom-dbg.h:993), the marginal rate, and -- from profiles/r02_ref_full_run.json --
+           the one FULL 50 M-read run measured on this pool: 626 s with 128 threads = 6.9 M k-mers/s, unitig set
+           identical to this implementation's.
 `--impl reference` times that reference binary as the step (bounded sample per step).
 """
 from __future__ import annotations
@@ -128,8 +129,14 @@ def run_reference(fq, threads, out_fa):
     return dt
 
 
-def reference_measurement(rs, sample, cores, n_runs, warmup=0):
-    """fixed start-up cost (1-read input, same -b) and `n_runs` timed runs of the first `sample` reads"""
+def reference_measurement(sample, cores, n_runs, warmup=0):
+    """The reference on a BOUNDED job of the same shape: `sample` reads at the workload's 40x coverage (a genome of
+    sample * L / 40 bases, same error rate, same k / kc / H / -b) -- NOT the first `sample` reads of the 50 M-read job,
+    which would be a 3x-coverage job with nothing to assemble.  Also measured: the start-up cost that depends on -b only
+    (1-read input)."""
+    from abyss_b200.synth import ReadSet
+    genome = max(1000, int(sample * L / 40))
+    rs = ReadSet(SEED, genome, sample, L, ERR, paired=True)
     tmp = tempfile.mkdtemp(prefix="abyss_ref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
     fq1, fq = os.path.join(tmp, "one.fq"), os.path.join(tmp, "sample.fq")
     write_sample_fastq(rs, 1, fq1)
@@ -141,27 +148,28 @@ def reference_measurement(rs, sample, cores, n_runs, warmup=0):
         dt = run_reference(fq, cores, out)
         if i >= warmup:
             times.append(dt)
-    import hashlib
-    md5 = hashlib.md5(open(out, "rb").read()).hexdigest()
     for f in (fq1, fq, out):
         os.remove(f)
     os.rmdir(tmp)
     t = sum(times) / len(times)
     kmers = sample * (L - K + 1)
-    full = N_READS * (L - K + 1)
-    marginal = kmers / max(t - fixed, 1e-3)
-    est_full_s = fixed + full / marginal
-    return {"t": t, "fixed_s": fixed, "as_run": kmers / t, "marginal": marginal, "full_job_estimate_s": est_full_s,
-            "full_job_value": full / est_full_s, "sample_fasta_md5": md5, "kmers": kmers}
+    m = {"t": t, "fixed_s": fixed, "as_run": kmers / t, "marginal": kmers / max(t - fixed, 1e-3), "kmers": kmers, "genome": genome}
+    full = os.path.join(ROOT, "profiles", "r02_ref_full_run.json")
+    if os.path.exists(full):  # one full 50 M-read run of the reference, measured once on this pool (scripts/ref_full_run.py)
+        fr = json.load(open(full))["reference"]
+        m["full_run"] = {"wall_s": fr["wall_s"], "kmers_per_s": fr["kmers_per_s"], "cmd": fr["cmd"], "source": "profiles/r02_ref_full_run.json"}
+    return m
 
 
 def cpu_baseline_dict(m, cores, sample):
-    return {"value": m["full_job_value"], "unit": "k-mers/s", "cores": cores, "kind": "reference",
-            "as_run_value": m["as_run"], "marginal_value": m["marginal"], "fixed_s": m["fixed_s"], "sample_s": m["t"],
-            "full_job_estimate_s": m["full_job_estimate_s"],
-            "sample": f"first {sample} reads of the workload, abyss-bloom-dbg -j{cores} (unmodified reference), files on tmpfs; "
-                      f"{m['t']:.1f} s per run of which {m['fixed_s']:.1f} s do not depend on the reads (1-read run, same -b); value = "
-                      f"{N_READS} reads at the marginal rate + the fixed cost"}
+    d = {"value": m["as_run"], "unit": "k-mers/s", "cores": cores, "kind": "reference",
+         "marginal_value": m["marginal"], "fixed_s": m["fixed_s"], "sample_s": m["t"],
+         "sample": f"{sample} reads of a {m['genome']} bp genome (the workload's 40x coverage, error rate, k, kc, H, -b 8 GiB), "
+                   f"abyss-bloom-dbg -j{cores} (unmodified reference), files on tmpfs; {m['t']:.1f} s per run of which {m['fixed_s']:.1f} s "
+                   "do not depend on the reads (1-read run, same -b: zero-filling the filters, contigEndKmers.rehash(2^28))"}
+    if "full_run" in m:
+        d["full_job_measured"] = m["full_run"]
+    return d
 
 
 def reference_arm(args, rank, world):
@@ -175,16 +183,16 @@ def reference_arm(args, rank, world):
         return
     # bounded: the whole call stays within a few minutes whatever --steps / --warmup say
     runs = args.warmup + args.steps
-    sample = args.ref_reads if args.ref_reads else (4_000_000 if runs <= 6 else 2_000_000 if runs <= 12 else 1_000_000)
-    rs = ReadSet(SEED, GENOME, N_READS, L, ERR, paired=True)
-    m = reference_measurement(rs, sample, cores, args.steps, args.warmup)
+    sample = args.ref_reads if args.ref_reads else (4_000_000 if runs <= 3 else 2_000_000 if runs <= 6 else 1_000_000 if runs <= 12 else 500_000)
+    m = reference_measurement(sample, cores, args.steps, args.warmup)
     line = {
-        "impl": "reference", "metric": "k-mers/sec (Bloom insert + unitig extend)", "value": m["full_job_value"], "unit": "k-mers/s",
+        "impl": "reference", "metric": "k-mers/sec (Bloom insert + unitig extend)", "value": m["as_run"], "unit": "k-mers/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * m["t"], "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": workload_config(args, extra={"sample_reads": sample}),
+        "config": workload_config(args, extra={"sample_reads": sample, "sample_genome": m["genome"],
+                                               "sample_note": "bounded job of the same shape: 40x coverage of a smaller genome"}),
         "cpu_baseline": cpu_baseline_dict(m, cores, sample),
-        "e2e": {"value": m["full_job_value"], "unit": "k-mers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "e2e": {"value": m["as_run"], "unit": "k-mers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
@@ -384,7 +392,7 @@ def main():
     if not args.no_cpu_baseline and os.path.exists(REF_BIN) and world == 1:
         cores = os.cpu_count() or 1
         sample = args.ref_reads or 4_000_000
-        cpu = cpu_baseline_dict(reference_measurement(rs, min(sample, rs.n), cores, 1), cores, min(sample, rs.n))
+        cpu = cpu_baseline_dict(reference_measurement(min(sample, rs.n), cores, 1), cores, min(sample, rs.n))
 
     line = {
         "metric": "k-mers/sec (Bloom insert + unitig extend)", "value": value, "unit": "k-mers/s", "n_gpus": world,
