@@ -47,9 +47,9 @@ def _stale(target: str, deps) -> bool:
     return open(stamp).read().strip() != _digest(deps)
 
 
-def _mark(target: str, deps) -> None:
+def _mark(target: str, deps, digest: str | None = None) -> None:
     with open(target + ".stamp", "w") as f:
-        f.write(_digest(deps))
+        f.write(digest or _digest(deps))
 
 
 def _host_sources():
@@ -82,17 +82,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
     procs = []
     for src, (obj, deps) in _objects().items():
         if force or _stale(obj, deps):
+            digest = _digest(deps)  # of what the compiler is about to read (an edit during the build must not look built)
             cmd = [NVCC, *FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-c", "-o", obj, os.path.join(CSRC, src)]
-            procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-    for cmd, pr in procs:
+            procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True), obj, deps, digest))
+    for cmd, pr, obj, deps, digest in procs:
         out, _ = pr.communicate()
         if pr.returncode != 0:
             raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + out)
+        _mark(obj, deps, digest)
         if verbose:
             print(out)
-    for src, (obj, deps) in _objects().items():
-        if os.path.exists(obj):
-            _mark(obj, deps)
     objs = [o for o, _ in _objects().values()]
     if force or _stale(LIB, objs):
         cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static", "-Xcompiler", "-fPIC", "-o", LIB, *objs,

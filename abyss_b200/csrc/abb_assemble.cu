@@ -23,6 +23,7 @@
 // reference would have, while the expensive graph walks run thousands at a time.
 #include "abb_common.h"
 #include "abb_walk.cuh"
+#include <cooperative_groups.h>
 #include <cub/device/device_select.cuh>
 #include <thrust/iterator/counting_iterator.h>
 #include <algorithm>
@@ -33,6 +34,7 @@
 #include <vector>
 
 namespace abb {
+namespace cg = cooperative_groups;
 
 // ------------------------------------------------------------------------------------------
 // device context: the Ctx concept of abb_walk.cuh for one warp
@@ -918,9 +920,8 @@ constexpr unsigned kBigContig = 1u << 15;
  * A read whose first contig is >= cs has not been started: its "all k-mers assembled" test runs
  * here; otherwise its verdict is already in rcode[].
  */
-__global__ void __launch_bounds__(1024)
-k_replay(ReplayIO io, unsigned s0, unsigned cs, unsigned ce, const __grid_constant__ HashCfg cfg, unsigned k,
-         const uint8_t* __restrict__ counters, uint8_t* bits, EndSet ends)
+__device__ void replay_segment(const ReplayIO& io, unsigned s0, unsigned cs, unsigned ce, const HashCfg& cfg, unsigned k,
+                               const uint8_t* __restrict__ counters, uint8_t* bits, EndSet ends)
 {
 	__shared__ unsigned s_cov;
 	__shared__ int s_flag;
@@ -1032,13 +1033,10 @@ k_replay(ReplayIO io, unsigned s0, unsigned cs, unsigned ce, const __grid_consta
 	}
 }
 
-/** big contig c of speculated read s, step 1: redundant unless some k-mer is not yet assembled.
+/** big contig c, step 1 (whole grid): redundant unless some k-mer is not yet assembled.
  *  caccept[c] was zeroed by the host; any thread that finds a missing k-mer sets it. */
-__global__ void __launch_bounds__(256)
-k_big_check(ReplayIO io, unsigned s, unsigned c, const __grid_constant__ HashCfg cfg, const uint8_t* __restrict__ bits)
+__device__ void big_check(const ReplayIO& io, unsigned c, const HashCfg& cfg, const uint8_t* __restrict__ bits)
 {
-	if (__ldcg(io.rcode + s) != RC_GENERATED_CONTIGS)
-		return;
 	const uint64_t c0 = io.cslot[c];
 	const unsigned nk = (unsigned)(io.cslot[c + 1] - c0);
 	bool missing = false;
@@ -1054,13 +1052,9 @@ k_big_check(ReplayIO io, unsigned s, unsigned c, const __grid_constant__ HashCfg
 	if (__any_sync(0xffffffffu, missing) && (threadIdx.x & 31) == 0)
 		io.caccept[c] = 1;
 }
-/** step 2: if not redundant, mark its k-mers assembled and sum their counts (ccov[c] zeroed by the host) */
-__global__ void __launch_bounds__(256)
-k_big_apply(ReplayIO io, unsigned s, unsigned c, const __grid_constant__ HashCfg cfg, const uint8_t* __restrict__ counters,
-            uint8_t* bits)
+/** step 2 (whole grid): mark its k-mers assembled and sum their counts (ccov[c] zeroed by the host) */
+__device__ void big_apply(const ReplayIO& io, unsigned c, const HashCfg& cfg, const uint8_t* __restrict__ counters, uint8_t* bits)
 {
-	if (__ldcg(io.rcode + s) != RC_GENERATED_CONTIGS || __ldcg(io.caccept + c) == 0)
-		return;
 	const uint64_t c0 = io.cslot[c];
 	const unsigned nk = (unsigned)(io.cslot[c + 1] - c0);
 	unsigned cov = 0;
@@ -1079,6 +1073,43 @@ k_big_apply(ReplayIO io, unsigned s, unsigned c, const __grid_constant__ HashCfg
 		cov += __shfl_down_sync(0xffffffffu, cov, d);
 	if ((threadIdx.x & 31) == 0 && cov)
 		atomicAdd(io.ccov + c, cov);
+}
+
+/**
+ * K5: the whole ordered replay of one speculation round in ONE cooperative launch (round 1: one launch of a
+ * one-CTA kernel per stretch between big contigs plus two whole-grid launches per big contig, 5 400 launches per job).
+ * CTA 0 walks the reads in file order exactly like processRead's bookkeeping (replay_segment) up to the next big
+ * contig; there the whole grid checks and, if it is not redundant, applies it, between grid barriers.  big[b] = index
+ * of the b-th big contig, big_s[b] = the speculated read it belongs to.
+ */
+__global__ void __launch_bounds__(1024)
+k_replay_all(ReplayIO io, unsigned n_contigs, const unsigned* __restrict__ big, const unsigned* __restrict__ big_s, unsigned n_big,
+             const __grid_constant__ HashCfg cfg, unsigned k, const uint8_t* __restrict__ counters, uint8_t* bits, EndSet ends)
+{
+	cg::grid_group grid = cg::this_grid();
+	unsigned seg_s = 0, seg_c = 0;
+	for (unsigned b = 0; b <= n_big; ++b) {
+		const unsigned c_big = b < n_big ? big[b] : n_contigs;
+		if (blockIdx.x == 0)
+			replay_segment(io, seg_s, seg_c, c_big, cfg, k, counters, bits, ends);
+		__threadfence();
+		grid.sync();
+		if (b == n_big)
+			break;
+		const unsigned s_of = big_s[b];
+		if (__ldcg(io.rcode + s_of) == RC_GENERATED_CONTIGS) { // uniform over the grid
+			big_check(io, c_big, cfg, bits);
+			__threadfence();
+			grid.sync();
+			if (__ldcg(io.caccept + c_big) != 0) {
+				big_apply(io, c_big, cfg, counters, bits);
+				__threadfence();
+				grid.sync();
+			}
+		}
+		seg_s = s_of;
+		seg_c = c_big + 1;
+	}
 }
 
 } // namespace abb
@@ -1108,7 +1139,7 @@ struct abb_assembler {
 	// batch state (device)
 	DevBuf<uint8_t> bases, valid, codes, vis, scan_tmp, cseq, cvalid, rcode, caccept;
 	DevBuf<uint64_t> offs, slot_offs, h0, coffs, cslot, ch0;
-	DevBuf<unsigned> cand, spec, spec_cbeg, clen, ccov, status, seg_contig, seg_len;
+	DevBuf<unsigned> cand, spec, spec_cbeg, clen, ccov, status, seg_contig, seg_len, big_idx, big_spec;
 	DevBuf<uint64_t> seg_beg, seg_slot, rep_off;
 	DevBuf<ContigRec> recs, recs_sorted;
 	DevBuf<Frame> frames;
@@ -1630,6 +1661,8 @@ int speculate_round(abb_assembler* a, const std::vector<unsigned>& cand, size_t*
 		return ABB_OK;
 	++a->st_iterations;
 	a->st_speculated += spec.size();
+	const float round_walk0 = a->ms_walk, round_rep0 = a->ms_repeat, round_vis0 = a->ms_visited, round_replay0 = a->ms_replay;
+	const auto round_t0 = std::chrono::steady_clock::now();
 
 	// ---- K4: extend all speculated reads (tiles on), then the exact vertex-by-vertex fallback for
 	// reads whose tiled walk cycled or produced a path with a repeated vertex
@@ -1786,26 +1819,35 @@ int speculate_round(abb_assembler* a, const std::vector<unsigned>& cand, size_t*
 			ABB_CUDA(cudaMemsetAsync(a->caccept.p, 0, nc, st));
 			ABB_CUDA(cudaMemsetAsync(a->ccov.p, 0, nc * sizeof(unsigned), st));
 		}
-		// one-CTA replay between big contigs; big contigs use the whole grid
-		unsigned seg_s = 0, seg_c = 0; // next read / contig to replay
-		unsigned s_of = 0;             // read owning contig c while scanning
-		for (unsigned c = 0; c <= nc; ++c) {
-			const bool big = c < nc && clen[c] - f->k + 1 >= kBigContig;
-			if (!big && c < nc)
-				continue;
-			k_replay<<<1, 1024, 0, st>>>(io, seg_s, seg_c, c, f->cfg, f->k, f->d_data, a->assembled->d_data, ends);
+		// one cooperative launch replays the whole round (k_replay_all)
+		{
+			std::vector<unsigned> big, big_s;
+			unsigned s_of = 0;
+			for (unsigned c = 0; c < nc; ++c) {
+				if (clen[c] - f->k + 1 < kBigContig)
+					continue;
+				while (spec_cbeg[s_of + 1] <= c)
+					++s_of;
+				big.push_back(c);
+				big_s.push_back(s_of);
+			}
+			ABB_CHECK(h2d(a->big_idx, big, st));
+			ABB_CHECK(h2d(a->big_spec, big_s, st));
+			static int replay_grid = 0;
+			if (replay_grid == 0) {
+				int per_sm = 0, sms = 0;
+				ABB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_replay_all, 1024, 0));
+				ABB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, f->device));
+				replay_grid = std::max(1, per_sm) * sms;
+			}
+			unsigned n_big = (unsigned)big.size(), nc_arg = nc, k_arg = f->k;
+			const unsigned* d_big = a->big_idx.p;
+			const unsigned* d_big_s = a->big_spec.p;
+			const uint8_t* d_counters = f->d_data;
+			uint8_t* d_bits = a->assembled->d_data;
+			void* params[] = { &io, &nc_arg, &d_big, &d_big_s, &n_big, &f->cfg, &k_arg, &d_counters, &d_bits, &ends };
+			ABB_CUDA(cudaLaunchCooperativeKernel((void*)k_replay_all, dim3((unsigned)replay_grid), dim3(1024), params, 0, st));
 			++a->st_launches;
-			if (c == nc)
-				break;
-			while (spec_cbeg[s_of + 1] <= c)
-				++s_of;
-			const unsigned nkm = clen[c] - f->k + 1;
-			const unsigned g = std::min<unsigned>(blocks_for(nkm, 256), 148 * 8);
-			k_big_check<<<g, 256, 0, st>>>(io, s_of, c, f->cfg, a->assembled->d_data);
-			k_big_apply<<<g, 256, 0, st>>>(io, s_of, c, f->cfg, f->d_data, a->assembled->d_data);
-			a->st_launches += 2;
-			seg_s = s_of;
-			seg_c = c + 1;
 		}
 		ABB_CUDA(cudaGetLastError());
 		ABB_CUDA(cudaMemcpyAsync(rcode.data(), a->rcode.p, n_ok, cudaMemcpyDeviceToHost, st));
@@ -1864,6 +1906,17 @@ int speculate_round(abb_assembler* a, const std::vector<unsigned>& cand, size_t*
 		}
 	}
 	a->st_wasted += wasted;
+	if (getenv("ABB_ROUND_LOG")) { // tuning aid: one line per speculation round
+		unsigned long long longest = 0, accepted = 0;
+		for (unsigned c = 0; c < nc; ++c) {
+			longest = std::max<unsigned long long>(longest, clen[c]);
+			accepted += caccept[c] ? 1 : 0;
+		}
+		fprintf(stderr, "round %llu: speculated %u wasted %u contigs %u accepted %llu longest %llu | visited %.1f walk %.1f repeat %.1f replay %.1f ms, wall %.1f ms\n",
+		        (unsigned long long)a->st_iterations, n_ok, wasted, nc, accepted, longest, a->ms_visited - round_vis0, a->ms_walk - round_walk0,
+		        a->ms_repeat - round_rep0, a->ms_replay - round_replay0,
+		        std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - round_t0).count());
+	}
 	// adapt the amount of speculation: grow while most speculated reads were really needed
 	if (n_ok == n_spec && !a->spec_fixed) {
 		if (wasted * 2 <= n_ok)
@@ -1975,6 +2028,8 @@ int abb_assembler_destroy(abb_assembler* a)
 	cudaFree(a->d_marker_set);
 	a->rep_off.release();
 	a->gather.release();
+	a->big_idx.release();
+	a->big_spec.release();
 	a->tile_export.release();
 	a->seg_contig.release(); a->seg_len.release(); a->seg_beg.release(); a->seg_slot.release();
 	a->new_markers.release(); a->rep_tab.release(); a->stage_bases.release(); a->rep_flag.release(); a->stage_hashes.release();
