@@ -62,6 +62,18 @@ struct WarpCtx {
 	const unsigned* tile_tab; // open addressing: tile index + 1, 0 = empty
 	unsigned tile_mask;
 
+	// profiling hook (ABB_ROUND_LOG): clock64 ticks between the stages of a walk, accumulated per speculated read
+	unsigned long long* dbg = nullptr;
+	long long t_last = 0;
+	__device__ void tick(int slot)
+	{
+		if (!dbg)
+			return;
+		const long long now = clock64();
+		if (slot >= 0 && lane == 0)
+			dbg[slot] += (unsigned long long)(now - t_last);
+		t_last = now;
+	}
 	__device__ bool tiles_enabled() const { return tile_tab != nullptr; }
 	__device__ const TileRec* tile_lookup(uint64_t key, unsigned cls) const
 	{
@@ -243,7 +255,8 @@ struct WarpCtx {
 		}
 		__syncwarp();
 	}
-	__device__ void mark_covered(const PathSet& ps, const uint64_t* rh, uint8_t* cov, unsigned nk, const ContigOut& o)
+	__device__ void mark_covered(const PathSet& ps, const uint64_t* rh, uint8_t* cov, unsigned nk, const ContigOut& o,
+	                             const uint8_t* read_ascii, unsigned seed_i)
 	{
 		for (unsigned j = lane; j < nk; j += 32) {
 			if (cov[j])
@@ -258,8 +271,49 @@ struct WarpCtx {
 		__syncwarp();
 		if (o.tiles_left.n + o.tiles_right.n == 0)
 			return;
-		// the spliced tiles' vertices are not in the PathSet: stream their hashes against a small
-		// table of the read's k-mer hashes
+		// The spliced tiles' vertices are not in the PathSet.  Fast path (no spaced seed): the contig string holds the
+		// seed k-mer at raw[seed_off] in the read's orientation, so as long as the read and the contig agree base for base
+		// away from the seed, the read's k-mers ARE the contig's vertices at those offsets.  A read that follows its unitig
+		// (the normal case: every k-mer of a candidate read is solid) is settled by ~150 byte compares; only k-mers the
+		// comparison does not reach fall through to the exact scan of all tile hashes below (it took 230 of the 266 ms of
+		// the slowest walk of the 50 M-read job before this shortcut).
+		if (!rt.nmask && o.raw) {
+			const unsigned maxf = min(nk - 1 - seed_i, o.raw_len - (o.seed_off + k));
+			unsigned mf = maxf;
+			for (unsigned base = 0; base < maxf; base += 32) {
+				const unsigned t = base + lane;
+				const bool bad = t < maxf && base_code(read_ascii[seed_i + k + t]) != *(const volatile uint8_t*)(o.raw + o.seed_off + k + t);
+				const unsigned m = __ballot_sync(0xffffffffu, bad);
+				if (m) {
+					mf = base + __ffs(m) - 1;
+					break;
+				}
+			}
+			const unsigned maxb = min(seed_i, o.seed_off);
+			unsigned mb = maxb;
+			for (unsigned base = 0; base < maxb; base += 32) {
+				const unsigned t = base + lane;
+				const bool bad = t < maxb && base_code(read_ascii[seed_i - 1 - t]) != *(const volatile uint8_t*)(o.raw + o.seed_off - 1 - t);
+				const unsigned m = __ballot_sync(0xffffffffu, bad);
+				if (m) {
+					mb = base + __ffs(m) - 1;
+					break;
+				}
+			}
+			bool all = true;
+			for (unsigned j = lane; j < nk; j += 32) {
+				if (!cov[j] && j + mb >= seed_i && j <= seed_i + mf) {
+					const uint64_t key = rh[j];
+					if (!((o.popped_front && key == o.front_h) || (o.popped_back && key == o.back_h)))
+						cov[j] = 1;
+				}
+				all &= cov[j] != 0;
+			}
+			if (__all_sync(0xffffffffu, all))
+				return;
+			__syncwarp();
+		}
+		// exact fallback: stream the tiles' hashes against a small table of the read's k-mer hashes
 		unsigned cap = 64;
 		while (cap < 2 * nk)
 			cap <<= 1;
@@ -278,20 +332,32 @@ struct WarpCtx {
 		__syncwarp();
 		for (int side = 0; side < 2; ++side) {
 			const U32Vec& tv = side ? o.tiles_right : o.tiles_left;
-			for (unsigned ti = lane; ti < tv.n; ti += 32) { // one lane per tile: 32 independent streams
+			// the warp sweeps one tile at a time with coalesced loads (8 hashes per lane in flight); the next tile's record
+			// and hashes are prefetched into L2 meanwhile, so a tile costs about one L2 round trip
+			for (unsigned ti = 0; ti < tv.n; ++ti) {
 				const TileRec* T = tile_recs + tv.p[ti];
+				if (ti + 2 < tv.n && lane == 0)
+					prefetch(tile_recs + tv.p[ti + 2]);
+				if (ti + 1 < tv.n) {
+					const TileRec* Tn = tile_recs + tv.p[ti + 1];
+					const uint64_t* thn = Tn->hashes;
+					if (lane * 16u < Tn->n)
+						prefetch(thn + lane * 16u);
+				}
 				const uint64_t* __restrict__ th = T->hashes;
 				const unsigned tn = T->n;
-				for (unsigned i0 = 0; i0 < tn; i0 += 8) {
+				for (unsigned i0 = 0; i0 < tn; i0 += 256) {
 					uint64_t kv[8];
 #pragma unroll
-					for (int j = 0; j < 8; ++j) // 8 independent loads before any probe
-						kv[j] = i0 + j < tn ? th[i0 + j] : 0;
+					for (int j = 0; j < 8; ++j) { // 8 independent coalesced loads before any probe
+						const unsigned idx = i0 + lane + 32u * j;
+						kv[j] = idx < tn ? th[idx] : 0;
+					}
 #pragma unroll
 					for (int j = 0; j < 8; ++j) {
 						uint64_t key = kv[j];
-						if (i0 + j >= tn)
-							break;
+						if (i0 + lane + 32u * j >= tn)
+							continue;
 						if ((o.popped_front && key == o.front_h) || (o.popped_back && key == o.back_h))
 							continue;
 						key = key ? key : 1;
@@ -520,12 +586,13 @@ __global__ void __launch_bounds__(kWalkWarps * 32)
 k_extend(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offs, const unsigned* __restrict__ spec, unsigned n_spec,
          WalkCfg w, const __grid_constant__ HashCfg cfg, Frame* frames, uint64_t* look, uint8_t* arena,
          unsigned long long arena_size, unsigned long long* arena_top, ContigRec* recs, unsigned* nrecs, unsigned rec_cap,
-         unsigned* __restrict__ status, TileView tv)
+         unsigned* __restrict__ status, TileView tv, unsigned long long* dbg)
 {
 	const unsigned gwarp = blockIdx.x * kWalkWarps + (threadIdx.x >> 5);
 	if (gwarp >= n_spec)
 		return;
 	WarpCtx c = make_ctx(w, &cfg, frames, look, gwarp, arena, arena_size, arena_top);
+	c.dbg = dbg ? dbg + 4ull * gwarp : nullptr;
 	c.tile_recs = tv.recs;
 	c.tile_tab = tv.tab;
 	c.tile_mask = tv.mask;
@@ -1167,7 +1234,7 @@ struct abb_assembler {
 	unsigned long long* d_tile_pool_top = nullptr;
 	unsigned long long* d_marker_set = nullptr;
 	unsigned marker_set_mask = 0;
-	DevBuf<unsigned long long> new_markers, rep_tab;
+	DevBuf<unsigned long long> new_markers, rep_tab, walk_dbg;
 	DevBuf<TileRec> tile_export;
 	DevBuf<uint8_t> stage_bases, rep_flag;
 	DevBuf<uint64_t> stage_hashes;
@@ -1439,7 +1506,14 @@ int produce_tiles(abb_assembler* a, uint64_t n_reads, uint64_t n_slots)
 	if (nm) {
 		int sms = 148;
 		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, f->device);
-		const unsigned grid = (unsigned)std::min<uint64_t>(blocks_for((uint64_t)nm * 4, kWalkWarps), (uint64_t)sms * 4);
+		// persistent warps pulling (marker, orientation, direction) items from a counter: as many CTAs as fit
+		static int tiles_per_sm = 0;
+		if (tiles_per_sm == 0) {
+			int n = 0;
+			ABB_DISPATCH_KW(a->kw, (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_make_tiles<KW>, kWalkWarps * 32, 0)));
+			tiles_per_sm = std::max(1, n);
+		}
+		const unsigned grid = (unsigned)std::min<uint64_t>(blocks_for((uint64_t)nm * 4, kWalkWarps), (uint64_t)sms * tiles_per_sm);
 		const unsigned warps = grid * kWalkWarps;
 		ABB_CHECK(ensure_scratch(a, warps));
 		ABB_CHECK(a->stage_bases.reserve((size_t)warps * kTileCap));
@@ -1492,6 +1566,12 @@ int run_extend(abb_assembler* a, unsigned n_spec, bool use_tiles, bool keep_aren
 	}
 	for (;;) {
 		ABB_CHECK(a->recs.reserve(rec_cap));
+		unsigned long long* dbg = nullptr;
+		if (getenv("ABB_ROUND_LOG")) {
+			ABB_CHECK(a->walk_dbg.reserve(4ull * n_spec));
+			ABB_CUDA(cudaMemsetAsync(a->walk_dbg.p, 0, 4ull * n_spec * sizeof(unsigned long long), st));
+			dbg = a->walk_dbg.p;
+		}
 		ABB_CHECK(ensure_arena(a, a->arena_size ? a->arena_size : std::max(kArenaDefault, g_arena_hint)));
 		ABB_CUDA(cudaMemcpyAsync(a->d_arena_top, &arena_mark, sizeof arena_mark, cudaMemcpyHostToDevice, st));
 		ABB_CUDA(cudaMemsetAsync(a->d_nrecs, 0, sizeof(unsigned), st));
@@ -1500,7 +1580,7 @@ int run_extend(abb_assembler* a, unsigned n_spec, bool use_tiles, bool keep_aren
 		cudaEventRecord(a->ev2[0], st);
 		ABB_DISPATCH_KW(a->kw, (k_extend<KW><<<blocks_for(n_spec, kWalkWarps), kWalkWarps * 32, 0, st>>>(
 		                           a->cur_bases, a->cur_offs, a->spec.p, n_spec, w, f->cfg, a->frames.p, a->look.p, a->d_arena, a->arena_size,
-		                           a->d_arena_top, a->recs.p, a->d_nrecs, rec_cap, a->status.p, tv)));
+		                           a->d_arena_top, a->recs.p, a->d_nrecs, rec_cap, a->status.p, tv, dbg)));
 		ABB_CUDA(cudaGetLastError());
 		cudaEventRecord(a->ev2[1], st);
 		++a->st_launches;
@@ -1512,6 +1592,21 @@ int run_extend(abb_assembler* a, unsigned n_spec, bool use_tiles, bool keep_aren
 			float ms = 0;
 			cudaEventElapsedTime(&ms, a->ev2[0], a->ev2[1]);
 			a->ms_walk += ms;
+		}
+		if (dbg) { // the slowest walk of this launch, by stage (SM clock ticks -> ms at 1.9 GHz)
+			std::vector<unsigned long long> h(4ull * n_spec);
+			cudaMemcpy(h.data(), dbg, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+			unsigned best = 0;
+			unsigned long long bt = 0;
+			for (unsigned i = 0; i < n_spec; ++i) {
+				const unsigned long long t = h[4 * i] + h[4 * i + 1] + h[4 * i + 2] + h[4 * i + 3];
+				if (t > bt) {
+					bt = t;
+					best = i;
+				}
+			}
+			fprintf(stderr, "  k_extend %u walkers: slowest #%u extend-left %.1f extend-right %.1f materialise+trim %.1f mark_covered %.1f ms\n", n_spec, best,
+			        h[4 * best] / 1.9e6, h[4 * best + 1] / 1.9e6, h[4 * best + 2] / 1.9e6, h[4 * best + 3] / 1.9e6);
 		}
 		if (nrecs > rec_cap) { // record buffer too small: rerun with room for everything
 			rec_cap = nrecs + nrecs / 4 + 16;
@@ -2028,6 +2123,7 @@ int abb_assembler_destroy(abb_assembler* a)
 	cudaFree(a->d_marker_set);
 	a->rep_off.release();
 	a->gather.release();
+	a->walk_dbg.release();
 	a->big_idx.release();
 	a->big_spec.release();
 	a->tile_export.release();

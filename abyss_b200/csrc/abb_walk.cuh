@@ -385,7 +385,7 @@ ABB_HD unsigned ctz4(unsigned m) { return (m & 1) ? 0 : (m & 2) ? 1 : (m & 4) ? 
  *   void copy8(dst, src, n), copy8_rev(dst, src, n)   cooperative byte copies (rev: dst[i] = src[n-1-i])
  *   void rehash(old, oldcap, new, newcap)              cooperative PathSet growth
  *   bool tiles_enabled(); const TileRec* tile_lookup(key, cls); const TileRec* tile_at(idx); void prefetch(const void*);
- *   uint32_t tile_index(const TileRec*); void wr32(uint32_t*, uint32_t)
+ *   uint32_t tile_index(const TileRec*); void wr32(uint32_t*, uint32_t); void tick(int) (profiling hook, may be empty)
  *   void mark_covered(ps, rh, cov, nk, contig)         cooperative: flag read k-mers that lie on the contig path
  *   Frame* frames; uint64_t* look;   per-warp scratch
  */
@@ -1000,6 +1000,8 @@ struct ContigOut {
 	unsigned psize;  // vertices before trimming (contigPath.size() as isTip sees it)
 	ExtCode left, right;
 	unsigned left_n, right_n; // vertices the two extendPath calls added (ContigRecord left/rightExtensionResult.first)
+	const uint8_t* raw;       // pathToSeq of the UNTRIMMED path (reversed left + seed + right), raw_len = psize + k - 1 codes
+	unsigned raw_len, seed_off; // the seed k-mer starts at raw[seed_off], in the orientation the read holds it
 	bool tip;        // isTip: not output, but its k-mers still count as assembled for this read
 	bool popped_front, popped_back; // a real path vertex (not a pushed duplicate) was trimmed off that end
 	uint64_t front_h, back_h;       // canonical hashes of the trimmed-off vertices
@@ -1023,10 +1025,13 @@ ABB_HD bool extend_seed(Ctx& c, const Vtx<KW>& seed, PathSet& ps, ContigOut* o)
 	o->pushed_front = o->pushed_back = false;
 	unsigned psize = 1;
 	Vtx<KW> front = seed, back = seed;
+	c.tick(-1);
 	o->left = extend_dir(c, front, REV, &psize, left, ps, &ok, o->tiles_left);
+	c.tick(0);
 	if (!ok || c.failed())
 		return false;
 	o->right = extend_dir(c, back, FWD, &psize, right, ps, &ok, o->tiles_right);
+	c.tick(1);
 	if (!ok || c.failed())
 		return false;
 	o->psize = psize;
@@ -1050,6 +1055,9 @@ ABB_HD bool extend_seed(Ctx& c, const Vtx<KW>& seed, PathSet& ps, ContigOut* o)
 	c.sync();
 	o->seq = s;
 	o->len = n;
+	o->raw = s;
+	o->raw_len = n;
+	o->seed_off = left.n;
 	if (o->tip || psize == 1) // trimBranchKmers returns immediately for a single vertex (bloom-dbg.h:727-728)
 		return true;
 
@@ -1175,9 +1183,11 @@ ABB_HD bool walk_read(Ctx& c, const uint8_t* read_ascii, unsigned L, Emit& emit)
 		ContigOut o;
 		if (!extend_seed(c, rv, ps, &o) || c.failed())
 			return false;
+		c.tick(2);
 		if (!o.tip)
 			emit(c, i, o);
-		c.mark_covered(ps, rh, cov, nk, o);
+		c.mark_covered(ps, rh, cov, nk, o, read_ascii, i);
+		c.tick(3);
 	}
 	return !c.failed();
 }

@@ -88,6 +88,7 @@ struct HostCtx {
 	uint32_t tile_index(const TileRec* t) const { return (uint32_t)(t - tile_recs.data()); }
 	const TileRec* tile_at(uint32_t idx) const { return &tile_recs[idx]; }
 	void prefetch(const void*) const {}
+	void tick(int) {}
 	void wr32(uint32_t* p, uint32_t v) { *p = v; }
 	uint64_t rd64(const uint64_t* p) { return *p; }
 	void wr64(uint64_t* p, uint64_t v) { *p = v; }
@@ -130,7 +131,7 @@ struct HostCtx {
 				n[t] = o[s];
 			}
 	}
-	void mark_covered(const PathSet& ps, const uint64_t* rh, uint8_t* cov, unsigned nk, const ContigOut& o)
+	void mark_covered(const PathSet& ps, const uint64_t* rh, uint8_t* cov, unsigned nk, const ContigOut& o, const uint8_t* = nullptr, unsigned = 0)
 	{
 		std::unordered_set<uint64_t> tilev;
 		for (int side = 0; side < 2; ++side) {
