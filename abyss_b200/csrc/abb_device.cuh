@@ -128,11 +128,13 @@ ABB_HD HashPair roll_left(HashPair h, const RollTab& t, unsigned out, unsigned i
 	return r;
 }
 
-// ---- exact n % d for an invariant 64-bit divisor d (Lemire/Granlund-Montgomery fastmod) ------
-// M = floor((2^128 - 1) / d) + 1; q = floor(M * n / 2^128) == n / d for every 64-bit n when
-// d >= 2 (tests/test_host_arith.py checks against % on random and adversarial values).
+// ---- exact n % d for an invariant 64-bit divisor d ------------------------------------------
+// m = floor(2^64 / d) (d >= 2).  q = floor(n * m / 2^64) is floor(n / d) or one less (n * m / 2^64 > n / d - 1 because
+// n < 2^64 and 2^64 - m * d < d), so r = n - q * d lies in [0, 2d) and one conditional subtraction makes it exact.
+// One 64x64 high multiply + one low multiply (round 1 used a 128-bit reciprocal: two high multiplies + carries);
+// this is the inner loop of every Bloom probe.  tests/test_host_arith.py checks it against % on random and adversarial values.
 struct FastMod {
-	uint64_t d, m_hi, m_lo;
+	uint64_t d, m_hi, m_lo; // m_hi = floor(2^64 / d); m_lo unused (kept for layout compatibility)
 };
 
 #if defined(__CUDA_ARCH__)
@@ -143,23 +145,17 @@ inline uint64_t mulhi64(uint64_t a, uint64_t b) { return (uint64_t)(((unsigned _
 
 ABB_HD uint64_t fastmod_u64(uint64_t n, const FastMod& f)
 {
-	// (M * n) >> 128, M = m_hi:m_lo
-	uint64_t a_hi = mulhi64(f.m_lo, n);
-	uint64_t b_lo = f.m_hi * n;
-	uint64_t b_hi = mulhi64(f.m_hi, n);
-	uint64_t s = b_lo + a_hi;
-	uint64_t q = b_hi + (s < b_lo ? 1u : 0u);
-	return n - q * f.d;
+	const uint64_t q = mulhi64(n, f.m_hi);
+	const uint64_t r = n - q * f.d;
+	return r >= f.d ? r - f.d : r;
 }
 
 inline FastMod make_fastmod(uint64_t d) // host only
 {
 	FastMod f;
 	f.d = d;
-	unsigned __int128 all1 = ~(unsigned __int128)0;
-	unsigned __int128 M = all1 / d + 1; // d >= 2 so this does not wrap
-	f.m_hi = (uint64_t)(M >> 64);
-	f.m_lo = (uint64_t)M;
+	f.m_hi = (uint64_t)((((unsigned __int128)1) << 64) / d); // d >= 2
+	f.m_lo = 0;
 	return f;
 }
 
