@@ -71,10 +71,11 @@ static FilterView view_of(const abb_filter* f)
 	return v;
 }
 
-/** conflict-map size: 2^26 two-bit entries (16 MiB per map; both maps are pinned in L2 while the insert runs,
- *  set_l2_policy); with the default window of 2^17 slots 3.2 % of the slots see an alias and are carried.  Exact (no
- *  aliases) for filters of up to 2^26 positions.  ABB_MAP_LOG2 overrides (tuning). */
-static uint64_t map_entries_for(uint64_t filter_size, unsigned lg = 26)
+/** conflict-map size: 2^25 two-bit entries (8 MiB per map; the three rotating maps are pinned in L2 while the insert
+ *  runs, set_l2_policy); with the default window of 2^17 slots 6.4 % of the slots see an alias and are carried (2^26
+ *  halves that and measured 3 % slower: the maps compete with the counter sectors for L2).  Exact (no aliases) for
+ *  filters of up to 2^25 positions.  ABB_MAP_LOG2 overrides (tuning). */
+static uint64_t map_entries_for(uint64_t filter_size, unsigned lg = 25)
 {
 	if (const char* e = getenv("ABB_MAP_LOG2")) {
 		const int v = atoi(e);
@@ -94,15 +95,15 @@ static unsigned age_windows_for(uint64_t window)
 /** make sure the ordered-insert workspace exists for the current window size and hash count */
 static int ensure_workspace(abb_filter* f)
 {
-	const uint64_t want_entries = map_entries_for(f->size, f->map_log2 ? f->map_log2 : 26);
+	const uint64_t want_entries = map_entries_for(f->size, f->map_log2 ? f->map_log2 : 25);
 	if (f->d_carry && f->ws_window == f->window && f->ws_H == f->H && f->map_entries == want_entries)
 		return ABB_OK;
 	cudaFree(f->d_map[0]); // one allocation holds both maps (one L2 access-policy window covers them)
 	for (int i = 0; i < 2; ++i) {
 		cudaFree(f->d_tags2[i]);
-		f->d_map[i] = nullptr;
 		f->d_tags2[i] = nullptr;
 	}
+	f->d_map[0] = f->d_map[1] = f->d_map[2] = nullptr;
 	cudaFree(f->d_carry);
 	cudaFree(f->d_slotbits);
 	f->d_carry = nullptr;
@@ -112,9 +113,10 @@ static int ensure_workspace(abb_filter* f)
 	// at most kCarryLanes carried slots reserve H positions each; load factor <= 1/8.  Only a prefix sized to the
 	// carried slots of a window is in use (tag_mask_for)
 	f->tag_slots = next_pow2(8ULL * kCarryLanes * f->H);
-	ABB_CUDA(cudaMalloc((void**)&f->d_map[0], 2 * map_bytes));
-	ABB_CUDA(cudaMemsetAsync(f->d_map[0], 0, 2 * map_bytes, f->stream));
+	ABB_CUDA(cudaMalloc((void**)&f->d_map[0], 3 * map_bytes));
+	ABB_CUDA(cudaMemsetAsync(f->d_map[0], 0, 3 * map_bytes, f->stream));
 	f->d_map[1] = f->d_map[0] + map_bytes / sizeof(unsigned);
+	f->d_map[2] = f->d_map[1] + map_bytes / sizeof(unsigned);
 	for (int i = 0; i < 2; ++i) {
 		ABB_CUDA(cudaMalloc((void**)&f->d_tags2[i], f->tag_slots * sizeof(unsigned long long)));
 		ABB_CUDA(cudaMemsetAsync(f->d_tags2[i], 0, f->tag_slots * sizeof(unsigned long long), f->stream));
@@ -163,7 +165,7 @@ static void set_l2_policy(abb_filter* f, bool on)
 		int max_persist = 0, max_window = 0;
 		cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, f->device);
 		cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, f->device);
-		const size_t bytes = 2 * std::max<size_t>(f->map_entries / 4, 256);
+		const size_t bytes = 3 * std::max<size_t>(f->map_entries / 4, 256);
 		if (max_persist <= 0 || max_window <= 0)
 			return;
 		cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>(bytes, (size_t)max_persist));
@@ -227,9 +229,11 @@ static int ordered_insert(abb_filter* f, const uint64_t* d_hashes, const uint8_t
 	a.w_begin = 0;
 	a.n_windows = (unsigned)n_windows;
 	a.cfg = f->cfg;
-	for (int i = 0; i < 2; ++i) {
+	for (int i = 0; i < 3; ++i) {
 		a.map[i].w = f->d_map[i];
 		a.map[i].mask = f->map_entries - 1;
+	}
+	for (int i = 0; i < 2; ++i) {
 		a.tags[i] = f->d_tags2[i];
 		a.carry[i] = f->d_carry + (uint64_t)i * cap;
 	}
@@ -241,8 +245,9 @@ static int ordered_insert(abb_filter* f, const uint64_t* d_hashes, const uint8_t
 	a.stats = f->d_stats;
 	a.dbg = getenv("ABB_DBG") ? (unsigned)atoi(getenv("ABB_DBG")) : 0u;
 	uint64_t* sorted = f->d_carry + 2 * cap;
-	// both tag tables and the control block start clean (the maps are left clean by every call)
+	// the maps, both tag tables and the control block start clean
 	ABB_CUDA(cudaMemsetAsync(f->d_ctl, 0, sizeof(InsertCtl), st));
+	ABB_CUDA(cudaMemsetAsync(f->d_map[0], 0, 3 * std::max<size_t>(f->map_entries / 4, 256), st));
 	for (int i = 0; i < 2; ++i)
 		ABB_CUDA(cudaMemsetAsync(f->d_tags2[i], 0, f->tag_slots * sizeof(unsigned long long), st));
 	const bool counting = f->kind == ABB_COUNTING;
@@ -597,6 +602,7 @@ static int sharded_ordered_insert(abb_filter* f, abb_comm* c, const uint64_t* d_
 		ABB_CUDA(cudaMemcpyAsync(ctl, &init, sizeof init, cudaMemcpyHostToDevice, st));
 		ABB_CUDA(cudaMemsetAsync(d_nout, 0, 4 * sizeof(unsigned), st));
 	}
+	ABB_CUDA(cudaMemsetAsync(f->d_map[0], 0, 3 * map_bytes, st)); // the maps start clean
 	unsigned n_in = 0; // host copy of the carry length (identical on every rank)
 	uint64_t oldest = 0;
 	int in = 0, p = 0;

@@ -105,7 +105,7 @@ struct abb_filter {
 	unsigned ws_H = 0;
 	uint64_t map_entries = 0; // two-bit entries per conflict map (power of two)
 	unsigned map_log2 = 0;    // 0 = default size
-	unsigned* d_map[2] = { nullptr, nullptr };
+	unsigned* d_map[3] = { nullptr, nullptr, nullptr }; // one allocation
 	unsigned long long* d_tags2[2] = { nullptr, nullptr }; // tag tables of the carried slots (alternating windows)
 	uint64_t tag_slots = 0;
 	uint64_t* d_carry = nullptr;    // two carry lists and the drain's sorted list, (window + kCarryLanes) slots each

@@ -392,6 +392,27 @@ ABB_D void map_mark(const ConflictMap& m, uint64_t pos)
 	if (((old >> sh) & 3u) == 1u)
 		atomicOr(&m.w[e >> 4], 2u << sh);
 }
+/** the marks of all H positions of a slot: the H first atomics are independent and in flight together; only then are
+ *  their return values looked at (a mark issued per position would serialise H L2 round trips per thread) */
+template <int MAXH>
+ABB_D void map_mark_all(const ConflictMap& m, const uint64_t* pos, unsigned H)
+{
+	unsigned old[MAXH];
+#pragma unroll
+	for (int i = 0; i < MAXH; ++i)
+		if (i < (int)H) {
+			const uint64_t e = pos[i] & m.mask;
+			old[i] = atomicOr(&m.w[e >> 4], 1u << ((unsigned)(e & 15) * 2));
+		}
+#pragma unroll
+	for (int i = 0; i < MAXH; ++i)
+		if (i < (int)H) {
+			const uint64_t e = pos[i] & m.mask;
+			const unsigned sh = (unsigned)(e & 15) * 2;
+			if (((old[i] >> sh) & 3u) == 1u)
+				atomicOr(&m.w[e >> 4], 2u << sh);
+		}
+}
 ABB_D void map_mark_carried(const ConflictMap& m, uint64_t pos)
 {
 	const uint64_t e = pos & m.mask;
@@ -441,7 +462,7 @@ struct InsertArgs {
 	unsigned window;        // W
 	unsigned w_begin, n_windows;
 	HashCfg cfg;
-	ConflictMap map[2];
+	ConflictMap map[3];     // window w reads map[w % 3], marks map[(w+1) % 3] and clears map[(w+2) % 3] (read by window w-1)
 	unsigned long long* tags[2];
 	unsigned tag_cap;       // entries allocated per tag table (power of two)
 	FilterView f;
@@ -464,10 +485,10 @@ ABB_D unsigned tag_mask_for(unsigned n_carried, unsigned H, unsigned cap)
 /**
  * K2: the persistent window kernel (cooperative launch, one CTA set resident for a whole chunk of windows).
  * Window w, phase A: the carried slots (exact ownership through tags[w & 1]) and the new slots [w0, w0 + n)
- * (independent unless one of their entries in map[w & 1] was touched again) apply or are put on the other carry
- * list; the same threads mark the slots of window w + 1 in map[(w+1) & 1] and clear the tag table of window w - 1.
- * Grid barrier.  Phase B: map[w & 1] is cleared, the slots just carried reserve their positions in tags[(w+1) & 1]
- * and mark them "touched again" in map[(w+1) & 1].  Grid barrier.  The counter loads are issued before the map / tag
+ * (independent unless one of their entries in the window's map was touched again) apply or are put on the other carry
+ * list; the same threads mark the slots of window w + 1 in the next map and clear the tag table and map of window w - 1.
+ * Grid barrier.  Phase B: the slots just carried reserve their positions in tags[(w+1) & 1] and mark them "touched
+ * again" in the next window's map.  Grid barrier.  (Three maps rotate: the one window w-1 read is cleared during phase A.)  The counter loads are issued before the map / tag
  * probes so that the HBM round trip overlaps the L2 round trip.  The kernel returns early (ctl->resume) when the
  * pending slots need the serial drain.
  */
@@ -487,15 +508,15 @@ k_insert_windows(const InsertArgs a)
 		for (uint64_t t = gtid; t < n0; t += T)
 			if (!a.valid || a.valid[t]) {
 				slot_positions<LITERAL, MAXH>(a.hashes, t, a.cfg, pos);
-#pragma unroll
-				for (int i = 0; i < MAXH; ++i)
-					if (i < (int)H)
-						map_mark(a.map[0], pos[i]);
+				map_mark_all<MAXH>(a.map[0], pos, H);
 			}
 		grid.sync();
 	}
 	for (unsigned w = a.w_begin; w < a.n_windows; ++w) {
 		const int in = (int)(w & 1), out = 1 - in;
+		const ConflictMap& mcur = a.map[w % 3];
+		const ConflictMap& mnext = a.map[(w + 1) % 3];
+		const ConflictMap& mold = a.map[(w + 2) % 3];
 		const uint64_t w0 = (uint64_t)w * W, w1 = w0 + W;
 		const unsigned n = (unsigned)min(W, a.n_slots - w0);
 		const unsigned n_next = w + 1 < a.n_windows ? (unsigned)min(W, a.n_slots - w1) : 0u;
@@ -555,14 +576,10 @@ k_insert_windows(const InsertArgs a)
 #pragma unroll
 				for (int i = 0; i < MAXH; ++i)
 					if (i < (int)H)
-						again |= map_get(a.map[in], pos[i]);
+						again |= map_get(mcur, pos[i]);
 			}
-			if (do_mark && !(a.dbg & 1u)) {
-#pragma unroll
-				for (int i = 0; i < MAXH; ++i)
-					if (i < (int)H)
-						map_mark(a.map[out], pos2[i]);
-			}
+			if (do_mark && !(a.dbg & 1u))
+				map_mark_all<MAXH>(mnext, pos2, H);
 			if (do_apply) {
 				if (!(again & 2u))
 					apply_alone<KIND, MAXH>(a.f, pos, v, H);
@@ -574,19 +591,18 @@ k_insert_windows(const InsertArgs a)
 		}
 		for (uint64_t i = gtid; i <= old_mask_out; i += T) // the tag table of window w - 1
 			a.tags[out][i] = 0;
+		if (!(a.dbg & 4u)) { // ... and its conflict map
+			uint4* mw = reinterpret_cast<uint4*>(mold.w);
+			const uint64_t words4 = (mold.mask + 1) / 64; // 16 entries per word, 4 words per uint4
+			for (uint64_t i = gtid; i < words4; i += T)
+				mw[i] = make_uint4(0, 0, 0, 0);
+		}
 		if (!(a.dbg & 16u))
 			grid.sync(); // (a grid barrier orders memory itself)
 		// ---- phase B
 		const unsigned n_out = a.ctl->n_carry[out];
 		const bool stop = n_out > kCarryLanes || a.ctl->old_flag != 0;
 		const bool last = w + 1 == a.n_windows;
-		{
-			uint4* mw = reinterpret_cast<uint4*>(a.map[in].w);
-			const uint64_t words4 = (a.map[in].mask + 1) / 64; // 16 entries per word, 4 words per uint4
-			if (!(a.dbg & 4u))
-				for (uint64_t i = gtid; i < words4; i += T)
-					mw[i] = make_uint4(0, 0, 0, 0);
-		}
 		const unsigned new_mask = tag_mask_for(n_out, H, a.tag_cap);
 		if (!stop && !last && !(a.dbg & 8u)) {
 			const TagTable tnext = { a.tags[out], new_mask };
@@ -598,7 +614,7 @@ k_insert_windows(const InsertArgs a)
 				for (int j = 0; j < MAXH; ++j)
 					if (j < (int)H) {
 						tag_reserve(tnext, pos[j], prio);
-						map_mark_carried(a.map[out], pos[j]);
+						map_mark_carried(mnext, pos[j]);
 					}
 			}
 		}

@@ -100,10 +100,21 @@ k_sh_gather(const uint64_t* __restrict__ hashes, const uint8_t* __restrict__ val
 		const uint64_t s = w1 + t;
 		if (!valid || valid[s]) {
 			slot_positions<LITERAL, MAXH>(hashes, s, cfg, pos);
+			unsigned old[MAXH];
+#pragma unroll
+			for (int i = 0; i < MAXH; ++i) // independent atomics first, their return values afterwards
+				if (i < (int)cfg.H && sh.own(pos[i])) {
+					const uint64_t e = pos[i] & next.mask;
+					old[i] = atomicOr(&next.w[e >> 4], 1u << ((unsigned)(e & 15) * 2));
+				}
 #pragma unroll
 			for (int i = 0; i < MAXH; ++i)
-				if (i < (int)cfg.H && sh.own(pos[i]))
-					map_mark(next, pos[i]);
+				if (i < (int)cfg.H && sh.own(pos[i])) {
+					const uint64_t e = pos[i] & next.mask;
+					const unsigned shf = (unsigned)(e & 15) * 2;
+					if (((old[i] >> shf) & 3u) == 1u)
+						atomicOr(&next.w[e >> 4], 2u << shf);
+				}
 		}
 	}
 }
