@@ -150,7 +150,7 @@ static int ensure_workspace(abb_filter* f)
  *  and everything else -- the random counter sectors, the hashes -- is treated as streaming, so that 30-60 MB of counter
  *  lines per window cannot push the maps out (ncu, round 2: without this 57 % of the map atomics missed L2 and the kernel
  *  moved 3x the algorithmic DRAM bytes).  ABB_L2_PERSIST=0 switches it off (tuning). */
-static void set_l2_policy(abb_filter* f, bool on)
+static void set_l2_policy(abb_filter* f, bool on, int n_maps = 3)
 {
 	static int enabled = -1;
 	if (enabled < 0) {
@@ -165,7 +165,7 @@ static void set_l2_policy(abb_filter* f, bool on)
 		int max_persist = 0, max_window = 0;
 		cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, f->device);
 		cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, f->device);
-		const size_t bytes = 3 * std::max<size_t>(f->map_entries / 4, 256);
+		const size_t bytes = (size_t)n_maps * std::max<size_t>(f->map_entries / 4, 256);
 		if (max_persist <= 0 || max_window <= 0)
 			return;
 		cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>(bytes, (size_t)max_persist));
@@ -180,8 +180,10 @@ static void set_l2_policy(abb_filter* f, bool on)
 		attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
 	}
 	cudaStreamSetAttribute(f->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
-	if (!on)
-		cudaCtxResetPersistingL2Cache(); // hand the carve-out back to pass 2
+	if (!on) { // hand the carve-out back to pass 2
+		cudaCtxResetPersistingL2Cache();
+		cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
+	}
 	cudaGetLastError(); // best effort: a device without the feature runs without the hint
 }
 
@@ -579,12 +581,14 @@ static int sharded_ordered_insert(abb_filter* f, abb_comm* c, const uint64_t* d_
 	f->window = user_window;
 	f->map_log2 = 0;
 	ABB_CHECK(rc);
-	ABB_CHECK(f->sh_buf.reserve(2 * (W + kCarryLanes) + 64));
+	// carried slots served per step: the tag table holds only own positions, so world times the single-GPU number fit
+	const unsigned max_lanes = (unsigned)std::min<uint64_t>((uint64_t)kCarryLanes * (unsigned)c->world, W / 2 + kCarryLanes);
+	ABB_CHECK(f->sh_buf.reserve(2 * (W + (uint64_t)max_lanes) + 64));
 	cudaStream_t st = f->stream;
 	const uint64_t n_windows = (n_slots + W - 1) / W;
 	const unsigned age_off = (unsigned)(age_windows_for(W) * W);
 	const unsigned drain_age = age_off / 3 * 2;
-	const uint64_t cap = W + kCarryLanes;
+	const uint64_t cap = 3 * (W + kCarryLanes) / 2; // two lists in the allocation of three (no drain list is needed here)
 	uint64_t* carry[2] = { f->d_carry, f->d_carry + cap };
 	ShardCtl* ctl = reinterpret_cast<ShardCtl*>(f->d_ctl);
 	unsigned* d_nout = f->d_ctl + 4; // [n_out]; the ctl block has 8 words
@@ -609,10 +613,10 @@ static int sharded_ordered_insert(abb_filter* f, abb_comm* c, const uint64_t* d_
 	uint8_t* buf = f->sh_buf.p;
 	// one step of the pipeline: the oldest carried slots + the n new slots of [w0, w0 + n); marks [w1, w1 + n_next)
 	auto step = [&](uint64_t w0, unsigned n, uint64_t w1, unsigned n_next) -> int {
-		const unsigned lanes_c = std::min<unsigned>(n_in, kCarryLanes);
-		// the tag table prefix this step uses (sized to the carried lanes), cleared first
+		const unsigned lanes_c = std::min<unsigned>(n_in, max_lanes);
+		// the tag table prefix this step uses (a rank reserves only the positions it owns: 1/world of them), cleared first
 		uint64_t tslots = 4096;
-		while (tslots < 8ULL * lanes_c * f->H && tslots < f->tag_slots)
+		while (tslots < 8ULL * lanes_c * f->H / (unsigned)c->world + 4096 && tslots < f->tag_slots)
 			tslots <<= 1;
 		const TagTable tab = { f->d_tags2[0], std::min<uint64_t>(tslots, f->tag_slots) - 1 };
 		if (lanes_c)
@@ -664,7 +668,7 @@ static int sharded_ordered_insert(abb_filter* f, abb_comm* c, const uint64_t* d_
 		return ABB_OK;
 	};
 	f->prof_stride = f->prof_ev.empty() ? 1 : std::max<uint64_t>(1, (2 * n_windows + f->prof_ev.size() - 1) / f->prof_ev.size());
-	set_l2_policy(f, true);
+	set_l2_policy(f, true, 2); // this path alternates between the first two maps
 	struct PolicyGuard {
 		abb_filter* f;
 		~PolicyGuard() { set_l2_policy(f, false); }
@@ -676,8 +680,8 @@ static int sharded_ordered_insert(abb_filter* f, abb_comm* c, const uint64_t* d_
 		const unsigned n = (unsigned)std::min<uint64_t>(W, n_slots - w0);
 		const uint64_t w1 = w0 + W;
 		const unsigned n_next = w + 1 < n_windows ? (unsigned)std::min<uint64_t>(W, n_slots - w1) : 0u;
-		if (n_in > kCarryLanes)
-			ABB_CHECK(drain(w0, kCarryLanes / 2));
+		if (n_in > max_lanes)
+			ABB_CHECK(drain(w0, max_lanes / 2));
 		if (n_in && w0 - oldest > drain_age)
 			ABB_CHECK(drain(w0, 0));
 		ABB_CHECK(step(w0, n, w1, n_next));
