@@ -360,10 +360,21 @@ int launch_hash(abb_filter* f, unsigned k, const uint8_t* d_care, const uint8_t*
 	cudaGetDevice(&dev);
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 	const unsigned grid = (unsigned)std::min<uint64_t>((n + kHashWarps - 1) / kHashWarps, (uint64_t)sms * 32);
+	static int tma = -1; // ABB_TMA=0: K1 without the bulk-copy staging (tuning / fallback)
+	if (tma < 0) {
+		const char* e = getenv("ABB_TMA");
+		tma = e ? atoi(e) : 1;
+		if (tma)
+			tma = cudaFuncSetAttribute(k_hash_reads_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kTmaStage) == cudaSuccess ? 1 : 0;
+	}
 	if (d_care)
 		k_hash_reads_masked<<<grid, kHashWarps * 32, 0, stream>>>(d_bases, d_offs + r0, d_slot_offs + r0, slot_base, n, k, d_care,
 		                                                          d_h0, d_valid);
-	else
+	else if (tma && (reinterpret_cast<uintptr_t>(d_bases) & 15) == 0) {
+		// read blocks staged into shared memory by the bulk-copy engine (cp.async.bulk), double buffered
+		const unsigned g = (unsigned)std::min<uint64_t>((n + kHashWarps - 1) / kHashWarps, (uint64_t)sms * 4);
+		k_hash_reads_tma<<<g, kHashWarps * 32, 2 * kTmaStage, stream>>>(d_bases, d_offs + r0, d_slot_offs + r0, slot_base, n, k, d_h0, d_valid);
+	} else
 		k_hash_reads<<<grid, kHashWarps * 32, 0, stream>>>(d_bases, d_offs + r0, d_slot_offs + r0, slot_base, n, k, d_h0, d_valid);
 	if (launches)
 		*launches += 1;

@@ -36,6 +36,7 @@
 #pragma once
 #include "abb_device.cuh"
 #include <cooperative_groups.h>
+#include <cuda/barrier>
 #include <cuda_runtime.h>
 
 namespace abb {
@@ -245,6 +246,86 @@ k_hash_reads(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ off
 		if (L < k)
 			continue;
 		hash_one_read(bases, beg, L, slot_offs[r] - slot_base, k, sP[warp], sQ[warp], sB[warp], lane, h0_out, valid_out);
+	}
+}
+
+// K1 with TMA staging (sm_90+/sm_100a bulk-copy engine).  A CTA of kHashWarps warps takes blocks of kHashWarps
+// consecutive reads; the bytes of a block are contiguous in the batch, so ONE cp.async.bulk (cuda::device::
+// memcpy_async_tx -> UBLKCP) moves them into shared memory and signals an mbarrier; the next block is in flight while
+// the warps hash the current one from shared memory (double buffer).  Blocks that do not fit a stage (long reads) and the
+// last bytes of a batch that a 16-byte-aligned copy would overrun are hashed straight from global memory.
+constexpr unsigned kTmaStage = 8192; // bytes per stage: 8 reads of <= ~1 000 bases
+
+static __global__ void __launch_bounds__(kHashWarps * 32)
+k_hash_reads_tma(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offs,
+                 const uint64_t* __restrict__ slot_offs, uint64_t slot_base, uint64_t n_reads, unsigned k,
+                 uint64_t* __restrict__ h0_out, uint8_t* __restrict__ valid_out)
+{
+	__shared__ uint64_t sP[kHashWarps][kRing];
+	__shared__ uint64_t sQ[kHashWarps][kRing];
+	__shared__ unsigned sB[kHashWarps][kRing];
+	extern __shared__ __align__(128) uint8_t stage_mem[]; // 2 x kTmaStage bytes (dynamic: the rings above use 40 KB of static)
+	uint8_t* const stage[2] = { stage_mem, stage_mem + kTmaStage };
+	__shared__ cuda::barrier<cuda::thread_scope_block> bar[2];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const uint64_t n_blocks = (n_reads + kHashWarps - 1) / kHashWarps;
+	const uint64_t n_bases = offs[n_reads]; // a copy never reaches past the reads of this launch
+	if (threadIdx.x == 0) {
+		init(&bar[0], 1);
+		init(&bar[1], 1);
+		cuda::device::experimental::fence_proxy_async_shared_cta(); // make the barriers visible to the copy engine
+	}
+	__syncthreads();
+	// [a0, a1): the 16-byte aligned byte range of block b, or a1 == a0 when it has to be read from global memory
+	auto range = [&](uint64_t b, uint64_t* a0, uint64_t* a1) {
+		const uint64_t r0 = b * kHashWarps, r1 = min(n_reads, r0 + kHashWarps);
+		const uint64_t lo = offs[r0] & ~15ULL, hi = (offs[r1] + 15) & ~15ULL;
+		*a0 = lo;
+		*a1 = (hi - lo <= kTmaStage && hi <= n_bases) ? hi : lo;
+	};
+	cuda::barrier<cuda::thread_scope_block>::arrival_token tok[2];
+	uint64_t b = blockIdx.x;
+	int st = 0;
+	uint64_t a0 = 0, a1 = 0;
+	if (b < n_blocks) {
+		range(b, &a0, &a1);
+		if (threadIdx.x == 0 && a1 > a0) {
+			cuda::device::memcpy_async_tx(stage[0], bases + a0, cuda::aligned_size_t<16>(a1 - a0), bar[0]);
+			tok[0] = cuda::device::barrier_arrive_tx(bar[0], 1, a1 - a0);
+		}
+	}
+	for (; b < n_blocks; b += gridDim.x, st ^= 1) {
+		// prefetch the next block of this CTA into the other stage (its previous contents were consumed before the
+		// __syncthreads at the end of the previous iteration)
+		const uint64_t nb = b + gridDim.x;
+		uint64_t n0 = 0, n1 = 0;
+		if (nb < n_blocks) {
+			range(nb, &n0, &n1);
+			if (threadIdx.x == 0 && n1 > n0) {
+				cuda::device::memcpy_async_tx(stage[st ^ 1], bases + n0, cuda::aligned_size_t<16>(n1 - n0), bar[st ^ 1]);
+				tok[st ^ 1] = cuda::device::barrier_arrive_tx(bar[st ^ 1], 1, n1 - n0);
+			}
+		}
+		const bool staged = a1 > a0;
+		if (staged) {
+			if (threadIdx.x == 0)
+				bar[st].wait(std::move(tok[st])); // the bytes have landed
+			__syncthreads();
+		}
+		const uint64_t r = b * kHashWarps + warp;
+		if (r < n_reads) {
+			const uint64_t beg = offs[r];
+			const unsigned L = (unsigned)(offs[r + 1] - beg);
+			if (L >= k) {
+				if (staged)
+					hash_one_read(stage[st], beg - a0, L, slot_offs[r] - slot_base, k, sP[warp], sQ[warp], sB[warp], lane, h0_out, valid_out);
+				else
+					hash_one_read(bases, beg, L, slot_offs[r] - slot_base, k, sP[warp], sQ[warp], sB[warp], lane, h0_out, valid_out);
+			}
+		}
+		__syncthreads(); // everybody is done with stage[st] before it is refilled two iterations later
+		a0 = n0;
+		a1 = n1;
 	}
 }
 

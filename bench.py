@@ -54,7 +54,7 @@ REF_BIN = os.path.join(ROOT, "oracle", "_ref", "abyss-bloom-dbg-ref")
 ALG_BYTES_PER_KMER = 64 * H + L / (L - K + 1)  # 257.7 B
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_insert_windows launch (ncu --set full; profiles/README.md), per
 # k-mer slot applied; None until a capture of this round's kernel exists
-NCU_TRAFFIC_PER_SLOT = None
+NCU_TRAFFIC_PER_SLOT = 766.6  # 52.93 GB read + 13.76 GB written by the launch that applied 87.0 M slots (profiles/r02_k_insert_windows_final_raw.csv)
 
 
 def peaks():
