@@ -20,12 +20,15 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 SOURCES = {
     "abb_api.cu": ["abb_common.h", "abb_device.cuh", "abb_insert.cuh", "abb_shard.cuh", "../../include/abyss_b200.h"],
     "abb_assemble.cu": ["abb_common.h", "abb_device.cuh", "abb_walk.cuh", "../../include/abyss_b200.h"],
+    "abb_overlap.cu": ["abb_common.h", "abb_device.cuh", "abb_overlap.cuh", "../../include/abyss_b200.h"],
 }
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr", "-ccbin", "g++",
 ]
 OBJDIR = os.path.join(LIBDIR, "obj")
+# the C++ host programs: the reference's command lines over the C ABI
+CLIS = (("abyss-bloom-dbg", "abyss_bloom_dbg.cc"), ("abyss-bloom", "abyss_bloom.cc"), ("AdjList", "adjlist.cc"))
 
 
 def _digest(paths) -> str:
@@ -72,7 +75,7 @@ def needs_build() -> bool:
         return True
     if _stale(LIB, [o for o, _ in _objects().values()]):
         return True
-    return any(_stale(os.path.join(LIBDIR, exe), _host_sources() + [LIB]) for exe in ("abyss-bloom-dbg", "abyss-bloom"))
+    return any(_stale(os.path.join(LIBDIR, exe), _host_sources() + [LIB]) for exe, _ in CLIS)
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -107,7 +110,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 def build_cli() -> None:
     """the C++ host programs (abyss-bloom-dbg, abyss-bloom) that link the C-ABI library"""
     host = os.path.join(ROOT, "host")
-    for exe, src in (("abyss-bloom-dbg", "abyss_bloom_dbg.cc"), ("abyss-bloom", "abyss_bloom.cc")):
+    for exe, src in CLIS:
         cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-pthread", "-o", os.path.join(LIBDIR, exe), os.path.join(host, src),
                "-L" + LIBDIR, "-labyssb200", "-Wl,-rpath,$ORIGIN"]
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -60,6 +60,15 @@ class AssemblyCounters(C.Structure):
                 ("contig_id", C.c_uint64)]
 
 
+class OverlapEdge(C.Structure):
+    _fields_ = [("u", C.c_uint32), ("v", C.c_uint32), ("distance", C.c_int32)]
+
+
+class OverlapStats(C.Structure):
+    _fields_ = [("vertices", C.c_uint64), ("exact_edges", C.c_uint64), ("short_edges", C.c_uint64), ("blunt_vertices", C.c_uint64),
+                ("launches", C.c_uint64)]
+
+
 _u64p = C.POINTER(C.c_uint64)
 _u8p = C.POINTER(C.c_uint8)
 _vp = C.c_void_p
@@ -121,6 +130,11 @@ SIGNATURES = {
     "abb_filter_set_window": (C.c_int, [_vp, C.c_uint64]),
     "abb_filter_set_profiling": (C.c_int, [_vp, C.c_int]),
     "abb_filter_stream": (_vp, [_vp]),
+    "abb_contains_reads": (C.c_int, [_vp, _vp, _vp, C.c_uint64, _vp, _vp, C.c_uint64, _u64p]),
+    "abb_overlap_create": (C.c_int, [C.POINTER(_vp), C.c_int]),
+    "abb_overlap_destroy": (C.c_int, [_vp]),
+    "abb_overlap_build": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint, C.c_uint, C.c_int, C.POINTER(C.POINTER(OverlapEdge)), _u64p]),
+    "abb_overlap_get_stats": (C.c_int, [_vp, C.POINTER(OverlapStats)]),
 }
 
 _lib = None

@@ -1183,6 +1183,65 @@ static int query_hashes(abb_filter* f, const uint64_t* hashes, uint64_t n, uint8
 int abb_contains_hashes(abb_filter* f, const uint64_t* hashes, uint64_t n, uint8_t* out) { return query_hashes(f, hashes, n, out, false); }
 int abb_mincount_hashes(abb_filter* f, const uint64_t* hashes, uint64_t n, uint8_t* out) { return query_hashes(f, hashes, n, out, true); }
 
+int abb_contains_reads(abb_filter* f, const char* bases, const uint64_t* offsets, uint64_t n_reads, uint8_t* out_flag, uint8_t* out_valid,
+                       uint64_t capacity, uint64_t* n_slots_out)
+{
+	ABB_REQUIRE(f, "NULL filter");
+	if (n_slots_out)
+		*n_slots_out = 0;
+	if (n_reads == 0)
+		return ABB_OK;
+	ABB_REQUIRE(bases && offsets, "NULL read buffers");
+	ABB_REQUIRE(offsets[0] == 0, "offsets[0] must be 0");
+	ABB_CUDA(cudaSetDevice(f->device));
+	const uint64_t n_bases = offsets[n_reads];
+	// own staging buffers: the batch a previous insert left resident (abb_filter_resident_reads) stays valid
+	DevBuf<uint8_t> d_bases;
+	DevBuf<uint64_t> d_offs;
+	auto done = [&](int rc) {
+		d_bases.release();
+		d_offs.release();
+		return rc;
+	};
+	int rc = d_bases.reserve(n_bases + 16);
+	if (rc == ABB_OK)
+		rc = d_offs.reserve(n_reads + 1);
+	if (rc != ABB_OK)
+		return done(rc);
+	auto run = [&]() -> int {
+		ABB_CUDA(cudaMemcpyAsync(d_bases.p, bases, n_bases, cudaMemcpyHostToDevice, f->stream));
+		ABB_CUDA(cudaMemcpyAsync(d_offs.p, offsets, (n_reads + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, f->stream));
+		uint64_t total = 0;
+		ABB_CHECK(compute_slot_offsets(f->k, d_offs.p, n_reads, f->slot_offs, f->scan_tmp, f->stream, &total, &f->st.launches));
+		if (n_slots_out)
+			*n_slots_out = total;
+		if (total == 0 || (!out_flag && !out_valid))
+			return ABB_OK;
+		ABB_REQUIRE(capacity >= total, "output buffers hold %llu slots, %llu needed", (unsigned long long)capacity, (unsigned long long)total);
+		ABB_CHECK(f->h0.reserve(total));
+		ABB_CHECK(f->valid.reserve(total));
+		ABB_CHECK(f->out8.reserve(total));
+		ABB_CHECK(launch_hash(f, f->k, f->d_care, d_bases.p, d_offs.p, f->slot_offs.p, 0, n_reads, 0, f->h0.p, f->valid.p, f->stream, &f->st.launches));
+		const FilterView fv = view_of(f);
+		const unsigned grid = std::min<unsigned>(blocks_for(total, 256), 148 * 16);
+		if (f->kind == ABB_COUNTING)
+			k_query_h0<0><<<grid, 256, 0, f->stream>>>(f->h0.p, f->valid.p, total, f->cfg, fv, f->threshold, f->out8.p);
+		else
+			k_query_h0<1><<<grid, 256, 0, f->stream>>>(f->h0.p, f->valid.p, total, f->cfg, fv, 0, f->out8.p);
+		f->st.launches += 1;
+		ABB_CUDA(cudaGetLastError());
+		if (out_flag)
+			ABB_CUDA(cudaMemcpyAsync(out_flag, f->out8.p, total, cudaMemcpyDeviceToHost, f->stream));
+		if (out_valid)
+			ABB_CUDA(cudaMemcpyAsync(out_valid, f->valid.p, total, cudaMemcpyDeviceToHost, f->stream));
+		ABB_CUDA(cudaStreamSynchronize(f->stream));
+		return ABB_OK;
+	};
+	rc = run();
+	cudaStreamSynchronize(f->stream);
+	return done(rc);
+}
+
 int abb_hash_reads(unsigned k, const char* mask, const char* bases, const uint64_t* offsets, uint64_t n_reads,
                    uint64_t* out_h0, uint8_t* out_valid, uint64_t* n_slots_out, int device)
 {

@@ -945,6 +945,37 @@ k_query(const uint64_t* __restrict__ hashes, uint64_t n, HashCfg cfg, FilterView
 	}
 }
 
+/** contains() per k-mer slot from the canonical hash h0 (the other H - 1 values follow from it, nthash.hpp:337-342);
+ *  slots that RollingHashIterator would skip report 0.  Used by the coverage track / sequence trimming queries
+ *  (bloom-dbg.h:399-447,1280-1334). */
+template <int KIND>
+__global__ void __launch_bounds__(256)
+k_query_h0(const uint64_t* __restrict__ h0, const uint8_t* __restrict__ valid, uint64_t n, HashCfg cfg, FilterView f, unsigned threshold,
+           uint8_t* __restrict__ out_contains)
+{
+	for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n; s += (uint64_t)gridDim.x * blockDim.x) {
+		if (!valid[s]) {
+			out_contains[s] = 0;
+			continue;
+		}
+		const uint64_t h = h0[s];
+		if (KIND == 0) {
+			unsigned mn = 255;
+			for (unsigned i = 0; i < cfg.H; ++i)
+				mn = min(mn, (unsigned)__ldcg(f.data + nth_pos(h, cfg, i)));
+			out_contains[s] = mn >= threshold;
+		} else {
+			const uint8_t* bits = f.data + (uint64_t)(f.levels - 1) * f.level_stride;
+			bool all = true;
+			for (unsigned i = 0; i < cfg.H; ++i) {
+				const uint64_t p = nth_pos(h, cfg, i);
+				all &= (__ldcg(bits + (p >> 3)) >> (p & 7)) & 1;
+			}
+			out_contains[s] = all;
+		}
+	}
+}
+
 /** popCount / filtered_popcount (CountingBloomFilter.hpp:219-244) and getPop (BloomFilter.hpp:313-320) */
 static __global__ void __launch_bounds__(256)
 k_popcount(const uint8_t* __restrict__ data, uint64_t nbytes, int counting, unsigned threshold,

@@ -7,8 +7,8 @@
 // = abb_insert_reads over every input file in order, pass 2 = abb_assembler_process_reads over
 // the same files again, FASTA records `>ID LEN COV read:READID` (printContig, bloom-dbg.h:455-487).
 // -i FILE loads a [BTLCountingBloomFilter_v1] file instead of pass 1 (prebuiltBloomAssembly,
-// :301-345).  Not supported (exit with a message): -g, -C/-R, -T, --checkpoint (debug / experimental
-// outputs of the reference).
+// :301-345).  -C FILE -R REF writes the 0/1 k-mer coverage track (writeCovTrack, bloom-dbg.h:1280-1334) with one GPU
+// query per batch of reference records.  Not supported (exit with a message): -g (GraphViz dump of the whole graph).
 #include "../../include/abyss_b200.h"
 #include "bloom_file.h"
 #include "reads.h"
@@ -94,8 +94,12 @@ static const char USAGE_MESSAGE[] =
     "                               output as one GPU), one host thread per GPU\n"
     "      --batch-reads=N          reads per GPU batch [4000000]\n"
     "\n"
-    "Spaced seeds (-K, --qr-seed, -s), -T, --read-log and --checkpoint work as in the reference;\n"
-    "-g, -C and -R (GraphViz / coverage-track debug outputs) are not supported by the B200 implementation.\n";
+    "  -C, --cov-track=FILE         WIG track with 0/1 indicating k-mers with coverage\n"
+    "                               above the --kc threshold; requires --ref\n"
+    "  -R, --ref=FILE               reference genome for --cov-track\n"
+    "\n"
+    "Spaced seeds (-K, --qr-seed, -s), -T, --read-log, --checkpoint and -C/-R work as in the reference;\n"
+    "-g (GraphViz dump of the graph) is not supported by the B200 implementation.\n";
 
 static AssemblyParams params;
 static ReadOpts ropt;
@@ -207,6 +211,80 @@ static void on_all_ranks(size_t n, Fn fn)
 		t.join();
 }
 
+/** writeCovTrack (bloom-dbg.h:1280-1334): variableStep WIG blocks of equal 0/1 "k-mer is in the solid filter" values along every
+ *  record of the reference; contains() of all k-mers of a batch of records is one GPU query (abb_contains_reads).  As in the
+ *  reference, windows with a non-ACGT base are skipped by the iterator and simply do not interrupt a block. */
+static void writeCovTrack(abb_filter* bloom)
+{
+	std::ofstream covTrack(params.covTrackPath.c_str());
+	auto good = [&]() {
+		if (!covTrack) {
+			std::cerr << "error: `" << params.covTrackPath << "': " << strerror(errno) << "\n";
+			exit(EXIT_FAILURE);
+		}
+	};
+	good();
+	if (params.verbose)
+		std::cerr << "Writing 0/1 k-mer coverage track for `" << params.refPath << "` to `" << params.covTrackPath << "`\n";
+	const unsigned k = abb_filter_kmer_size(bloom);
+	SeqReader ref(params.refPath, ropt);
+	ReadBatch b;
+	std::vector<uint8_t> flag, valid;
+	auto flush = [&]() {
+		if (b.size() == 0)
+			return;
+		uint64_t slots = 0;
+		for (size_t i = 0; i < b.size(); ++i) {
+			const uint64_t len = b.offsets[i + 1] - b.offsets[i];
+			slots += len >= k ? len - k + 1 : 0;
+		}
+		flag.resize(slots + 1);
+		valid.resize(slots + 1);
+		uint64_t n = 0;
+		check(abb_contains_reads(bloom, b.bases.data(), b.offsets.data(), b.size(), flag.data(), valid.data(), slots + 1, &n), "coverage track");
+		uint64_t s0 = 0;
+		for (size_t i = 0; i < b.size(); ++i) {
+			const uint64_t len = b.offsets[i + 1] - b.offsets[i];
+			const uint64_t w = len >= k ? len - k + 1 : 0;
+			const std::string chr = b.id(i);
+			bool firstVal = true;
+			uint64_t blockStart = 1, blockLength = 0;
+			unsigned blockVal = 0;
+			auto block = [&]() { // outputWigBlock (:1253-1266)
+				covTrack << "variableStep chrom=" << chr << " span=" << blockLength << "\n" << blockStart << ' ' << blockVal << '\n';
+				good();
+			};
+			for (uint64_t p = 0; p < w; ++p) {
+				if (!valid[s0 + p])
+					continue;
+				const unsigned val = flag[s0 + p] ? 1 : 0;
+				if (firstVal || val != blockVal) {
+					if (!firstVal)
+						block();
+					firstVal = false;
+					blockStart = p + 1; // WIG coordinates are 1-based
+					blockLength = 1;
+					blockVal = val;
+				} else
+					blockLength++;
+			}
+			if (blockLength > 0)
+				block();
+			s0 += w;
+		}
+		b.clear();
+	};
+	std::string id, seq;
+	while (ref.next(id, seq)) {
+		b.add(id, seq);
+		if (b.bases.size() >= (256u << 20))
+			flush();
+	}
+	flush();
+	good();
+	covTrack.close();
+}
+
 int main(int argc, char** argv)
 {
 	bool die = false;
@@ -296,8 +374,8 @@ int main(int argc, char** argv)
 		std::cerr << "Try `" << PROGRAM << " --help' for more information.\n";
 		exit(EXIT_FAILURE);
 	}
-	if (!params.graphPath.empty() || !params.covTrackPath.empty()) {
-		std::cerr << PROGRAM ": -g and -C are not supported by the B200 implementation\n";
+	if (!params.graphPath.empty()) {
+		std::cerr << PROGRAM ": -g is not supported by the B200 implementation\n";
 		exit(EXIT_FAILURE);
 	}
 	/* initGlobals (bloom-dbg.cc:215-233) + MaskedKmer::setMask (BloomDBG/MaskedKmer.h:25-48), once k is known */
@@ -635,6 +713,9 @@ int main(int argc, char** argv)
 	});
 	if (params.verbose)
 		std::cerr << "Assembly complete\n";
+	/* writeAuxiliaryFiles (bloom-dbg.cc:190-212) */
+	if (!params.covTrackPath.empty() && !params.refPath.empty())
+		writeCovTrack(bloom);
 	if (ckptOn && !params.keepCheckpoint) { // removeCheckpointData (Checkpoint.h:229-247)
 		checkpointOut.close();
 		for (const std::string& f : { ckDbg, ckVisited, ckCounters, ckFasta, ckFasta + ".tmp" })

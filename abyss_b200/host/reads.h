@@ -153,6 +153,9 @@ class SeqReader {
 		close_input(m_f, m_pipe, m_path);
 	}
 
+	/** the comment (rest of the header line after the id) of the record the last next() returned */
+	const std::string& last_comment() const { return m_comment; }
+
 	/** next record; false at end of file */
 	bool next(std::string& id, std::string& seq)
 	{
@@ -184,6 +187,7 @@ class SeqReader {
 				++i;
 			const char* comment = l + i;
 			const size_t clen = n - i;
+			m_comment.assign(comment, clen);
 			bool skip = false;
 			if (clen > 3 && comment[1] == ':' && comment[3] == ':') { // Casava: read:chastity:flags:index
 				if (m_opt.chastityFilter && comment[2] == 'Y')
@@ -343,7 +347,7 @@ class SeqReader {
 	bool m_pipe = false, m_eof = false;
 	RawBuf m_buf;
 	size_t m_pos = 0, m_end = 0;
-	std::string m_q;
+	std::string m_q, m_comment;
 	uint64_t m_line = 0;
 };
 

@@ -255,6 +255,39 @@ typedef struct abb_assembly_stats {
 } abb_assembly_stats;
 int abb_assembler_stats(const abb_assembler* a, abb_assembly_stats* out);
 
+/* ---- debug / auxiliary queries over reads (BloomDBG/bloom-dbg.h: writeCovTrack :1280-1334, trimSeq :399-447) ----
+ * For every k-mer window of every sequence (slot numbering as in abb_hash_reads): out_valid[slot] = 1 if
+ * RollingHashIterator would yield it, out_flag[slot] = contains() of the filter (counting: minCount >= threshold;
+ * bit / cascading: all bits of the last level) -- one GPU pass instead of one contains() call per k-mer.
+ * out_flag / out_valid hold at least the number of slots (sum over sequences of max(0, len - k + 1)). */
+int abb_contains_reads(abb_filter* f, const char* bases, const uint64_t* offsets, uint64_t n_reads, uint8_t* out_flag,
+                       uint8_t* out_valid, uint64_t capacity, uint64_t* n_slots_out);
+
+/* ---- the next stage: contig overlap graph (AdjList/AdjList.cpp:140-291; bin/abyss-pe:577 runs it on the unitig FASTA) ----
+ * Vertices are ContigNode indices (Common/ContigNode.h): 2*i = contig i as given, 2*i+1 = its reverse complement.
+ * Edges u -> v: the last `overlap` bases of u equal the first `overlap` bases of v; distance = -overlap.
+ *  - overlap = k-1 exactly for every such pair (buildOverlapGraph, :247-268);
+ *  - min_overlap <= overlap < k-1 (longest only) between vertices that the first step left without an out-edge
+ *    (addOverlapsSA, :140-201); min_overlap = 0 or > k-1 means k-1 (:386-388), i.e. only the first step.
+ *  - ss != 0 (--SS): only edges between vertices of the same orientation (:159,262).
+ * The edge array is ordered as the reference's graph iterates it (vertices ascending, each out-list in the order
+ * AdjList adds the edges), so any of its output formats can be written from it.  It is library owned and valid
+ * until the next call on the handle.  Contig ends must be nucleotides (ambiguity codes are flattened as in
+ * Common/Sequence.h:50-72; 'N' is an error, the reference aborts) and contigs longer than k-1. */
+typedef struct abb_overlap abb_overlap;
+typedef struct abb_overlap_edge {
+	uint32_t u, v;
+	int32_t distance;
+} abb_overlap_edge;
+typedef struct abb_overlap_stats {
+	uint64_t vertices, exact_edges, short_edges, blunt_vertices, launches;
+} abb_overlap_stats;
+int abb_overlap_create(abb_overlap** out, int device);
+int abb_overlap_destroy(abb_overlap* h);
+int abb_overlap_build(abb_overlap* h, const char* bases, const uint64_t* offsets, uint64_t n_contigs, unsigned k,
+                      unsigned min_overlap, int ss, const abb_overlap_edge** edges, uint64_t* n_edges);
+int abb_overlap_get_stats(const abb_overlap* h, abb_overlap_stats* out);
+
 /* ---- profiling hooks used by bench.py ---------------------------------------------------- */
 typedef struct abb_insert_stats {
 	uint64_t kmers;           /* valid k-mers inserted */

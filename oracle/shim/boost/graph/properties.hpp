@@ -15,14 +15,22 @@ template <class PM> struct property_traits;
 enum vertex_bundle_t { vertex_bundle }; enum edge_bundle_t { edge_bundle };
 enum vertex_name_t { vertex_name }; enum edge_name_t { edge_name };
 enum vertex_index_t { vertex_index }; enum edge_weight_t { edge_weight };
-template <class G> struct edge_bundle_type { typedef no_property type; };
-template <class G> struct vertex_bundle_type { typedef no_property type; };
-template <class G> struct edge_property { typedef no_property type; };
-template <class G> struct vertex_property { typedef no_property type; };
+/* the graph's own nested type when it has one (Boost does the same), no_property otherwise */
+#define ABB_SHIM_NESTED(TRAIT, MEMBER) \
+  template <class G> struct TRAIT { \
+    template <class T> static typename T::MEMBER pick(int); template <class T> static no_property pick(...); \
+    typedef decltype(pick<G>(0)) type; };
+ABB_SHIM_NESTED(edge_bundle_type, edge_bundled)
+ABB_SHIM_NESTED(vertex_bundle_type, vertex_bundled)
+ABB_SHIM_NESTED(edge_property, edge_property_type)
+ABB_SHIM_NESTED(vertex_property, vertex_property_type)
+#undef ABB_SHIM_NESTED
 template <class T> void function_requires() {}
 }
 #define BOOST_INSTALL_PROPERTY(KIND, NAME)
 namespace boost {
 template <class R, class PM> struct put_get_helper {};
+template <class PM, class R, class K> inline R get(const put_get_helper<R, PM>& pm, const K& k) { return static_cast<const PM&>(pm)[k]; }
+template <class G, class Tag> struct property_map;
 struct readable_property_map_tag {};
 }

@@ -151,3 +151,23 @@ def test_abyss_bloom_dbg_cli_bad_seed(cases):
     _, fq, _ = cases["e2e_g20k_k32"]
     r = subprocess.run([os.path.join(BIN, "abyss-bloom-dbg"), "-k32", "--qr-seed=16", "-b1M", fq], capture_output=True, text=True)
     assert r.returncode != 0 and "spaced seed must begin and end with '1's" in r.stderr  # the reference's message for this k
+
+
+def test_coverage_track(cases, tmp_path):
+    # -C FILE -R REF: the 0/1 "k-mer is solid" WIG track over a reference (writeCovTrack, bloom-dbg.h:1280-1334), one GPU query
+    # per batch of reference records (abb_contains_reads); golden = the unmodified reference (make_golden_covtrack.py)
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from make_golden_covtrack import ref_fasta
+    c, fq, d = cases["e2e_g20k_k32"]
+    rs = ReadSet.from_coverage(c["seed"], c["genome"], c["cov"], c["L"], c["err"])
+    ref = str(tmp_path / "ref.fa")
+    ref_fasta(rs, ref)
+    wig = str(tmp_path / "cov.wig")
+    r = subprocess.run([os.path.join(BIN, "abyss-bloom-dbg"), f"-k{c['k']}", f"--kc={c['kc']}", f"-b{c['b']}", f"-H{c['H']}", "-C", wig, "-R", ref,
+                        "-o", os.devnull, fq], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert open(wig).read() == open(os.path.join(ROOT, "tests", "golden", "covtrack_g20k_k32.wig")).read()
+    # -C without -R is a usage error, as in the reference (bloom-dbg.cc:512-515)
+    r = subprocess.run([os.path.join(BIN, "abyss-bloom-dbg"), "-k32", "-b1M", "-C", wig, fq], capture_output=True, text=True)
+    assert r.returncode != 0 and "you must specify a reference" in r.stderr
