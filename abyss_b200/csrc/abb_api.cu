@@ -425,8 +425,30 @@ int compute_slot_offsets(unsigned k, const uint64_t* d_offs, uint64_t n_reads, D
 
 static int sharded_ordered_insert(abb_filter* f, abb_comm* c, const uint64_t* d_h0, const uint8_t* d_valid, uint64_t n_slots);
 
+/** a host-to-device copy of the bases that is still in flight, in pieces of `piece` bytes on f->copy_stream
+ *  (f->copy_ev[i] fires when bytes [i * piece, (i + 1) * piece) have landed); h_offs are the caller's offsets */
+struct PendingCopy {
+	const uint64_t* h_offs = nullptr;
+	uint64_t piece = 0;
+	size_t n_pieces = 0;
+	size_t waited = 0; // pieces the filter's stream already waits for
+};
+
+/** make the filter's stream wait until bases [0, end) are on the device */
+static int wait_bases(abb_filter* f, PendingCopy* pc, uint64_t end)
+{
+	if (!pc || end == 0)
+		return ABB_OK;
+	const size_t need = std::min<size_t>(pc->n_pieces, (size_t)((end + pc->piece - 1) / pc->piece));
+	if (need > pc->waited) {
+		ABB_CUDA(cudaStreamWaitEvent(f->stream, f->copy_ev[need - 1], 0)); // pieces complete in order
+		pc->waited = need;
+	}
+	return ABB_OK;
+}
+
 static int insert_reads_dev(abb_filter* f, const uint8_t* d_bases, const uint64_t* d_offs, uint64_t n_reads,
-                            uint64_t* n_kmers_out, abb_comm* comm = nullptr)
+                            uint64_t* n_kmers_out, abb_comm* comm = nullptr, PendingCopy* pc = nullptr)
 {
 	uint64_t total = 0;
 	ABB_CHECK(compute_slot_offsets(f->k, d_offs, n_reads, f->slot_offs, f->scan_tmp, f->stream, &total, &f->st.launches));
@@ -467,6 +489,8 @@ static int insert_reads_dev(abb_filter* f, const uint8_t* d_bases, const uint64_
 			continue;
 		ABB_CHECK(f->h0.reserve(slots));
 		ABB_CHECK(f->valid.reserve(slots));
+		if (pc)
+			ABB_CHECK(wait_bases(f, pc, pc->h_offs[r1]));
 		ABB_CUDA(cudaEventRecord(f->ev0, f->stream));
 		ABB_CHECK(launch_hash(f, f->k, f->d_care, d_bases, d_offs, f->slot_offs.p, r0, r1, slot_at[c], f->h0.p, f->valid.p,
 		                      f->stream, &f->st.launches));
@@ -862,6 +886,12 @@ int abb_filter_destroy(abb_filter* f)
 		cudaEventDestroy(f->ev0);
 	if (f->ev1)
 		cudaEventDestroy(f->ev1);
+	for (auto e : f->copy_ev)
+		cudaEventDestroy(e);
+	if (f->copy_stream) {
+		cudaStreamSynchronize(f->copy_stream);
+		cudaStreamDestroy(f->copy_stream);
+	}
 	if (f->stream)
 		cudaStreamDestroy(f->stream);
 	delete f;
@@ -934,10 +964,45 @@ int abb_insert_reads(abb_filter* f, const char* bases, const uint64_t* offsets, 
 	ABB_CUDA(cudaSetDevice(f->device));
 	ABB_CHECK(f->bases.reserve(n_bases + 16));
 	ABB_CHECK(f->offs.reserve(n_reads + 1));
-	ABB_CUDA(cudaMemcpyAsync(f->bases.p, bases, n_bases, cudaMemcpyHostToDevice, f->stream));
 	ABB_CUDA(cudaMemcpyAsync(f->offs.p, offsets, (n_reads + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, f->stream));
 	f->resident_reads = n_reads;
-	return insert_reads_dev(f, f->bases.p, f->offs.p, n_reads, n_kmers_out);
+	// The bases travel in pieces on a second stream; chunk c of the insert only waits for the pieces that hold its reads, so
+	// the copy of the rest hides behind the hashing and inserting of the earlier chunks (with pinned host memory; a pageable
+	// buffer makes cudaMemcpyAsync synchronous and the order is simply copy, then insert).  ABB_H2D_OVERLAP=0: one copy up front.
+	static int overlap = -1;
+	if (overlap < 0) {
+		const char* e = getenv("ABB_H2D_OVERLAP");
+		overlap = e ? atoi(e) : 1;
+	}
+	constexpr uint64_t kPiece = 256ULL << 20;
+	if (!overlap || n_bases <= kPiece) {
+		ABB_CUDA(cudaMemcpyAsync(f->bases.p, bases, n_bases, cudaMemcpyHostToDevice, f->stream));
+		return insert_reads_dev(f, f->bases.p, f->offs.p, n_reads, n_kmers_out);
+	}
+	if (!f->copy_stream)
+		ABB_CUDA(cudaStreamCreateWithFlags(&f->copy_stream, cudaStreamNonBlocking));
+	PendingCopy pc;
+	pc.h_offs = offsets;
+	pc.piece = kPiece;
+	pc.n_pieces = (size_t)((n_bases + kPiece - 1) / kPiece);
+	while (f->copy_ev.size() < pc.n_pieces) {
+		cudaEvent_t ev;
+		ABB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+		f->copy_ev.push_back(ev);
+	}
+	// the destination may still be read by work queued on the filter's stream (pass 2 of a previous job)
+	ABB_CUDA(cudaEventRecord(f->ev0, f->stream));
+	ABB_CUDA(cudaStreamWaitEvent(f->copy_stream, f->ev0, 0));
+	for (size_t i = 0; i < pc.n_pieces; ++i) {
+		const uint64_t b0 = (uint64_t)i * kPiece, b1 = std::min<uint64_t>(n_bases, b0 + kPiece);
+		ABB_CUDA(cudaMemcpyAsync(f->bases.p + b0, bases + b0, b1 - b0, cudaMemcpyHostToDevice, f->copy_stream));
+		ABB_CUDA(cudaEventRecord(f->copy_ev[i], f->copy_stream));
+	}
+	const int rc = insert_reads_dev(f, f->bases.p, f->offs.p, n_reads, n_kmers_out, nullptr, &pc);
+	// The last chunk waited for the last piece, so normally everything has landed; after an early return (no k-mers, an
+	// error) the copy may still be running, and the caller owns the host buffer again once this call returns.
+	ABB_CUDA(cudaStreamSynchronize(f->copy_stream));
+	return rc;
 }
 
 int abb_insert_reads_sharded(abb_filter* f, abb_comm* c, const char* bases, const uint64_t* offsets, uint64_t n_reads, int finalize,

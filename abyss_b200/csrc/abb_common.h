@@ -98,6 +98,9 @@ struct abb_filter {
 	abb::HashCfg cfg;
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	// host-buffer insert: the bases travel in pieces on their own stream while earlier chunks are hashed and inserted
+	cudaStream_t copy_stream = nullptr;
+	std::vector<cudaEvent_t> copy_ev; // copy_ev[i]: piece i has landed
 
 	// ordered-insert workspace (abb_insert.cuh K2)
 	uint64_t window = 0;      // slots per window

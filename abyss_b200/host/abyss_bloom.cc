@@ -88,7 +88,7 @@ int main(int argc, char** argv)
 	uint64_t batchReads = 4000000;
 	std::string type = "konnector";
 	ReadOpts ropt;
-	static int chastity = 1, trimMasked = 1, illuminaQ = 0;
+	static int chastity = 1, trimMasked = 1, qualityOffset = 0; // 0 = the format's own offset
 	static const struct option longopts[] = {
 		{ "bloom-size", required_argument, NULL, 'b' }, { "kmer", required_argument, NULL, 'k' },
 		{ "num-hashes", required_argument, NULL, 'H' }, { "levels", required_argument, NULL, 'l' },
@@ -96,7 +96,7 @@ int main(int argc, char** argv)
 		{ "trim-quality", required_argument, NULL, 'q' }, { "verbose", no_argument, NULL, 'v' },
 		{ "chastity", no_argument, &chastity, 1 }, { "no-chastity", no_argument, &chastity, 0 },
 		{ "trim-masked", no_argument, &trimMasked, 1 }, { "no-trim-masked", no_argument, &trimMasked, 0 },
-		{ "standard-quality", no_argument, &illuminaQ, 0 }, { "illumina-quality", no_argument, &illuminaQ, 1 },
+		{ "standard-quality", no_argument, &qualityOffset, 33 }, { "illumina-quality", no_argument, &qualityOffset, 64 },
 		{ "device", required_argument, NULL, 1000 }, { "batch-reads", required_argument, NULL, 1001 },
 		{ NULL, 0, NULL, 0 }
 	};
@@ -127,7 +127,7 @@ int main(int argc, char** argv)
 	}
 	ropt.chastityFilter = chastity;
 	ropt.trimMasked = trimMasked;
-	ropt.qualityOffset = illuminaQ ? 64 : 0;
+	ropt.qualityOffset = qualityOffset;
 	if (k == 0) {
 		std::cerr << PROGRAM ": missing mandatory option `-k'\n";
 		usage();

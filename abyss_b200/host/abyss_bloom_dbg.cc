@@ -106,7 +106,7 @@ static ReadOpts ropt;
 
 enum { OPT_HELP = 1, OPT_VERSION, QR_SEED, MIN_KMER_COV, CHECKPOINT, KEEP_CHECKPOINT, CHECKPOINT_PREFIX, READ_LOG, OPT_DEVICE, OPT_DEVICES, OPT_BATCH };
 
-static int chastity = 1, trimMasked = 1, illuminaQ = 0;
+static int chastity = 1, trimMasked = 1, qualityOffset = 0; // opt::qualityOffset (DataLayer/Options.h): 0 = the format's own
 static const char shortopts[] = "b:C:g:H:i:j:k:K:o:q:Q:R:s:t:T:v";
 static const struct option longopts[] = {
 	{ "bloom-size", required_argument, NULL, 'b' },
@@ -127,8 +127,8 @@ static const struct option longopts[] = {
 	{ "out", required_argument, NULL, 'o' },
 	{ "trim-quality", required_argument, NULL, 'q' },
 	{ "mask-quality", required_argument, NULL, 'Q' },
-	{ "standard-quality", no_argument, &illuminaQ, 0 },
-	{ "illumina-quality", no_argument, &illuminaQ, 1 },
+	{ "standard-quality", no_argument, &qualityOffset, 33 },
+	{ "illumina-quality", no_argument, &qualityOffset, 64 },
 	{ "qr-seed", required_argument, NULL, QR_SEED },
 	{ "ref", required_argument, NULL, 'R' },
 	{ "spaced-seed", required_argument, NULL, 's' },
@@ -334,7 +334,7 @@ int main(int argc, char** argv)
 	}
 	ropt.chastityFilter = chastity;
 	ropt.trimMasked = trimMasked;
-	ropt.qualityOffset = illuminaQ ? 64 : 0;
+	ropt.qualityOffset = qualityOffset;
 
 	if (params.bloomPath.empty() && params.bloomSize == 0) {
 		std::cerr << PROGRAM ": missing mandatory option `-b'\n";

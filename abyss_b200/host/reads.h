@@ -5,9 +5,10 @@
 //   '>' FASTA (multi-line) and '@' FASTQ records, '#' comment lines, Casava 1.8 headers with the
 //   chastity filter (opt::chastityFilter, default on), trimming of masked (lower-case) ends
 //   (opt::trimMasked, default on -- FastaReader.cpp:29), quality trimming (-q) and masking (-Q),
-//   quality offset 33/64, case folding.  SAM/qseq/export and colour-space input are not handled
-//   (the reference's FastaReader.cpp:270-360 paths): the CLI reports them as unsupported.
+//   quality offset 33/64, case folding; SAM records (FastaReader.cpp:270-327: secondary / QC-fail filters, /1 /2 suffixes,
+//   reverse-strand records turned back) and qseq / export records (:328-352).  Colour-space input is not handled.
 #pragma once
+#include <algorithm>
 #include <cctype>
 #include <cerrno>
 #include <cmath>
@@ -32,7 +33,7 @@ struct ReadOpts {
 	int trimMasked = 1;
 	int qualityThreshold = 0;
 	int internalQThreshold = 0;
-	int qualityOffset = 0; // 0 = format default (33)
+	int qualityOffset = 0; // opt::qualityOffset: 0 = the format's own (33 for FASTA / FASTQ / SAM, 64 for qseq / export)
 };
 
 /** growable byte buffer that does not zero-fill (std::vector<char>::resize would touch every byte twice) */
@@ -170,10 +171,10 @@ class SeqReader {
 			if (c == EOF)
 				return false;
 			if (c != '>' && c != '@') {
-				line(l, n);
-				die();
-				fprintf(stderr, "only FASTA ('>') and FASTQ ('@') input is supported by the B200 CLI, saw `%c' near\n%.*s\n", c, (int)n, l);
-				exit(EXIT_FAILURE);
+				if (!line_record(id, seq))
+					continue; // filtered out (secondary alignment, failed the chastity filter)
+				finish_record(seq, m_q, m_lineQualityOffset);
+				return true;
 			}
 			line(l, n); // header
 			if (n > 3 && l[0] == '@' && isalpha((unsigned char)l[1]) && isalpha((unsigned char)l[2]) && l[3] == '\t')
@@ -255,33 +256,153 @@ class SeqReader {
 			for (auto& ch : seq) // FOLD_CASE
 				if (ch >= 'a' && ch <= 'z')
 					ch = (char)(ch - 32);
-			const int qoff = 33; // FastaReader.cpp: `qualityOffset = 33` for '>' / '@' records; --illumina-quality only applies to qseq/export
-			if (m_opt.qualityThreshold > 0 && !q.empty()) { // FastaReader.cpp:376-394
-				const int good = qoff + m_opt.qualityThreshold;
-				size_t front = 0, back = q.size();
-				while (front < q.size() && (unsigned char)q[front] < good)
-					++front;
-				while (back > 0 && (unsigned char)q[back - 1] < good)
-					--back;
-				if (front >= back) {
-					seq.erase(1);
-					q.erase(1);
-				} else {
-					seq = seq.substr(front, back - front);
-					q = q.substr(front, back - front);
-				}
-			}
-			if (m_opt.internalQThreshold > 0 && !q.empty()) { // FastaReader.cpp:396-407
-				const int good = qoff + m_opt.internalQThreshold;
-				for (size_t j = 0; j < q.size(); ++j)
-					if ((unsigned char)q[j] < good)
-						seq[j] = 'N';
-			}
+			finish_record(seq, q, 33);
 			return true;
 		}
 	}
 
   private:
+	/** the part of FastaReader::read every format shares (FastaReader.cpp:361-407): -q trims the ends, -Q masks inside.  The
+	 *  quality offset is the format's (33 for FASTA / FASTQ / SAM, 64 for qseq / export) unless --standard-quality or
+	 *  --illumina-quality was given (`if (opt::qualityOffset > 0) qualityOffset = opt::qualityOffset`, :361-362). */
+	void finish_record(std::string& seq, std::string& q, int formatOffset) const
+	{
+		const int qoff = m_opt.qualityOffset > 0 ? m_opt.qualityOffset : formatOffset;
+		if (m_opt.qualityThreshold > 0 && !q.empty()) { // FastaReader.cpp:376-394
+			const int good = qoff + m_opt.qualityThreshold;
+			size_t front = 0, back = q.size();
+			while (front < q.size() && (unsigned char)q[front] < good)
+				++front;
+			while (back > 0 && (unsigned char)q[back - 1] < good)
+				--back;
+			if (front >= back) {
+				seq.erase(1);
+				q.erase(1);
+			} else {
+				seq = seq.substr(front, back - front);
+				q = q.substr(front, back - front);
+			}
+		}
+		if (m_opt.internalQThreshold > 0 && !q.empty()) { // FastaReader.cpp:396-407
+			const int good = qoff + m_opt.internalQThreshold;
+			for (size_t j = 0; j < q.size(); ++j)
+				if ((unsigned char)q[j] < good)
+					seq[j] = 'N';
+		}
+	}
+	/** isChaste (FastaReader.cpp:94-107) */
+	bool is_chaste(const std::string& s, const char* l, size_t n)
+	{
+		if (s == "1" || s == "Y")
+			return true;
+		if (s == "0" || s == "N")
+			return false;
+		die();
+		fprintf(stderr, "chastity filter should be one of 0, 1, N or Y\nand saw `%s' near\n%.*s\n", s.c_str(), (int)n, l);
+		exit(EXIT_FAILURE);
+	}
+	/** a record that is one tab-separated line: SAM (FastaReader.cpp:283-327) or qseq / export (:328-352).  Neither is case
+	 *  folded nor trimmed of masked ends (the reference only does that for '>' / '@' records).  false = record filtered out. */
+	bool line_record(std::string& id, std::string& seq)
+	{
+		const char* l;
+		size_t n;
+		line(l, n);
+		std::vector<std::string>& f = m_fields;
+		f.clear();
+		{ // std::getline(in, field, '\t') semantics: a trailing tab does not open an empty last field
+			size_t b = 0;
+			while (b < n) {
+				const char* t = (const char*)memchr(l + b, '\t', n - b);
+				const size_t e = t ? (size_t)(t - l) : n;
+				f.emplace_back(l + b, e - b);
+				b = e + 1;
+			}
+		}
+		std::string& q = m_q;
+		if (f.size() >= 11 && (f[9].size() == f[10].size() || f[10] == "*")) { // SAM
+			const unsigned long flags = strtoul(f[1].c_str(), nullptr, 0);
+			if (flags & 0x100) // FSECONDARY
+				return false;
+			if (m_opt.chastityFilter && (flags & 0x200)) // FQCFAIL
+				return false;
+			id = f[0];
+			char which = '0';
+			switch (flags & 0xc1) { // FPAIRED|FREAD1|FREAD2
+			case 0: case 1: break;
+			case 0x41: id += "/1"; which = '1'; break;
+			case 0x81: id += "/2"; which = '2'; break;
+			default:
+				die();
+				fprintf(stderr, "invalid flags: `%s' near%.*s\n", id.c_str(), (int)n, l);
+				exit(EXIT_FAILURE);
+			}
+			m_comment = (flags & 0x200) ? "0:Y:0:" : "0:N:0:";
+			m_comment[0] = which;
+			seq = f[9];
+			q = f[10];
+			if (seq == "*")
+				seq.clear();
+			if (q == "*")
+				q.clear();
+			if (flags & 0x10) { // FREVERSE: back to the strand that was sequenced (reverseComplement, Common/Sequence.cpp)
+				std::string rcs(seq.rbegin(), seq.rend());
+				for (char& ch : rcs)
+					ch = complement_char(ch);
+				seq.swap(rcs);
+				std::reverse(q.begin(), q.end());
+			}
+			m_lineQualityOffset = 33;
+			if (!q.empty() && q.size() != seq.size()) {
+				die();
+				fprintf(stderr, "sequence and quality must be the same length near\n%s\n%s\n", seq.c_str(), q.c_str());
+				exit(EXIT_FAILURE);
+			}
+			return true;
+		}
+		if (f.size() == 11 || f.size() == 22) { // qseq or export
+			const bool chaste = is_chaste(f.back(), l, n);
+			if (m_opt.chastityFilter && !chaste)
+				return false;
+			id = f[0];
+			for (int i = 1; i < 6; ++i)
+				if (!f[i].empty()) {
+					id += ':';
+					id += f[i];
+				}
+			if (!f[6].empty() && f[6] != "0") {
+				id += '#';
+				id += f[6];
+			}
+			id += '/'; // the reverse read is the second read, or the third of an indexed run
+			id += f[7] == "3" ? "2" : f[7];
+			m_comment = f[7] + (chaste ? ":N:0:" : ":Y:0:");
+			seq = f[8];
+			q = f[9];
+			m_lineQualityOffset = 64;
+			if (q.size() != seq.size()) {
+				die();
+				fprintf(stderr, "sequence and quality must be the same length near\n%s\n%s\n", seq.c_str(), q.c_str());
+				exit(EXIT_FAILURE);
+			}
+			return true;
+		}
+		die();
+		fprintf(stderr, "Expected either `>' or `@' or 11 fields\nand saw `%c' and %zu fields near\n%.*s\n", n ? l[0] : ' ', f.size(), (int)n, l);
+		exit(EXIT_FAILURE);
+	}
+	/** complement of a nucleotide or IUPAC code, case kept (complementBaseChar, Common/Sequence.cpp:24-58) */
+	static char complement_char(char c)
+	{
+		static const char* from = "ACGTMRWSYKVHDBNacgtmrwsykvhdbn.";
+		static const char* to = "TGCAKYWSRMBDHVNtgcakywsrmbdhvn.";
+		const char* p = c ? strchr(from, c) : nullptr;
+		if (!p) {
+			fprintf(stderr, "error: unexpected character: `%c'\n", c);
+			abort();
+		}
+		return to[p - from];
+	}
 	FILE* die()
 	{
 		fprintf(stderr, "%s:%llu: error: ", m_path.c_str(), (unsigned long long)m_line);
@@ -348,6 +469,8 @@ class SeqReader {
 	RawBuf m_buf;
 	size_t m_pos = 0, m_end = 0;
 	std::string m_q, m_comment;
+	std::vector<std::string> m_fields;
+	int m_lineQualityOffset = 33;
 	uint64_t m_line = 0;
 };
 
@@ -359,7 +482,8 @@ class SeqReader {
  * BloomIO.h:50-94).  A piece boundary is a line that starts a record: in a file whose first byte is '>' a line
  * starting with '>' (sequence lines cannot); in a file whose first byte is '@' a line starting with '@' whose second
  * successor starts with '+' (a quality line that starts with '@' is followed by a header and a sequence line).
- * Anything else ('#' comments first, SAM headers, stdin oddities) is parsed by the reading thread itself.
+ * SAM, qseq and export files hold one record per line and are cut at any line start.  A file that begins with '#' comment
+ * lines is handed to one worker as a single piece.
  */
 class BatchStream {
   public:
@@ -646,11 +770,20 @@ class BatchStream {
 						eof = true;
 					buf.n += got;
 				}
-				if (!mode && buf.n)
-					mode = buf.data()[0] == '>' || buf.data()[0] == '@' ? buf.data()[0] : '?';
+				if (!mode && buf.n) {
+					const char* d = buf.data();
+					const bool sam_header = buf.n > 3 && d[0] == '@' && isalpha((unsigned char)d[1]) && isalpha((unsigned char)d[2]) && d[3] == '\t';
+					// SAM / qseq / export: one record per line, a piece may end at any line; '#' comments first: serial
+					mode = sam_header ? 'L' : (d[0] == '>' || d[0] == '@') ? d[0] : d[0] == '#' ? '?' : 'L';
+				}
 				if (eof || mode == '?')
 					break;
-				const size_t cut = last_record_start(buf.data(), buf.n, mode);
+				size_t cut = 0;
+				if (mode == 'L') {
+					const char* nl = buf.n > 1 ? (const char*)memrchr(buf.data(), '\n', buf.n - 1) : nullptr;
+					cut = nl ? (size_t)(nl - buf.data()) + 1 : 0;
+				} else
+					cut = last_record_start(buf.data(), buf.n, mode);
 				if (cut) {
 					carry.reserve(buf.n - cut + m_piece);
 					memcpy(carry.data(), buf.data() + cut, buf.n - cut);

@@ -24,6 +24,7 @@
 #include "vendor/btl_bloomfilter/CountingBloomFilter.hpp"
 #include "vendor/btl_bloomfilter/BloomFilter.hpp"
 #include "DataLayer/FastaReader.h"
+#include "DataLayer/Options.h"
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -61,6 +62,13 @@ int main(int argc, char** argv)
 		// BloomIO.h:58 / bloom-dbg.h:917) -- "id<TAB>sequence" per record, or records/s
 		if (argc < 4) usage();
 		const bool dump = std::string(argv[2]) == "dump";
+		// the reader's global options (DataLayer/Options.h), as abyss-bloom-dbg's -q / -Q / --illumina-quality / --no-chastity /
+		// --no-trim-masked set them
+		if (const char* e = getenv("REF_Q")) opt::qualityThreshold = atoi(e);
+		if (const char* e = getenv("REF_MASKQ")) opt::internalQThreshold = atoi(e);
+		if (const char* e = getenv("REF_QOFF")) opt::qualityOffset = atoi(e);
+		if (getenv("REF_NO_CHASTITY")) opt::chastityFilter = 0;
+		if (getenv("REF_NO_TRIM_MASKED")) opt::trimMasked = 0;
 		size_t n = 0, bases = 0;
 		auto t0 = std::chrono::steady_clock::now();
 		for (int i = 3; i < argc; ++i) {

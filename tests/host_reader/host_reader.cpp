@@ -15,6 +15,10 @@ int main(int argc, char** argv)
 		o.internalQThreshold = atoi(q);
 	if (getenv("READER_NO_CHASTITY"))
 		o.chastityFilter = 0;
+	if (getenv("READER_NO_TRIM_MASKED"))
+		o.trimMasked = 0;
+	if (const char* q = getenv("READER_QOFF"))
+		o.qualityOffset = atoi(q);
 	if (argc < 3)
 		return 2;
 	const bool timing = getenv("READER_TIME") != nullptr;

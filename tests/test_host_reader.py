@@ -152,3 +152,70 @@ def test_compressed_input_and_quoting(exe, tmp_path):
     bad.write_bytes(b"this is not gzip")
     r = subprocess.run([exe, "serial", str(bad)], capture_output=True, text=True)
     assert r.returncode != 0 and "decompressor" in r.stderr
+
+
+def _rand_seq(rng, n, alphabet="ACGT"):
+    return "".join(rng.choice(alphabet) for _ in range(n))
+
+
+def sam_text(n, seed):
+    """SAM with a header, every flag combination the reader looks at (FPAIRED/FREAD1/FREAD2, FREVERSE, FSECONDARY, FQCFAIL),
+    `*` sequences and qualities, lower-case bases, optional fields"""
+    rng = random.Random(seed)
+    out = ["@HD\tVN:1.0\tSO:unsorted", "@SQ\tSN:chr1\tLN:100000", "@PG\tID:bwa\tVN:0.7"]
+    for i in range(n):
+        flags = rng.choice([0, 1, 0x41, 0x81, 0x51, 0x91, 0x10, 0x100, 0x141, 0x200, 0x241, 0x4, 0x45])
+        L = rng.randint(20, 120)
+        s = _rand_seq(rng, L, "ACGTNacgt" if rng.random() < 0.2 else "ACGT")
+        q = "".join(chr(rng.randint(33, 73)) for _ in range(L))
+        r = rng.random()
+        if r < 0.05:
+            s, q = "*", "*"
+        elif r < 0.15:
+            q = "*"
+        extra = "\tNM:i:0\tBX:Z:ACGT-1" if rng.random() < 0.3 else ""
+        out.append(f"read{i}\t{flags}\tchr1\t{rng.randint(1, 9999)}\t60\t{L}M\t=\t{rng.randint(1, 9999)}\t0\t{s}\t{q}{extra}")
+    return "\n".join(out) + "\n"
+
+
+def qseq_text(n, seed, export=False):
+    """qseq (11 fields) or export (22 fields): machine, run, lane, tile, x, y, index, read number, bases ('.' = no call),
+    qualities (offset 64), ..., filter"""
+    rng = random.Random(seed)
+    out = []
+    for i in range(n):
+        L = rng.randint(20, 100)
+        s = _rand_seq(rng, L, "ACGT.")
+        q = "".join(chr(rng.randint(64, 104)) for _ in range(L))
+        f = ["M1", str(rng.randint(1, 9)), str(rng.randint(1, 8)), str(rng.randint(1, 99)), str(i), str(rng.randint(0, 999)),
+             rng.choice(["0", "ACGTAC", ""]), rng.choice(["1", "2", "3"]), s, q]
+        chaste = rng.choice(["1", "0"] if not export else ["Y", "N"])
+        if export:
+            f += ["chr1", "", "123", "F", "100", "20", "0", "", "", "", "N"]
+        f.append(chaste)
+        assert len(f) == (22 if export else 11)
+        out.append("\t".join(f))
+    return "\n".join(out) + "\n"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_ARITH), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("opts", [{}, {"Q": "20"}, {"MASKQ": "15"}, {"NO_CHASTITY": "1"}, {"Q": "10", "QOFF": "64"}, {"MASKQ": "12", "QOFF": "33"},
+                                  {"NO_TRIM_MASKED": "1"}])
+def test_sam_qseq_export_equal_reference_reader(exe, tmp_path, opts):
+    # the record formats of DataLayer/FastaReader.cpp:270-352 next to FASTQ, with the reader options of the command line
+    # (-q, -Q, --illumina-quality / --standard-quality, --no-chastity, --no-trim-masked), against the UNMODIFIED reference reader
+    files = {"a.sam": sam_text(800, 21), "b_qseq.txt": qseq_text(600, 22), "c_export.txt": qseq_text(400, 23, export=True),
+             "d.fq": fastq(500, 24, casava=True), "e.fa": fasta(200, 25)}
+    paths = []
+    for name, text in files.items():
+        p = tmp_path / name
+        p.write_text(text, newline="")
+        paths.append(str(p))
+    ref = subprocess.run([REF_ARITH, "reads", "dump", *paths], capture_output=True, text=True, env=dict(os.environ, **{"REF_" + k: v for k, v in opts.items()}))
+    assert ref.returncode == 0, ref.stderr
+    env = {"READER_" + k: v for k, v in opts.items()}
+    serial, _ = run(exe, "serial", *paths, env=env)
+    assert serial == ref.stdout
+    got, _ = run(exe, "stream", 3, 250, 4096, *paths, env=env)
+    assert got == ref.stdout
+    assert ref.stdout.count("\n") > 1500
