@@ -18,7 +18,7 @@ LIB = os.path.join(LIBDIR, "libabyssb200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 # translation unit -> the headers it includes (abb_assemble.cu takes minutes: rebuild it only when its own headers change)
 SOURCES = {
-    "abb_api.cu": ["abb_common.h", "abb_device.cuh", "abb_insert.cuh", "abb_shard.cuh", "../../include/abyss_b200.h"],
+    "abb_api.cu": ["abb_common.h", "abb_device.cuh", "abb_insert.cuh", "abb_shard.cuh", "abb_graph.cuh", "../../include/abyss_b200.h"],
     "abb_assemble.cu": ["abb_common.h", "abb_device.cuh", "abb_walk.cuh", "../../include/abyss_b200.h"],
     "abb_overlap.cu": ["abb_common.h", "abb_device.cuh", "abb_overlap.cuh", "../../include/abyss_b200.h"],
 }

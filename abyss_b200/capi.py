@@ -60,6 +60,10 @@ class AssemblyCounters(C.Structure):
                 ("contig_id", C.c_uint64)]
 
 
+class SuccInfo(C.Structure):
+    _fields_ = [("hash", C.c_uint64 * 4), ("mask", C.c_uint8), ("pad", C.c_uint8 * 7)]
+
+
 class OverlapEdge(C.Structure):
     _fields_ = [("u", C.c_uint32), ("v", C.c_uint32), ("distance", C.c_int32)]
 
@@ -131,6 +135,7 @@ SIGNATURES = {
     "abb_filter_set_profiling": (C.c_int, [_vp, C.c_int]),
     "abb_filter_stream": (_vp, [_vp]),
     "abb_contains_reads": (C.c_int, [_vp, _vp, _vp, C.c_uint64, _vp, _vp, C.c_uint64, _u64p]),
+    "abb_successors": (C.c_int, [_vp, _vp, C.c_uint64, C.c_uint, _vp, _vp, _vp]),
     "abb_overlap_create": (C.c_int, [C.POINTER(_vp), C.c_int]),
     "abb_overlap_destroy": (C.c_int, [_vp]),
     "abb_overlap_build": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint, C.c_uint, C.c_int, C.POINTER(C.POINTER(OverlapEdge)), _u64p]),

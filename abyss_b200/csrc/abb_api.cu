@@ -372,7 +372,7 @@ int launch_hash(abb_filter* f, unsigned k, const uint8_t* d_care, const uint8_t*
 		                                                          d_h0, d_valid);
 	else if (tma && (reinterpret_cast<uintptr_t>(d_bases) & 15) == 0) {
 		// read blocks staged into shared memory by the bulk-copy engine (cp.async.bulk), double buffered
-		const unsigned g = (unsigned)std::min<uint64_t>((n + kHashWarps - 1) / kHashWarps, (uint64_t)sms * 4);
+		const unsigned g = (unsigned)std::min<uint64_t>((n + kTmaReads - 1) / kTmaReads, (uint64_t)sms * 4);
 		k_hash_reads_tma<<<g, kHashWarps * 32, 2 * kTmaStage, stream>>>(d_bases, d_offs + r0, d_slot_offs + r0, slot_base, n, k, d_h0, d_valid);
 	} else
 		k_hash_reads<<<grid, kHashWarps * 32, 0, stream>>>(d_bases, d_offs + r0, d_slot_offs + r0, slot_base, n, k, d_h0, d_valid);
@@ -1143,7 +1143,7 @@ int abb_filter_allgather(abb_filter* f, abb_comm* c)
 	ABB_REQUIRE(f && c, "NULL argument");
 	ABB_REQUIRE(f->levels == 1, "only single-level filters are sharded");
 	ABB_CUDA(cudaSetDevice(f->device));
-	if (c->world == 1)
+	if (c->world == 1 || f->replicated_insert)
 		return ABB_OK;
 	const uint64_t chunk = shard_chunk(f->bytes_per_level, (unsigned)c->world);
 	ABB_REQUIRE(chunk * c->world <= f->bytes_per_level + 4096, "too many ranks for the all-gather slack");
@@ -1202,7 +1202,18 @@ int abb_insert_reads_sharded_dev(abb_filter* f, abb_comm* c, const char* d_bases
 	ABB_REQUIRE(n_reads == 0 || (d_bases && d_offsets), "NULL read buffers");
 	ABB_REQUIRE(f->device == c->device, "filter and communicator live on different devices");
 	ABB_CUDA(cudaSetDevice(f->device));
-	ABB_CHECK(insert_reads_dev(f, (const uint8_t*)d_bases, d_offsets, n_reads, n_kmers_out, c->world > 1 ? c : nullptr));
+	// Policy: the position-sharded insert divides the counter traffic by the world size but every rank still evaluates every
+	// lane and pays a collective per window; measured on B200 it beats one GPU only from 4 ranks on (pass 1 of the bench job:
+	// 2.17 s on 1 GPU, 2.81 s sharded over 2, 1.78 s over 4).  Below ABB_SHARD_MIN_WORLD ranks (default 4) every rank
+	// therefore runs the whole insert itself -- same bytes, no communication -- and only pass 2 is divided.
+	static int min_world = -1;
+	if (min_world < 0) {
+		const char* e = getenv("ABB_SHARD_MIN_WORLD");
+		min_world = e ? std::max(2, atoi(e)) : 4;
+	}
+	const bool shard = c->world > 1 && c->world >= min_world;
+	f->replicated_insert = !shard;
+	ABB_CHECK(insert_reads_dev(f, (const uint8_t*)d_bases, d_offsets, n_reads, n_kmers_out, shard ? c : nullptr));
 	if (finalize)
 		ABB_CHECK(abb_filter_allgather(f, c));
 	return ABB_OK;
@@ -1305,6 +1316,52 @@ int abb_contains_reads(abb_filter* f, const char* bases, const uint64_t* offsets
 	rc = run();
 	cudaStreamSynchronize(f->stream);
 	return done(rc);
+}
+
+int abb_successors(abb_filter* f, const char* kmers, uint64_t n, unsigned max_chain, abb_succ_info* out, unsigned* out_len, uint64_t* self_hash)
+{
+	ABB_REQUIRE(f, "NULL filter");
+	if (n == 0)
+		return ABB_OK;
+	ABB_REQUIRE(kmers && out && out_len && self_hash, "NULL buffer");
+	ABB_REQUIRE(max_chain >= 1 && max_chain <= 128, "max_chain must be in 1..128");
+	ABB_REQUIRE(f->mask.empty(), "graph neighbourhood queries are not available with a spaced seed");
+	ABB_REQUIRE(f->H <= 64, "too many hash functions");
+	ABB_CUDA(cudaSetDevice(f->device));
+	DevBuf<uint8_t> d_k;
+	DevBuf<abb_succ_info> d_info;
+	DevBuf<unsigned> d_len;
+	DevBuf<uint64_t> d_self;
+	auto run = [&]() -> int {
+		ABB_CHECK(d_k.reserve(n * f->k));
+		ABB_CHECK(d_info.reserve(n * max_chain));
+		ABB_CHECK(d_len.reserve(n));
+		ABB_CHECK(d_self.reserve(n));
+		ABB_CUDA(cudaMemcpyAsync(d_k.p, kmers, n * f->k, cudaMemcpyHostToDevice, f->stream));
+		ABB_CUDA(cudaMemsetAsync(d_info.p, 0, n * max_chain * sizeof(abb_succ_info), f->stream));
+		const FilterView fv = view_of(f);
+		if (f->kind == ABB_COUNTING) {
+			const FilterProbe<0> probe = { f->cfg, fv, f->threshold };
+			k_successors<0><<<blocks_for(n, 128), 128, 0, f->stream>>>(d_k.p, n, f->k, max_chain, probe, d_info.p, d_len.p, d_self.p);
+		} else {
+			const FilterProbe<1> probe = { f->cfg, fv, 0 };
+			k_successors<1><<<blocks_for(n, 128), 128, 0, f->stream>>>(d_k.p, n, f->k, max_chain, probe, d_info.p, d_len.p, d_self.p);
+		}
+		f->st.launches += 1;
+		ABB_CUDA(cudaGetLastError());
+		ABB_CUDA(cudaMemcpyAsync(out, d_info.p, n * max_chain * sizeof(abb_succ_info), cudaMemcpyDeviceToHost, f->stream));
+		ABB_CUDA(cudaMemcpyAsync(out_len, d_len.p, n * sizeof(unsigned), cudaMemcpyDeviceToHost, f->stream));
+		ABB_CUDA(cudaMemcpyAsync(self_hash, d_self.p, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, f->stream));
+		ABB_CUDA(cudaStreamSynchronize(f->stream));
+		return ABB_OK;
+	};
+	const int rc = run();
+	cudaStreamSynchronize(f->stream);
+	d_k.release();
+	d_info.release();
+	d_len.release();
+	d_self.release();
+	return rc;
 }
 
 int abb_hash_reads(unsigned k, const char* mask, const char* bases, const uint64_t* offsets, uint64_t n_reads,

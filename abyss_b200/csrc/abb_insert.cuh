@@ -35,6 +35,7 @@
 // the table is cleared only once every 15 windows.
 #pragma once
 #include "abb_device.cuh"
+#include "abb_graph.cuh"
 #include <cooperative_groups.h>
 #include <cuda/barrier>
 #include <cuda_runtime.h>
@@ -249,12 +250,14 @@ k_hash_reads(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ off
 	}
 }
 
-// K1 with TMA staging (sm_90+/sm_100a bulk-copy engine).  A CTA of kHashWarps warps takes blocks of kHashWarps
-// consecutive reads; the bytes of a block are contiguous in the batch, so ONE cp.async.bulk (cuda::device::
-// memcpy_async_tx -> UBLKCP) moves them into shared memory and signals an mbarrier; the next block is in flight while
-// the warps hash the current one from shared memory (double buffer).  Blocks that do not fit a stage (long reads) and the
-// last bytes of a batch that a 16-byte-aligned copy would overrun are hashed straight from global memory.
-constexpr unsigned kTmaStage = 8192; // bytes per stage: 8 reads of <= ~1 000 bases
+// K1 with TMA staging (sm_90+/sm_100a bulk-copy engine).  A CTA of kHashWarps warps takes blocks of kTmaReads consecutive
+// reads; the bytes of a block are contiguous in the batch, so ONE cp.async.bulk (cuda::device::memcpy_async_tx -> UBLKCP)
+// moves them into shared memory and signals an mbarrier; the next block is in flight while the warps hash the current one
+// from shared memory (double buffer; every warp takes kTmaReads / kHashWarps reads of the block, so the two block barriers
+// of a stage are paid once per 32 reads).  Blocks that do not fit a stage (long reads) and the last bytes of a batch that a
+// 16-byte-aligned copy would overrun are hashed straight from global memory.
+constexpr unsigned kTmaStage = 8192; // bytes per stage
+constexpr unsigned kTmaReads = 32;   // reads per stage: 32 x 150 bases = 4 800 bytes
 
 static __global__ void __launch_bounds__(kHashWarps * 32)
 k_hash_reads_tma(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offs,
@@ -268,7 +271,7 @@ k_hash_reads_tma(const uint8_t* __restrict__ bases, const uint64_t* __restrict__
 	uint8_t* const stage[2] = { stage_mem, stage_mem + kTmaStage };
 	__shared__ cuda::barrier<cuda::thread_scope_block> bar[2];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const uint64_t n_blocks = (n_reads + kHashWarps - 1) / kHashWarps;
+	const uint64_t n_blocks = (n_reads + kTmaReads - 1) / kTmaReads;
 	const uint64_t n_bases = offs[n_reads]; // a copy never reaches past the reads of this launch
 	if (threadIdx.x == 0) {
 		init(&bar[0], 1);
@@ -278,7 +281,7 @@ k_hash_reads_tma(const uint8_t* __restrict__ bases, const uint64_t* __restrict__
 	__syncthreads();
 	// [a0, a1): the 16-byte aligned byte range of block b, or a1 == a0 when it has to be read from global memory
 	auto range = [&](uint64_t b, uint64_t* a0, uint64_t* a1) {
-		const uint64_t r0 = b * kHashWarps, r1 = min(n_reads, r0 + kHashWarps);
+		const uint64_t r0 = b * kTmaReads, r1 = min(n_reads, r0 + kTmaReads);
 		const uint64_t lo = offs[r0] & ~15ULL, hi = (offs[r1] + 15) & ~15ULL;
 		*a0 = lo;
 		*a1 = (hi - lo <= kTmaStage && hi <= n_bases) ? hi : lo;
@@ -312,8 +315,8 @@ k_hash_reads_tma(const uint8_t* __restrict__ bases, const uint64_t* __restrict__
 				bar[st].wait(std::move(tok[st])); // the bytes have landed
 			__syncthreads();
 		}
-		const uint64_t r = b * kHashWarps + warp;
-		if (r < n_reads) {
+		const uint64_t r_end = min(n_reads, (b + 1) * (uint64_t)kTmaReads);
+		for (uint64_t r = b * kTmaReads + warp; r < r_end; r += kHashWarps) {
 			const uint64_t beg = offs[r];
 			const unsigned L = (unsigned)(offs[r + 1] - beg);
 			if (L >= k) {
@@ -974,6 +977,48 @@ k_query_h0(const uint64_t* __restrict__ h0, const uint8_t* __restrict__ valid, u
 			out_contains[s] = all;
 		}
 	}
+}
+
+/** contains() of the filter for a canonical hash (counting: minCount >= threshold; bits: last level) */
+template <int KIND>
+struct FilterProbe {
+	HashCfg cfg;
+	FilterView f;
+	unsigned threshold;
+	ABB_HD static unsigned ld(const uint8_t* p)
+	{
+#if defined(__CUDA_ARCH__)
+		return __ldcg(p);
+#else
+		return *p;
+#endif
+	}
+	ABB_HD bool operator()(uint64_t h0) const
+	{
+		bool ok = true;
+		for (unsigned i = 0; i < cfg.H; ++i) { // independent loads: issued back to back
+			const uint64_t p = nth_pos(h0, cfg, i);
+			if (KIND == 0)
+				ok &= ld(f.data + p) >= threshold;
+			else
+				ok &= (ld(f.data + (uint64_t)(f.levels - 1) * f.level_stride + (p >> 3)) >> (p & 7)) & 1;
+		}
+		return ok;
+	}
+};
+
+/** out-edges of graph vertices for the GraphViz dump: one thread per start k-mer runs successors_chain (abb_graph.cuh); a
+ *  search frontier is a handful of vertices and a chain is a sequence of dependent lookups, so this is latency, not
+ *  bandwidth -- the 4 x H lookups of one vertex are independent and overlap */
+template <int KIND>
+__global__ void __launch_bounds__(128)
+k_successors(const uint8_t* __restrict__ kmers, uint64_t n, unsigned k, unsigned max_chain, FilterProbe<KIND> probe,
+             abb_succ_info* __restrict__ info, unsigned* __restrict__ len, uint64_t* __restrict__ self)
+{
+	const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (w >= n)
+		return;
+	len[w] = successors_chain(kmers + w * k, k, max_chain, probe, info + w * max_chain, self + w);
 }
 
 /** popCount / filtered_popcount (CountingBloomFilter.hpp:219-244) and getPop (BloomFilter.hpp:313-320) */

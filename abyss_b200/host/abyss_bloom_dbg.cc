@@ -8,9 +8,11 @@
 // the same files again, FASTA records `>ID LEN COV read:READID` (printContig, bloom-dbg.h:455-487).
 // -i FILE loads a [BTLCountingBloomFilter_v1] file instead of pass 1 (prebuiltBloomAssembly,
 // :301-345).  -C FILE -R REF writes the 0/1 k-mer coverage track (writeCovTrack, bloom-dbg.h:1280-1334) with one GPU
-// query per batch of reference records.  Not supported (exit with a message): -g (GraphViz dump of the whole graph).
+// query per batch of reference records; -g FILE writes the GraphViz dump of the graph (outputGraph, :1171-1242): the breadth-first
+// order is the reference's, the Bloom lookups of the frontier are GPU batches (abb_successors).
 #include "../../include/abyss_b200.h"
 #include "bloom_file.h"
+#include "graph_dump.h"
 #include "reads.h"
 #include <getopt.h>
 #include <climits>
@@ -20,6 +22,8 @@
 #include <iostream>
 #include <sstream>
 #include <thread>
+#include <unordered_map>
+#include <unordered_set>
 
 #define PROGRAM "abyss-bloom-dbg"
 #define MAX_KMER 192
@@ -98,8 +102,10 @@ static const char USAGE_MESSAGE[] =
     "                               above the --kc threshold; requires --ref\n"
     "  -R, --ref=FILE               reference genome for --cov-track\n"
     "\n"
-    "Spaced seeds (-K, --qr-seed, -s), -T, --read-log, --checkpoint and -C/-R work as in the reference;\n"
-    "-g (GraphViz dump of the graph) is not supported by the B200 implementation.\n";
+    "  -g  --graph=FILE             write de Bruijn graph to FILE (GraphViz)\n"
+    "\n"
+    "Spaced seeds (-K, --qr-seed, -s), -T, --read-log, --checkpoint, -C/-R and -g work as in the reference\n"
+    "(-g not together with a spaced seed).\n";
 
 static AssemblyParams params;
 static ReadOpts ropt;
@@ -285,6 +291,21 @@ static void writeCovTrack(abb_filter* bloom)
 	covTrack.close();
 }
 
+/** outputGraph (bloom-dbg.h:1171-1242) over the C ABI; the traversal itself is host/graph_dump.h */
+static void outputGraph(const std::vector<std::string>& files, abb_filter* bloom, std::ostream& out)
+{
+	host::output_graph(
+	    abb_filter_kmer_size(bloom), params.verbose, [&](auto fn) { for_each_batch(files, fn); },
+	    [&](const char* bases, const uint64_t* offsets, uint64_t n, uint8_t* flag, uint8_t* valid, uint64_t cap) {
+		    uint64_t slots = 0;
+		    check(abb_contains_reads(bloom, bases, offsets, n, flag, valid, cap, &slots), "graph");
+	    },
+	    [&](const char* kmers, uint64_t n, unsigned max_chain, abb_succ_info* info, unsigned* len, uint64_t* self) {
+		    check(abb_successors(bloom, kmers, n, max_chain, info, len, self), "graph");
+	    },
+	    out);
+}
+
 int main(int argc, char** argv)
 {
 	bool die = false;
@@ -374,8 +395,8 @@ int main(int argc, char** argv)
 		std::cerr << "Try `" << PROGRAM << " --help' for more information.\n";
 		exit(EXIT_FAILURE);
 	}
-	if (!params.graphPath.empty()) {
-		std::cerr << PROGRAM ": -g is not supported by the B200 implementation\n";
+	if (!params.graphPath.empty() && (params.K > 0 || params.qrSeedLen > 0 || !params.spacedSeed.empty())) {
+		std::cerr << PROGRAM ": -g is not supported together with a spaced seed by the B200 implementation\n";
 		exit(EXIT_FAILURE);
 	}
 	/* initGlobals (bloom-dbg.cc:215-233) + MaskedKmer::setMask (BloomDBG/MaskedKmer.h:25-48), once k is known */
@@ -716,6 +737,23 @@ int main(int argc, char** argv)
 	/* writeAuxiliaryFiles (bloom-dbg.cc:190-212) */
 	if (!params.covTrackPath.empty() && !params.refPath.empty())
 		writeCovTrack(bloom);
+	if (!params.graphPath.empty()) {
+		std::ofstream graphOut(params.graphPath.c_str());
+		auto good = [&]() {
+			if (!graphOut) {
+				std::cerr << "error: `" << params.graphPath << "': " << strerror(errno) << "\n";
+				exit(EXIT_FAILURE);
+			}
+		};
+		good();
+		std::vector<std::string> all = loadFiles; // outputGraph reads every file argument (bloom-dbg.cc:204-211)
+		if (asmFiles != loadFiles)
+			all.insert(all.end(), asmFiles.begin(), asmFiles.end());
+		outputGraph(all, bloom, graphOut);
+		good();
+		graphOut.close();
+		good();
+	}
 	if (ckptOn && !params.keepCheckpoint) { // removeCheckpointData (Checkpoint.h:229-247)
 		checkpointOut.close();
 		for (const std::string& f : { ckDbg, ckVisited, ckCounters, ckFasta, ckFasta + ".tmp" })

@@ -263,6 +263,20 @@ int abb_assembler_stats(const abb_assembler* a, abb_assembly_stats* out);
 int abb_contains_reads(abb_filter* f, const char* bases, const uint64_t* offsets, uint64_t n_reads, uint8_t* out_flag,
                        uint8_t* out_valid, uint64_t capacity, uint64_t* n_slots_out);
 
+/* ---- out-edges of graph vertices, for the GraphViz dump `-g` (outputGraph, BloomDBG/bloom-dbg.h:1171-1242; out_edge_iterator,
+ * BloomDBG/RollingBloomDBG.h:300-360): for each of n k-mers (n * k characters, ACGT) the successors that the filter contains.
+ * While a vertex has exactly one out-edge the walk continues to that successor, up to max_chain (1..128) vertices, so out holds
+ * n * max_chain entries: out[i * max_chain + s] describes the s-th vertex of chain i (s = 0: k-mer i itself); out_len[i] =
+ * entries filled.  mask bit b (A, C, G, T = 0..3): the successor with last base b exists; hash[b]: its canonical ntHash
+ * (vertex identity).  self_hash[i]: canonical hash of k-mer i.  Not available with a spaced seed. */
+typedef struct abb_succ_info {
+	uint64_t hash[4];
+	uint8_t mask;
+	uint8_t pad[7];
+} abb_succ_info;
+int abb_successors(abb_filter* f, const char* kmers, uint64_t n, unsigned max_chain, abb_succ_info* out, unsigned* out_len,
+                   uint64_t* self_hash);
+
 /* ---- the next stage: contig overlap graph (AdjList/AdjList.cpp:140-291; bin/abyss-pe:577 runs it on the unitig FASTA) ----
  * Vertices are ContigNode indices (Common/ContigNode.h): 2*i = contig i as given, 2*i+1 = its reverse complement.
  * Edges u -> v: the last `overlap` bases of u equal the first `overlap` bases of v; distance = -overlap.

@@ -171,3 +171,53 @@ def test_coverage_track(cases, tmp_path):
     # -C without -R is a usage error, as in the reference (bloom-dbg.cc:512-515)
     r = subprocess.run([os.path.join(BIN, "abyss-bloom-dbg"), "-k32", "-b1M", "-C", wig, fq], capture_output=True, text=True)
     assert r.returncode != 0 and "you must specify a reference" in r.stderr
+
+
+def test_graphviz_dump(tmp_path, abb):
+    # -g FILE: the breadth-first GraphViz dump of the Bloom filter de Bruijn graph (outputGraph, bloom-dbg.h:1171-1242): the
+    # traversal order is the reference's, the Bloom lookups are GPU batches (abb_contains_reads, abb_successors); goldens from
+    # the unmodified reference (make_golden_graph.py)
+    import gzip
+    for c in json.load(open(os.path.join(ROOT, "tests", "golden", "graph_cases.json"))):
+        rs = ReadSet.from_coverage(c["seed"], c["genome"], c["cov"], c["L"], c["err"])
+        fq = str(tmp_path / (c["name"] + ".fq"))
+        rs.write_fastq(fq)
+        dot = str(tmp_path / (c["name"] + ".dot"))
+        r = subprocess.run([os.path.join(BIN, "abyss-bloom-dbg"), f"-k{c['k']}", f"--kc={c['kc']}", f"-b{c['b']}", f"-H{c['H']}", "-g", dot,
+                            "--batch-reads=700", "-o", os.devnull, fq], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        data = open(dot, "rb").read()
+        assert len(data) == c["bytes"] and hashlib.sha256(data).hexdigest() == c["sha256"], c["name"]
+        full = os.path.join(ROOT, "tests", "golden", c["name"] + ".dot.gz")
+        if os.path.exists(full):
+            assert data == gzip.open(full, "rb").read()
+    r = subprocess.run([os.path.join(BIN, "abyss-bloom-dbg"), "-k21", "-K5", "-b64k", "-g", dot, fq], capture_output=True, text=True)
+    assert r.returncode != 0 and "spaced seed" in r.stderr
+
+
+def test_successors_c_abi(abb):
+    # abb_successors against a filter that holds exactly the k-mers of one sequence: every vertex has one out-edge, the
+    # chain runs to max_chain and reproduces the sequence; the canonical hashes equal those of abb_hash_reads
+    import ctypes as C
+    import numpy as np
+    rng = np.random.default_rng(5)
+    k = 31
+    seq = "".join("ACGT"[i] for i in rng.integers(0, 4, 400))
+    f = abb.Filter.counting(1 << 22, 4, k, 1)
+    f.insert_reads([seq])
+    h0, valid, _ = abb.hash_reads(k, [seq])
+    lib = abb.load()
+    info = (abb.SuccInfo * 64)()
+    ln = (C.c_uint * 1)()
+    self_h = (C.c_uint64 * 1)()
+    km = seq[:k].encode()
+    abb.check(lib.abb_successors(f.handle(), km, 1, 64, info, ln, self_h))
+    assert self_h[0] == int(h0[0]) and ln[0] == 64
+    for s in range(64):
+        b = "ACGT".index(seq[k + s])
+        assert info[s].mask == 1 << b, (s, info[s].mask)
+        assert info[s].hash[b] == int(h0[s + 1])
+    # a k-mer the filter has never seen: no out-edges (up to false positives, none at this load), chain length 1
+    abb.check(lib.abb_successors(f.handle(), b"A" * k, 1, 64, info, ln, self_h))
+    assert ln[0] == 1 and info[0].mask == 0
+    f.close()

@@ -16,6 +16,7 @@ import os, sys, json, hashlib, numpy as np, torch, torch.distributed as dist
 sys.path.insert(0, %(root)r)
 from abyss_b200 import capi
 from abyss_b200.synth import ReadSet
+os.environ["ABB_SHARD_MIN_WORLD"] = "2"  # the position-sharded insert also at world size 2 (the library default keeps 2 ranks replicated)
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(rank)
 dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
@@ -91,8 +92,10 @@ def test_cli_devices_option(tmp_path, ndev):
     fq = str(tmp_path / "r.fq")
     rs.write_fastq(fq)
     fa, log = str(tmp_path / "out.fa"), str(tmp_path / "read.log")
-    r = subprocess.run([os.path.join(ROOT, "abyss_b200", "lib", "abyss-bloom-dbg"), f"-k{c['k']}", f"--kc={c['kc']}", f"-b{c['b']}", f"-H{c['H']}",
-                        f"--devices=0-{ndev - 1}", "--batch-reads=1500", f"--read-log={log}", "-o", fa, fq], capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stderr
-    assert open(fa).read() == open(os.path.join(gd, "e2e_g20k_k32.fa")).read()
-    assert open(log).read() == open(os.path.join(gd, "e2e_g20k_k32.readlog.tsv")).read()
+    for policy in ({"ABB_SHARD_MIN_WORLD": "2"}, {}):  # sharded insert forced / the library's own choice for this world size
+        r = subprocess.run([os.path.join(ROOT, "abyss_b200", "lib", "abyss-bloom-dbg"), f"-k{c['k']}", f"--kc={c['kc']}", f"-b{c['b']}", f"-H{c['H']}",
+                            f"--devices=0-{ndev - 1}", "--batch-reads=1500", f"--read-log={log}", "-o", fa, fq], capture_output=True, text=True, timeout=600,
+                           env=dict(os.environ, **policy))
+        assert r.returncode == 0, r.stderr
+        assert open(fa).read() == open(os.path.join(gd, "e2e_g20k_k32.fa")).read()
+        assert open(log).read() == open(os.path.join(gd, "e2e_g20k_k32.readlog.tsv")).read()

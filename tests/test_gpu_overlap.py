@@ -32,7 +32,10 @@ def run_case(exe, case, tmp_path):
 def test_cli_goldens(abb, tmp_path):
     exe = os.path.join(BIN, "AdjList")
     want = json.load(open(os.path.join(GOLD, "overlap_cases.json")))
-    for c in oc.all_cases():
+    # every process start pays a CUDA context: the command line runs the tiled sets, every format on the unitig sets and a few
+    # fuzz sets; the remaining fuzz sets go through the same per-item functions and writers in tests/test_host_overlap.py
+    cases = [c for c in oc.all_cases() if not c["name"].startswith("fuzz") or c["name"] in ("fuzz7", "fuzz11", "fuzz23", "fuzz42")]
+    for c in cases:
         got = run_case(exe, c, tmp_path)
         assert len(got) == want[c["name"]]["bytes"], c["name"]
         assert hashlib.sha256(got).hexdigest() == want[c["name"]]["sha256"], c["name"]
@@ -44,7 +47,7 @@ def test_cli_goldens(abb, tmp_path):
 @pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/AdjList-ref not built")
 def test_cli_live_against_reference(abb, tmp_path):
     exe = os.path.join(BIN, "AdjList")
-    cases = [oc.fuzz_case(s) for s in range(2000, 2030)] + [oc.tiled_case(9, 1500000, 64, 50, 0), oc.tiled_case(10, 800000, 40, 0, 4)]
+    cases = [oc.fuzz_case(s) for s in range(2000, 2008)] + [oc.tiled_case(9, 1500000, 64, 50, 0), oc.tiled_case(10, 800000, 40, 0, 4)]
     for c in cases:
         fa = str(tmp_path / "in.fa")
         oc.write_fasta(c, fa)
