@@ -187,6 +187,30 @@ static void set_l2_policy(abb_filter* f, bool on, int n_maps = 3)
 	cudaGetLastError(); // best effort: a device without the feature runs without the hint
 }
 
+/** Scope that holds the L2 policy.  Changing the persisting carve-out (cudaDeviceSetLimit, cudaCtxResetPersistingL2Cache)
+ *  synchronises the whole device -- including a host-to-device copy running on another stream -- so a caller that overlaps
+ *  a copy with the insert takes the hold once, before the copy starts; the per-chunk scopes inside then do nothing. */
+struct PolicyHold {
+	abb_filter* f;
+	bool took;
+	PolicyHold(abb_filter* f_, int n_maps) : f(f_), took(!f_->l2_policy_held && f_->d_map[0] != nullptr)
+	{
+		if (took) {
+			set_l2_policy(f, true, n_maps);
+			f->l2_policy_held = true;
+		}
+	}
+	~PolicyHold()
+	{
+		if (took) {
+			set_l2_policy(f, false);
+			f->l2_policy_held = false;
+		}
+	}
+	PolicyHold(const PolicyHold&) = delete;
+	PolicyHold& operator=(const PolicyHold&) = delete;
+};
+
 /** cooperative launch of the persistent window kernel with as many CTAs as fit on the device */
 template <int KIND, bool LITERAL, int MAXH>
 static int launch_windows(const InsertArgs& args, int device, cudaStream_t st)
@@ -253,11 +277,7 @@ static int ordered_insert(abb_filter* f, const uint64_t* d_hashes, const uint8_t
 	for (int i = 0; i < 2; ++i)
 		ABB_CUDA(cudaMemsetAsync(f->d_tags2[i], 0, f->tag_slots * sizeof(unsigned long long), st));
 	const bool counting = f->kind == ABB_COUNTING;
-	set_l2_policy(f, true);
-	struct PolicyGuard {
-		abb_filter* f;
-		~PolicyGuard() { set_l2_policy(f, false); }
-	} policy_guard{ f };
+	PolicyHold policy(f, 3);
 	while (a.w_begin < a.n_windows) {
 		const bool timed = f->profile && f->prof_used + 2 <= f->prof_ev.size();
 		if (timed)
@@ -703,11 +723,7 @@ static int sharded_ordered_insert(abb_filter* f, abb_comm* c, const uint64_t* d_
 		return ABB_OK;
 	};
 	f->prof_stride = f->prof_ev.empty() ? 1 : std::max<uint64_t>(1, (2 * n_windows + f->prof_ev.size() - 1) / f->prof_ev.size());
-	set_l2_policy(f, true, 2); // this path alternates between the first two maps
-	struct PolicyGuard {
-		abb_filter* f;
-		~PolicyGuard() { set_l2_policy(f, false); }
-	} policy_guard{ f };
+	PolicyHold policy(f, 2); // this path alternates between the first two maps
 	ABB_CHECK(step(0, 0, 0, (unsigned)std::min<uint64_t>(W, n_slots))); // marks of window 0
 	p = 1 - p; // the marks went to maps[1 - p]
 	for (uint64_t w = 0; w < n_windows; ++w) {
@@ -981,6 +997,9 @@ int abb_insert_reads(abb_filter* f, const char* bases, const uint64_t* offsets, 
 	}
 	if (!f->copy_stream)
 		ABB_CUDA(cudaStreamCreateWithFlags(&f->copy_stream, cudaStreamNonBlocking));
+	if (f->kind != ABB_BIT)
+		ABB_CHECK(ensure_workspace(f)); // the maps exist before the policy that pins them is set
+	PolicyHold policy(f, 3); // before the copy starts: setting it later would wait for the whole copy (see PolicyHold)
 	PendingCopy pc;
 	pc.h_offs = offsets;
 	pc.piece = kPiece;

@@ -119,6 +119,7 @@ struct abb_filter {
 
 	// per-call buffers (bases/offs keep the device copy of the last host batch: abb_filter_resident_reads)
 	uint64_t resident_reads = 0;
+	bool l2_policy_held = false;    // an enclosing scope already pinned the conflict maps in L2 (abb_api.cu PolicyHold)
 	bool replicated_insert = false; // the last "sharded" insert ran replicated (small worlds): nothing to all-gather
 	abb::DevBuf<uint8_t> bases;
 	abb::DevBuf<uint64_t> offs, slot_offs, h0, lit;

@@ -211,13 +211,13 @@ def test_successors_c_abi(abb):
     ln = (C.c_uint * 1)()
     self_h = (C.c_uint64 * 1)()
     km = seq[:k].encode()
-    abb.check(lib.abb_successors(f.handle(), km, 1, 64, info, ln, self_h))
+    abb.check(lib.abb_successors(f.handle, km, 1, 64, info, ln, self_h))
     assert self_h[0] == int(h0[0]) and ln[0] == 64
     for s in range(64):
         b = "ACGT".index(seq[k + s])
         assert info[s].mask == 1 << b, (s, info[s].mask)
         assert info[s].hash[b] == int(h0[s + 1])
     # a k-mer the filter has never seen: no out-edges (up to false positives, none at this load), chain length 1
-    abb.check(lib.abb_successors(f.handle(), b"A" * k, 1, 64, info, ln, self_h))
+    abb.check(lib.abb_successors(f.handle, b"A" * k, 1, 64, info, ln, self_h))
     assert ln[0] == 1 and info[0].mask == 0
     f.close()
