@@ -483,7 +483,9 @@ static int insert_reads_dev(abb_filter* f, const uint8_t* d_bases, const uint64_
 		bounds = { 0, n_reads };
 	} else {
 		const unsigned max_chunks = (unsigned)(total / kChunkSlots + 3) * 2;
-		DevBuf<uint64_t> d_bounds;
+		// a member buffer: a cudaMalloc / cudaFree per call would synchronise the device, i.e. wait for the host-to-device copy
+		// that abb_insert_reads runs next to this insert
+		DevBuf<uint64_t>& d_bounds = f->bounds;
 		ABB_CHECK(d_bounds.reserve(max_chunks + 2));
 		k_chunk_bounds<<<1, 1, 0, f->stream>>>(f->slot_offs.p, n_reads, kChunkSlots, d_bounds.p, max_chunks,
 		                                      (unsigned*)(d_bounds.p + max_chunks + 1));
@@ -491,7 +493,6 @@ static int insert_reads_dev(abb_filter* f, const uint8_t* d_bases, const uint64_
 		std::vector<uint64_t> h(max_chunks + 2);
 		ABB_CUDA(cudaMemcpyAsync(h.data(), d_bounds.p, (max_chunks + 2) * sizeof(uint64_t), cudaMemcpyDeviceToHost, f->stream));
 		ABB_CUDA(cudaStreamSynchronize(f->stream));
-		d_bounds.release();
 		unsigned nc = (unsigned)(h[max_chunks + 1] & 0xffffffffu);
 		bounds.assign(h.begin(), h.begin() + nc + 1);
 	}
@@ -892,6 +893,11 @@ int abb_filter_destroy(abb_filter* f)
 	f->slot_offs.release();
 	f->h0.release();
 	f->lit.release();
+	f->bounds.release();
+	f->gq_kmers.release();
+	f->gq_info.release();
+	f->gq_len.release();
+	f->gq_self.release();
 	f->valid.release();
 	f->scan_tmp.release();
 	f->out8.release();
@@ -1347,10 +1353,10 @@ int abb_successors(abb_filter* f, const char* kmers, uint64_t n, unsigned max_ch
 	ABB_REQUIRE(f->mask.empty(), "graph neighbourhood queries are not available with a spaced seed");
 	ABB_REQUIRE(f->H <= 64, "too many hash functions");
 	ABB_CUDA(cudaSetDevice(f->device));
-	DevBuf<uint8_t> d_k;
-	DevBuf<abb_succ_info> d_info;
-	DevBuf<unsigned> d_len;
-	DevBuf<uint64_t> d_self;
+	DevBuf<uint8_t>& d_k = f->gq_kmers;
+	DevBuf<abb_succ_info>& d_info = f->gq_info;
+	DevBuf<unsigned>& d_len = f->gq_len;
+	DevBuf<uint64_t>& d_self = f->gq_self;
 	auto run = [&]() -> int {
 		ABB_CHECK(d_k.reserve(n * f->k));
 		ABB_CHECK(d_info.reserve(n * max_chain));
@@ -1376,10 +1382,6 @@ int abb_successors(abb_filter* f, const char* kmers, uint64_t n, unsigned max_ch
 	};
 	const int rc = run();
 	cudaStreamSynchronize(f->stream);
-	d_k.release();
-	d_info.release();
-	d_len.release();
-	d_self.release();
 	return rc;
 }
 

@@ -122,8 +122,13 @@ struct abb_filter {
 	bool l2_policy_held = false;    // an enclosing scope already pinned the conflict maps in L2 (abb_api.cu PolicyHold)
 	bool replicated_insert = false; // the last "sharded" insert ran replicated (small worlds): nothing to all-gather
 	abb::DevBuf<uint8_t> bases;
-	abb::DevBuf<uint64_t> offs, slot_offs, h0, lit;
+	abb::DevBuf<uint64_t> offs, slot_offs, h0, lit, bounds;
 	abb::DevBuf<uint8_t> valid, scan_tmp, out8, sh_buf;
+	// abb_successors staging (a graph dump issues thousands of small queries: no allocation per call)
+	abb::DevBuf<uint8_t> gq_kmers;
+	abb::DevBuf<abb_succ_info> gq_info;
+	abb::DevBuf<unsigned> gq_len;
+	abb::DevBuf<uint64_t> gq_self;
 
 	// statistics
 	abb_insert_stats st = {};

@@ -199,15 +199,29 @@ def reference_arm(args, rank, world):
     print(json.dumps(line))
 
 
+def insert_sharded(world):
+    """the library's policy (abb_insert_reads_sharded_dev): below ABB_SHARD_MIN_WORLD ranks (default 4) every rank runs the whole
+    insert itself -- the position-sharded insert only beats one GPU from 4 ranks on -- and only pass 2 is divided"""
+    return world > 1 and world >= max(2, int(os.environ.get("ABB_SHARD_MIN_WORLD", "4")))
+
+
+def parallelism(world):
+    if world == 1:
+        return "1 GPU"
+    p2 = ("pass 2: read classification, candidate scans and tile production sharded over the ranks (all-gather / exchange), "
+          "walks and file-order replay replicated")
+    if insert_sharded(world):
+        return (f"pass 1: counters sharded by position range over {world} GPUs, one ncclAllReduce(min) per file-order window, "
+                f"all-gather of the shards (exact: same counters as 1 GPU); {p2}")
+    return f"pass 1: replicated on each of the {world} GPUs (no communication; the sharded insert is used from 4 GPUs on); {p2}"
+
+
 def workload_config(args, extra=None):
     c = {"workload": f"{args.reads} x {L} bp synthetic paired reads, {GENOME} bp random genome, err {ERR}, k={K} kc={KC} H={H} -b 8GiB "
                      "(BASELINE.json configs[1])",
          "reads": args.reads, "read_len": L, "k": K, "kc": KC, "num_hashes": H, "bloom_bytes": BLOOM_BYTES,
          "l2_policy": "inputs (7.5 GB reads) and filters (8.6 GB) far exceed the 126 MB L2; no flush needed",
-         "parallelism": (f"pass 1: counters sharded by position range over {args.gpus} GPUs, one ncclAllReduce(min) per file-order "
-                         "window, all-gather of the shards (exact: same counters as 1 GPU); pass 2: read classification sharded by "
-                         "reads (all-gather), the rest replicated"
-                         if args.gpus > 1 else "1 GPU")}
+         "parallelism": parallelism(args.gpus)}
     if extra:
         c.update(extra)
     return c
@@ -378,19 +392,20 @@ def main():
     peak, peak_src = peaks()
     launch_ms = ist.ms_commit / max(1, ist.commit_launches)
     slots_per_launch = ist.commit_slots / max(1, ist.commit_launches)
-    # at N > 1 each rank moves 1/N of the counter sectors of every slot it evaluates
-    alg_per_slot = (64 * H) / world + L / (L - K + 1)
+    # sharded insert: each rank moves 1/N of the counter sectors of every slot it evaluates; replicated insert: all of them
+    sharded = insert_sharded(world)
+    alg_per_slot = (64 * H) / (world if sharded else 1) + L / (L - K + 1)
     achieved = alg_per_slot * slots_per_launch / (launch_ms * 1e-3) / 1e9 if launch_ms > 0 else 0.0
     phase_ms = ist.ms_pass1
     phase_achieved = alg_per_slot * nk / (phase_ms * 1e-3) / 1e9
-    kernel = "k_insert_windows (persistent ordered counting-Bloom min-increment)" if world == 1 else \
+    kernel = "k_insert_windows (persistent ordered counting-Bloom min-increment)" if not sharded else \
         "k_sh_gather + ncclAllReduce(min) + k_sh_apply (one file-order window, counters sharded by position)"
     roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": NCU_TRAFFIC_PER_SLOT * slots_per_launch if NCU_TRAFFIC_PER_SLOT else None,
                 "peak_source": peak_src, "alg_bytes_per_kmer": alg_per_slot, "launches": int(ist.commit_launches),
                 "slots_per_launch": slots_per_launch, "avg_launch_ms": launch_ms, "share_of_step": ist.ms_commit / ms_step,
                 "insert_phase": {"ms": phase_ms, "achieved": phase_achieved, "frac": phase_achieved / peak,
-                                 "what": "hash + ordered insert + drains" + (" + all-gather of the shards" if world > 1 else "")}}
+                                 "what": "hash + ordered insert + drains" + (" + all-gather of the shards" if sharded else "")}}
 
     cpu = None
     if not args.no_cpu_baseline and os.path.exists(REF_BIN) and world == 1:
