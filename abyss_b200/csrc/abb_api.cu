@@ -380,13 +380,18 @@ int launch_hash(abb_filter* f, unsigned k, const uint8_t* d_care, const uint8_t*
 	cudaGetDevice(&dev);
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 	const unsigned grid = (unsigned)std::min<uint64_t>((n + kHashWarps - 1) / kHashWarps, (uint64_t)sms * 32);
-	static int tma = -1; // ABB_TMA=0: K1 without the bulk-copy staging (tuning / fallback)
-	if (tma < 0) {
+	// ABB_TMA=0: K1 without the bulk-copy staging (tuning / fallback).  The opt-in to 56 KB of shared memory is a per-device
+	// attribute of the kernel: a process that drives several GPUs (abyss-bloom-dbg --devices) sets it on each of them.
+	static int tma_env = -1;
+	static int tma_dev[64] = { 0 }; // 0 = not tried on this device, 1 = usable, -1 = not usable
+	if (tma_env < 0) {
 		const char* e = getenv("ABB_TMA");
-		tma = e ? atoi(e) : 1;
-		if (tma)
-			tma = cudaFuncSetAttribute(k_hash_reads_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kTmaStage) == cudaSuccess ? 1 : 0;
+		tma_env = e ? atoi(e) : 1;
 	}
+	int& tma_here = tma_dev[dev & 63];
+	if (tma_env && tma_here == 0)
+		tma_here = cudaFuncSetAttribute(k_hash_reads_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kTmaStage) == cudaSuccess ? 1 : -1;
+	const bool tma = tma_env && tma_here == 1;
 	if (d_care)
 		k_hash_reads_masked<<<grid, kHashWarps * 32, 0, stream>>>(d_bases, d_offs + r0, d_slot_offs + r0, slot_base, n, k, d_care,
 		                                                          d_h0, d_valid);
