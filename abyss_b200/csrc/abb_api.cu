@@ -1035,10 +1035,28 @@ int abb_insert_reads(abb_filter* f, const char* bases, const uint64_t* offsets, 
 	return rc;
 }
 
+/** true: the counters are sharded over the ranks; false: every rank runs the whole insert (see abb_insert_reads_sharded_dev) */
+static bool shard_policy(int world)
+{
+	static int min_world = -1;
+	if (min_world < 0) {
+		const char* e = getenv("ABB_SHARD_MIN_WORLD");
+		min_world = e ? std::max(2, atoi(e)) : 4;
+	}
+	return world > 1 && world >= min_world;
+}
+
 int abb_insert_reads_sharded(abb_filter* f, abb_comm* c, const char* bases, const uint64_t* offsets, uint64_t n_reads, int finalize,
                              uint64_t* n_kmers_out)
 {
 	ABB_REQUIRE(f && c, "NULL argument");
+	if (!shard_policy(c->world)) { // replicated insert: the single-GPU host path, with its copy hidden behind the insert
+		ABB_REQUIRE(f->kind == ABB_COUNTING, "the sharded insert is implemented for counting filters");
+		ABB_REQUIRE(f->device == c->device, "filter and communicator live on different devices");
+		f->replicated_insert = true;
+		(void)finalize; // nothing to all-gather: every rank holds the whole filter
+		return abb_insert_reads(f, bases, offsets, n_reads, n_kmers_out);
+	}
 	if (n_kmers_out)
 		*n_kmers_out = 0;
 	ABB_REQUIRE(n_reads == 0 || (bases && offsets), "NULL read buffers");
@@ -1236,12 +1254,7 @@ int abb_insert_reads_sharded_dev(abb_filter* f, abb_comm* c, const char* d_bases
 	// lane and pays a collective per window; measured on B200 it beats one GPU only from 4 ranks on (pass 1 of the bench job:
 	// 2.17 s on 1 GPU, 2.81 s sharded over 2, 1.78 s over 4).  Below ABB_SHARD_MIN_WORLD ranks (default 4) every rank
 	// therefore runs the whole insert itself -- same bytes, no communication -- and only pass 2 is divided.
-	static int min_world = -1;
-	if (min_world < 0) {
-		const char* e = getenv("ABB_SHARD_MIN_WORLD");
-		min_world = e ? std::max(2, atoi(e)) : 4;
-	}
-	const bool shard = c->world > 1 && c->world >= min_world;
+	const bool shard = shard_policy(c->world);
 	f->replicated_insert = !shard;
 	ABB_CHECK(insert_reads_dev(f, (const uint8_t*)d_bases, d_offsets, n_reads, n_kmers_out, shard ? c : nullptr));
 	if (finalize)
