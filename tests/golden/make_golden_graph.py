@@ -14,13 +14,28 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
-from abyss_b200.synth import ReadSet  # noqa: E402
+from abyss_b200.synth import ReadSet, edge_mutate  # noqa: E402
 
 DBG = os.path.join(ROOT, "oracle", "_ref", "abyss-bloom-dbg-ref")
 CASES = [
     dict(name="graph_g2k_k21", seed=31, genome=2000, cov=20, L=80, err=0.01, k=21, kc=2, b="64k", H=3),
     dict(name="graph_g10k_k25", seed=23, genome=10000, cov=25, L=100, err=0.01, k=25, kc=2, b="1M", H=3),
+    # reads with 'N' (the trimmed read is the longest run of solid k-mers, a gap in the k-mer positions ends a run), lower-case
+    # ends (removed by the reader) and reads shorter than k
+    dict(name="graph_edge_k21", seed=33, genome=3000, cov=25, L=80, err=0.01, k=21, kc=2, b="256k", H=3, edge=True),
 ]
+
+
+def write_reads(c, path):
+    """the reads of a case as FASTQ (shared with the tests)"""
+    rs = ReadSet.from_coverage(c["seed"], c["genome"], c["cov"], c["L"], c["err"])
+    if not c.get("edge"):
+        rs.write_fastq(path)
+        return
+    seqs = edge_mutate([a.tobytes().decode() for a in rs.ascii(0, rs.n)], every_n=5, every_lc=7, every_short=11)
+    with open(path, "w") as f:
+        for i, s in enumerate(seqs):
+            f.write(f"@{rs.read_id(i)}\n{s}\n+\n{'I' * len(s)}\n")
 
 
 def counters_for_budget(b):
@@ -35,9 +50,8 @@ def main():
     os.makedirs(tmp, exist_ok=True)
     out = []
     for c in CASES:
-        rs = ReadSet.from_coverage(c["seed"], c["genome"], c["cov"], c["L"], c["err"])
         fq = os.path.join(tmp, c["name"] + ".fq")
-        rs.write_fastq(fq)
+        write_reads(c, fq)
         dot = os.path.join(tmp, c["name"] + ".dot")
         cmd = f"ulimit -s 65536; {DBG} -k{c['k']} --kc={c['kc']} -b{c['b']} -H{c['H']} -j1 -g {dot} {fq} > /dev/null"
         subprocess.run(["bash", "-c", cmd], check=True)

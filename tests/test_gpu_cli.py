@@ -178,10 +178,12 @@ def test_graphviz_dump(tmp_path, abb):
     # traversal order is the reference's, the Bloom lookups are GPU batches (abb_contains_reads, abb_successors); goldens from
     # the unmodified reference (make_golden_graph.py)
     import gzip
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from make_golden_graph import write_reads
     for c in json.load(open(os.path.join(ROOT, "tests", "golden", "graph_cases.json"))):
-        rs = ReadSet.from_coverage(c["seed"], c["genome"], c["cov"], c["L"], c["err"])
         fq = str(tmp_path / (c["name"] + ".fq"))
-        rs.write_fastq(fq)
+        write_reads(c, fq)
         dot = str(tmp_path / (c["name"] + ".dot"))
         r = subprocess.run([os.path.join(BIN, "abyss-bloom-dbg"), f"-k{c['k']}", f"--kc={c['kc']}", f"-b{c['b']}", f"-H{c['H']}", "-g", dot,
                             "--batch-reads=700", "-o", os.devnull, fq], capture_output=True, text=True)

@@ -9,7 +9,10 @@ import subprocess
 
 import pytest
 
-from abyss_b200.synth import ReadSet
+import sys
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+from make_golden_graph import write_reads  # noqa: E402
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = os.path.join(ROOT, "tests", "golden")
@@ -27,9 +30,8 @@ def harness(tmp_path_factory):
 @pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
 def test_graph_dump(harness, tmp_path, case):
     c = case
-    rs = ReadSet.from_coverage(c["seed"], c["genome"], c["cov"], c["L"], c["err"])
     fq = str(tmp_path / "r.fq")
-    rs.write_fastq(fq)
+    write_reads(c, fq)
     r = subprocess.run([harness, str(c["k"]), str(c["kc"]), str(c["H"]), str(c["counters"]), fq], capture_output=True)
     assert r.returncode == 0, r.stderr.decode()
     assert len(r.stdout) == c["bytes"] and r.stdout.count(b"\n") == c["lines"]
