@@ -71,3 +71,28 @@ def test_errors(harness, tmp_path):
     assert r.returncode != 0 and "duplicate ID" in r.stderr
     r = subprocess.run([harness, fa], capture_output=True, text=True)
     assert r.returncode != 0 and "missing -k,--kmer option" in r.stderr
+
+
+DBG_REF = os.path.join(ROOT, "oracle", "_ref", "abyss-bloom-dbg-ref")
+
+
+@pytest.mark.skipif(not (os.path.exists(REF) and os.path.exists(DBG_REF)), reason="oracle/_ref not built")
+@pytest.mark.parametrize("k,m,fmt", [(32, 0, "--adj"), (32, 20, "--dot"), (48, 30, "--gfa1"), (64, 50, "--gfa2"), (96, 50, "--sam"), (40, 25, "--asqg")])
+def test_real_unitig_sets(harness, tmp_path, k, m, fmt):
+    # the pipeline of bin/abyss-pe on config 1 (53 333 x 150 bp reads of a 200 kbp genome): the reference's own
+    # unitig FASTA (tips, branches, blunt ends from coverage gaps) into both AdjList implementations
+    from abyss_b200.synth import ReadSet
+    rs = ReadSet(1, 200000, 53333, 150, 0.005)
+    fq = str(tmp_path / "r.fq")
+    rs.write_fastq(fq)
+    fa = str(tmp_path / "unitigs-1.fa")
+    subprocess.run(["bash", "-c", f"ulimit -s 65536; {DBG_REF} -k{k} --kc=2 -b64M -H4 -j1 {fq} > {fa} 2>/dev/null"], check=True)
+    n = sum(1 for line in open(fa) if line.startswith(">"))
+    assert n > 300
+    args = [f"-k{k}", f"-m{m}", fmt, fa]
+    a = subprocess.run([REF] + args, capture_output=True)
+    assert a.returncode == 0, a.stderr.decode()
+    b = subprocess.run([harness] + args, capture_output=True)
+    assert b.returncode == 0, b.stderr.decode()
+    assert oc.normalise(a.stdout, REF) == oc.normalise(b.stdout, harness)
+    assert len(a.stdout) > 20 * n
