@@ -53,9 +53,10 @@ def fasta(n, seed):
     return "".join(out)
 
 
+@pytest.mark.parametrize("mapped", [True, False])  # regular files parsed in place from a memory mapping / read through a buffer
 @pytest.mark.parametrize("piece", [64, 1000, 1 << 16])
 @pytest.mark.parametrize("threads", [1, 3])
-def test_stream_equals_serial(exe, tmp_path, piece, threads):
+def test_stream_equals_serial(exe, tmp_path, piece, threads, mapped):
     files = {}
     files["a.fq"] = fastq(3000, 1)
     files["b.fq"] = fastq(1500, 2, crlf=True, casava=True)
@@ -74,7 +75,7 @@ def test_stream_equals_serial(exe, tmp_path, piece, threads):
     paths.append(str(gz))
     want, _ = run(exe, "serial", *paths)
     assert want.count("\n") > 5000
-    got, batches = run(exe, "stream", threads, 997, piece, *paths)
+    got, batches = run(exe, "stream", threads, 997, piece, *paths, env=None if mapped else {"ABB_NO_MMAP": "1"})
     assert got == want
     assert all(b == 997 for b in batches[:-1]) and 0 < batches[-1] <= 997 and sum(batches) == want.count("\n")
 
@@ -218,4 +219,24 @@ def test_sam_qseq_export_equal_reference_reader(exe, tmp_path, opts):
     assert serial == ref.stdout
     got, _ = run(exe, "stream", 3, 250, 4096, *paths, env=env)
     assert got == ref.stdout
+    got, _ = run(exe, "stream", 3, 250, 4096, *paths, env=dict(env, ABB_NO_MMAP="1"))
+    assert got == ref.stdout
     assert ref.stdout.count("\n") > 1500
+
+
+@pytest.mark.parametrize("mapped", [True, False])
+def test_error_line_number_in_a_later_piece(exe, tmp_path, mapped):
+    # a broken record far into the file: the message names the line of the file (FastaReader::die, FastaReader.cpp:52-58) although
+    # the piece that holds it was parsed on its own (mapped pieces count the lines before them only when a message is printed)
+    lines = fastq(400, 31).split("\n")
+    bad = 4 * 300 + 2          # the '+' line of record 300 (0-based line index)
+    assert lines[bad] == "+"
+    lines[bad] = "-"
+    p = tmp_path / "bad.fq"
+    p.write_text("\n".join(lines))
+    env = dict(os.environ, **({} if mapped else {"ABB_NO_MMAP": "1"}))
+    r = subprocess.run([exe, "stream", "3", "100", "2000", str(p)], capture_output=True, text=True, env=env)
+    assert r.returncode != 0
+    assert f"bad.fq:{bad}: error: expected `+' and saw `-'" in r.stderr, r.stderr
+    r = subprocess.run([exe, "serial", str(p)], capture_output=True, text=True)
+    assert f"bad.fq:{bad}: error: expected `+' and saw `-'" in r.stderr, r.stderr
