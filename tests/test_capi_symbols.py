@@ -43,3 +43,35 @@ def test_no_cpu_fallback(abb):
         assert e.code == abb.ABB_ENODEV
     else:
         raise AssertionError("hash_reads must fail without a CUDA device")
+
+
+def test_header_is_plain_c(tmp_path):
+    # the boundary is a C ABI: include/abyss_b200.h compiles as C99 (no C++, no torch or CUDA types) and a C program links against
+    # the library using nothing but that header
+    import subprocess
+    src = tmp_path / "use_abi.c"
+    src.write_text(
+        '#include "abyss_b200.h"\n'
+        "#include <stdio.h>\n"
+        "int main(void) {\n"
+        "    abb_filter* f = NULL; abb_overlap* o = NULL; abb_succ_info s; abb_overlap_edge e; abb_assembly_params p = {0, 0, 0, 0};\n"
+        "    (void)s; (void)e; (void)p;\n"
+        "    printf(\"%d\\n\", abb_version());\n"
+        "    if (abb_device_count() <= 0) {\n"
+        "        int rc = abb_filter_create(&f, ABB_COUNTING, 1024, 4, 20, 2, \"\", 0);\n"
+        "        int rc2 = abb_overlap_create(&o, 0);\n"
+        "        printf(\"%d %d %s\\n\", rc, rc2, abb_last_error());\n"
+        "    }\n"
+        "    return 0;\n"
+        "}\n")
+    exe = tmp_path / "use_abi"
+    lib = os.path.join(ROOT, "abyss_b200", "lib")
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), "-o", str(exe), str(src),
+                    "-L" + lib, "-labyssb200", "-Wl,-rpath," + lib], check=True, capture_output=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.split("\n")
+    assert lines[0] == "100"
+    import torch
+    if not torch.cuda.is_available():
+        assert lines[1].startswith("-2 -2 ") and "no CPU fallback" in lines[1]  # ABB_ENODEV from both entry points
