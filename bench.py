@@ -64,6 +64,31 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def pass2_rooflines(phases_ms, solid_reads, bases_assembled, peak, world=1):
+    """HBM rooflines of the two pass-2 kernels that probe the 7.6 GB filter at random (32-byte sectors).
+    k_classify: a solid read costs (L-k+1) * H sectors for the solid test plus 2 * 5 * 4 * H for the two depth-5 blunt-end
+    look-aheads (reads that fail early are counted as zero: a lower bound); the phase also holds the re-hash of the reads.
+    k_make_tiles: every graph vertex lies on 4 tiles (2 orientations x 2 directions) and a tile step probes the 8 neighbours
+    with H functions (8 * H sectors).  Both stages are divided over the ranks at N > 1."""
+    out = []
+    try:
+        per_solid = (L - K + 1) * H * 32 + 2 * 5 * 4 * H * 32
+        specs = (("k_classify (solid test + blunt-end look-ahead per read; phase incl. the re-hash of the reads)", "classify",
+                  solid_reads * per_solid / world, f"solid_reads x ({L - K + 1} x H + 40 x H) x 32 B"),
+                 ("k_make_tiles (marker-to-marker walks: 8 neighbours x H probes per vertex step)", "tiles",
+                  4 * bases_assembled * 8 * H * 32 / world, "4 x graph vertices x 8 x H x 32 B"))
+        for name, phase, nbytes, formula in specs:
+            ms = float(phases_ms.get(phase, 0.0))
+            if ms <= 0 or nbytes <= 0:
+                continue
+            achieved = nbytes / (ms * 1e-3) / 1e9
+            out.append({"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                        "alg_bytes": nbytes, "alg_bytes_formula": formula, "phase_ms": ms})
+    except Exception as e:  # never let a derived figure break the bench line
+        out.append({"error": repr(e)})
+    return out
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
 
@@ -418,7 +443,10 @@ def main():
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": workload_config(args), "clocks": clk.summary(), "e2e": e2e,
-        "gpu_launches": int(ist.launches + ast.launches), "roofline": roofline, "cpu_baseline": cpu,
+        "gpu_launches": int(ist.launches + ast.launches), "roofline": roofline,
+        "roofline_pass2": pass2_rooflines({"classify": ast.ms_classify, "tiles": ast.ms_tiles}, int(cnt.solid_reads), int(cnt.bases_assembled),
+                                          peak, world),
+        "cpu_baseline": cpu,
         "phases_ms": {"hash": ist.ms_hash, "insert": ist.ms_insert, "classify": ast.ms_classify, "visited": ast.ms_visited,
                       "tiles": ast.ms_tiles, "extend": ast.ms_extend, "extend_walk": ast.ms_walk, "extend_stage": ast.ms_stage,
                       "extend_repeat_check": ast.ms_repeat, "replay": ast.ms_replay, "pass2_wall": ast.ms_total,

@@ -75,3 +75,20 @@ def test_header_is_plain_c(tmp_path):
     import torch
     if not torch.cuda.is_available():
         assert lines[1].startswith("-2 -2 ") and "no CPU fallback" in lines[1]  # ABB_ENODEV from both entry points
+
+
+def test_bench_derived_rooflines():
+    # bench.py's pass-2 roofline entries are plain arithmetic on counters the run reports: checked here on the numbers of the
+    # committed bench line (profiles/r02_bench_line_1gpu.json), and never allowed to raise
+    import importlib.util
+    import json
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    line = json.loads(open(os.path.join(ROOT, "profiles", "r02_bench_line_1gpu.json")).read().strip().splitlines()[-1])
+    r = bench.pass2_rooflines(line["phases_ms"], 20_000_000, line["bases_assembled"], 6489.9)
+    assert len(r) == 2 and all(0 < x["frac"] < 1 for x in r)
+    tiles = [x for x in r if x["kernel"].startswith("k_make_tiles")][0]
+    assert abs(tiles["alg_bytes"] - 4 * line["bases_assembled"] * 1024) < 1
+    assert bench.pass2_rooflines({}, 0, 0, 6489.9) == []
+    assert "error" in bench.pass2_rooflines(None, 1, 1, 1.0)[0]
