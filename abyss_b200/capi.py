@@ -542,3 +542,35 @@ def bloom_dbg(read_ids, seqs_or_arrays, k: int, kc: int = 2, num_hashes: int = 4
     a.close()
     f.close()
     return "".join(out), (np.concatenate(codes) if codes else np.zeros(0, dtype=np.uint8))
+
+
+def overlap_graph(seqs_or_arrays, k: int, min_overlap: int = 50, ss: bool = False, device: int = 0):
+    """AdjList -k K -m M [--SS] (AdjList/AdjList.cpp:140-291) on one GPU: the edges of the contig overlap graph as a list of
+    (u, v, distance) with u, v = 2 * contig + sense (ContigNode), in the order the reference's graph iterates them."""
+    lib = load()
+    bases, offs = seqs_or_arrays if isinstance(seqs_or_arrays, tuple) else pack_reads(seqs_or_arrays)
+    h = _vp()
+    check(lib.abb_overlap_create(C.byref(h), device))
+    try:
+        e = C.POINTER(OverlapEdge)()
+        n = C.c_uint64(0)
+        check(lib.abb_overlap_build(h, _ptr(bases), _ptr(offs), len(offs) - 1, k, min_overlap, int(ss), C.byref(e), C.byref(n)))
+        return [(e[i].u, e[i].v, e[i].distance) for i in range(n.value)]
+    finally:
+        lib.abb_overlap_destroy(h)
+
+
+def successors(filt: "Filter", kmers, max_chain: int = 1):
+    """out-edges of graph vertices (RollingBloomDBG out_edge_iterator; abb_successors): for every k-mer a list of
+    (mask, [hash_A, hash_C, hash_G, hash_T]) per chain vertex, and the canonical hash of the k-mer itself."""
+    lib = load()
+    ks = [s.encode() if isinstance(s, str) else bytes(s) for s in kmers]
+    n = len(ks)
+    info = (SuccInfo * (n * max_chain))()
+    ln = (C.c_uint * n)()
+    self_h = (C.c_uint64 * n)()
+    check(lib.abb_successors(filt.handle, b"".join(ks), n, max_chain, info, ln, self_h))
+    out = []
+    for i in range(n):
+        out.append(([(info[i * max_chain + s].mask, list(info[i * max_chain + s].hash)) for s in range(ln[i])], self_h[i]))
+    return out
