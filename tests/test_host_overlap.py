@@ -96,3 +96,21 @@ def test_real_unitig_sets(harness, tmp_path, k, m, fmt):
     assert b.returncode == 0, b.stderr.decode()
     assert oc.normalise(a.stdout, REF) == oc.normalise(b.stdout, harness)
     assert len(a.stdout) > 0
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/AdjList-ref not built")
+def test_option_aliases_and_stdin(harness, tmp_path):
+    # --gv = --dot, --gfa = --gfa1, -m0 = k-1, long options, several input files, contigs on standard input
+    c = oc.tiled_case(21, 20000, 31, 20)
+    half = len(c["records"]) // 2
+    a_fa, b_fa = str(tmp_path / "a.fa"), str(tmp_path / "b.fa")
+    oc.write_fasta(dict(c, records=c["records"][:half]), a_fa)
+    oc.write_fasta(dict(c, records=c["records"][half:]), b_fa)
+    both = open(a_fa).read() + open(b_fa).read()
+    for args, stdin in ((["--kmer=31", "--min-overlap=20", "--gv", a_fa, b_fa], None), (["-k31", "-m0", "--gfa", a_fa, b_fa], None),
+                        (["-k", "31", "-m", "25", "--SS", "--adj"], both), (["-k31", "--no-SS", "--asqg", "-"], both)):
+        ref = subprocess.run([REF] + args, input=stdin, capture_output=True, text=True)
+        assert ref.returncode == 0, ref.stderr
+        got = subprocess.run([harness] + args, input=stdin, capture_output=True, text=True)
+        assert got.returncode == 0, got.stderr
+        assert got.stdout == ref.stdout, args
